@@ -1,0 +1,206 @@
+/* fb_math.h -- the arithmetic specification of the fbgnn hot path.
+ *
+ * Every floating-point step of the decoder (quaternary BP, binary BP, feedback GNN) is
+ * written in terms of the functions below.  They use only IEEE-754 binary32 operations
+ * with a fixed evaluation order (add, mul, fma, div, integer bit manipulation), so the
+ * same source gives bit-identical results on the host (gcc, -ffp-contract=off) and on
+ * the device (nvcc, explicit __f*_rn intrinsics which are never contracted).  That is
+ * what lets the CUDA kernels be compared BIT-EXACTLY with the CPU oracle instead of
+ * within a tolerance that BP's chaotic dynamics would blow through.
+ *
+ * The formulas restate the TensorFlow ops the reference calls:
+ *   tf.math.softplus        decoding_q.py:265,270,373,458,462   (Eigen softplus functor:
+ *                           x > 13.942385 -> x ; x < -13.942385 -> exp(x) ; else log1p(exp(x)))
+ *   tf.reduce_logsumexp     decoding_q.py:266,271,459,463       (max-shifted, log not log1p)
+ *   _phi (quaternary)       decoding_q.py:365-373
+ *   _phi (binary)           decoding.py:625-633
+ *   tanh activation         gnn.py:55-58 (Keras Dense(..., "tanh"))
+ * exp/log/tanh themselves are polynomial / rational approximations accurate to about
+ * 1-2 ulp (measured in tests/test_math.py against float64).
+ *
+ * This header is plain C99 / CUDA C++ and has no dependencies.
+ */
+#ifndef FBGNN_FB_MATH_H
+#define FBGNN_FB_MATH_H
+
+#include <stdint.h>
+
+#if defined(__CUDA_ARCH__)
+#  define FB_HD __host__ __device__ __forceinline__
+#  define FB_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#  define FB_ADD(a, b)    __fadd_rn((a), (b))
+#  define FB_SUB(a, b)    __fsub_rn((a), (b))
+#  define FB_MUL(a, b)    __fmul_rn((a), (b))
+#  define FB_DIV(a, b)    __fdiv_rn((a), (b))
+#  define FB_F2I(f)       __float_as_int(f)
+#  define FB_I2F(i)       __int_as_float(i)
+#  define FB_FMAX(a, b)   fmaxf((a), (b))
+#  define FB_FMIN(a, b)   fminf((a), (b))
+#else
+#  include <math.h>
+#  include <string.h>
+#  if defined(__CUDACC__)
+#    define FB_HD __host__ __device__ inline
+#  else
+#    define FB_HD static inline
+#  endif
+#  define FB_FMA(a, b, c) fmaf((a), (b), (c))
+#  define FB_ADD(a, b)    ((float)((float)(a) + (float)(b)))
+#  define FB_SUB(a, b)    ((float)((float)(a) - (float)(b)))
+#  define FB_MUL(a, b)    ((float)((float)(a) * (float)(b)))
+#  define FB_DIV(a, b)    ((float)((float)(a) / (float)(b)))
+static inline int32_t fb_f2i_(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
+static inline float fb_i2f_(int32_t i) { float f; memcpy(&f, &i, 4); return f; }
+#  define FB_F2I(f)       fb_f2i_(f)
+#  define FB_I2F(i)       fb_i2f_(i)
+/* operands are never NaN on the decoder path; ties (+0/-0) do not occur with a<b tests */
+#  define FB_FMAX(a, b)   (((a) < (b)) ? (b) : (a))
+#  define FB_FMIN(a, b)   (((b) < (a)) ? (b) : (a))
+#endif
+
+/* ---- constants of the reference ------------------------------------------------- */
+#define FB_PHI_CLIP_LO   8.5e-8f          /* decoding_q.py:372, decoding.py:632 */
+#define FB_PHI_CLIP_HI   16.635532f
+#define FB_SOFTPLUS_THR  13.942385f       /* -(log(FLT_EPSILON) + 2), Eigen softplus */
+#define FB_LLR_MAX       20.0f            /* decoding_q.py:51, decoding.py:320 */
+#define FB_ATANH_CLIP    0.9999999f       /* 1 - 1e-7 in float32, decoding_q.py:49 */
+
+/* ---- exp ------------------------------------------------------------------------- */
+/* exp(x) for x >= -87.0 (no underflow handling), x <= 88.  Cephes-style: n = rint(x/ln2),
+ * r = x - n*ln2 (two-step), degree-5 polynomial on r^2 plus 1 + r, scaled by 2^n through
+ * the exponent field. */
+FB_HD float fb_expf_core(float x) {
+    const float magic = 12582912.0f;                 /* 1.5 * 2^23 : round-to-nearest-even */
+    float t = FB_FMA(x, 1.44269504088896341f, magic);
+    int32_t n = FB_F2I(t) - 0x4B400000;
+    float fn = FB_SUB(t, magic);
+    float r = FB_FMA(fn, -0.693359375f, x);
+    r = FB_FMA(fn, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = FB_FMA(p, r, 1.3981999507e-3f);
+    p = FB_FMA(p, r, 8.3334519073e-3f);
+    p = FB_FMA(p, r, 4.1665795894e-2f);
+    p = FB_FMA(p, r, 1.6666665459e-1f);
+    p = FB_FMA(p, r, 5.0000001201e-1f);
+    float r2 = FB_MUL(r, r);
+    p = FB_FMA(p, r2, r);
+    p = FB_ADD(p, 1.0f);
+    return FB_I2F(FB_F2I(p) + (int32_t)((uint32_t)n << 23));
+}
+
+/* exp(x) for any finite x <= 88: results below 2^-126 are flushed to +0. */
+FB_HD float fb_expf(float x) {
+    float xc = FB_FMAX(x, -87.0f);
+    float e = fb_expf_core(xc);
+    return (x < -87.0f) ? 0.0f : e;
+}
+
+/* ---- log ------------------------------------------------------------------------- */
+/* log(x) for positive normal x.  Cephes-style: x = m * 2^e with m in [sqrt(1/2), sqrt(2)),
+ * f = m - 1, log(1+f) = f - f^2/2 + f^3 P(f), plus e*ln2 split in two parts. */
+FB_HD float fb_logf(float x) {
+    int32_t ix = FB_F2I(x);
+    int32_t e = (ix - 0x3f3504f3) >> 23;              /* arithmetic shift */
+    float m = FB_I2F(ix - (int32_t)((uint32_t)e << 23));
+    float fe = (float)e;
+    float f = FB_SUB(m, 1.0f);
+    float z = FB_MUL(f, f);
+    float p = 7.0376836292e-2f;
+    p = FB_FMA(p, f, -1.1514610310e-1f);
+    p = FB_FMA(p, f, 1.1676998740e-1f);
+    p = FB_FMA(p, f, -1.2420140846e-1f);
+    p = FB_FMA(p, f, 1.4249322787e-1f);
+    p = FB_FMA(p, f, -1.6668057665e-1f);
+    p = FB_FMA(p, f, 2.0000714765e-1f);
+    p = FB_FMA(p, f, -2.4999993993e-1f);
+    p = FB_FMA(p, f, 3.3333331174e-1f);
+    float y = FB_MUL(FB_MUL(p, f), z);                /* f^3 P(f) */
+    y = FB_FMA(fe, -2.12194440e-4f, y);
+    y = FB_FMA(z, -0.5f, y);
+    float r = FB_ADD(f, y);
+    return FB_FMA(fe, 0.693359375f, r);
+}
+
+/* crude reciprocal (relative error < 1e-3) used only to scale a half-ulp correction */
+FB_HD float fb_rcp_crude(float u) {
+    float y = FB_I2F(0x7EF311C7 - FB_F2I(u));
+    float t = FB_FMA(-u, y, 2.0f);
+    y = FB_MUL(y, t);
+    t = FB_FMA(-u, y, 2.0f);
+    return FB_MUL(y, t);
+}
+
+/* log1p(e) for e > 0 : log(u) + c/u with u = fl(1+e), c = the rounding error of that sum */
+FB_HD float fb_log1pf_pos(float e) {
+    float u = FB_ADD(1.0f, e);
+    float hi = FB_FMAX(e, 1.0f);
+    float lo = FB_FMIN(e, 1.0f);
+    float c = FB_SUB(lo, FB_SUB(u, hi));              /* Fast2Sum error term (exact) */
+    float l = fb_logf(u);
+    return FB_FMA(c, fb_rcp_crude(u), l);
+}
+
+/* ---- TensorFlow composites ------------------------------------------------------- */
+/* tf.math.softplus */
+FB_HD float fb_softplusf(float x) {
+    float e = fb_expf(x > FB_SOFTPLUS_THR ? 0.0f : x);
+    if (x > FB_SOFTPLUS_THR) return x;
+    if (x < -FB_SOFTPLUS_THR) return e;
+    return fb_log1pf_pos(e);
+}
+
+/* tf.reduce_logsumexp over the two values (a, b); both finite. */
+FB_HD float fb_logaddexpf(float a, float b) {
+    float mx = FB_FMAX(a, b);
+    float mn = FB_FMIN(a, b);
+    float t = fb_expf(FB_SUB(mn, mx));                /* the larger term is exp(0) = 1 */
+    float s = FB_ADD(1.0f, t);
+    return FB_ADD(fb_logf(s), mx);
+}
+
+/* quaternary decoder phi, decoding_q.py:365-373: softplus(x) - log(exp(x) - 1) after clipping */
+FB_HD float fb_phi4f(float x) {
+    x = FB_FMIN(FB_FMAX(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI);
+    float e = fb_expf_core(x);
+    float sp = (x > FB_SOFTPLUS_THR) ? x : fb_log1pf_pos(e);
+    return FB_SUB(sp, fb_logf(FB_SUB(e, 1.0f)));
+}
+
+/* binary decoder phi, decoding.py:625-633: log(exp(x) + 1) - log(exp(x) - 1) after clipping */
+FB_HD float fb_phi2f(float x) {
+    x = FB_FMIN(FB_FMAX(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI);
+    float e = fb_expf_core(x);
+    return FB_SUB(fb_logf(FB_ADD(e, 1.0f)), fb_logf(FB_SUB(e, 1.0f)));
+}
+
+/* tanh: rational approximation x*P(x^2)/Q(x^2) on the clamped argument (the scheme Eigen's
+ * float tanh, i.e. the TF CPU kernel, uses). */
+FB_HD float fb_tanhf(float x) {
+    float xc = FB_FMIN(FB_FMAX(x, -7.90531110763549805f), 7.90531110763549805f);
+    float x2 = FB_MUL(xc, xc);
+    float p = -2.76076847742355e-16f;
+    p = FB_FMA(p, x2, 2.00018790482477e-13f);
+    p = FB_FMA(p, x2, -8.60467152213735e-11f);
+    p = FB_FMA(p, x2, 5.12229709037114e-08f);
+    p = FB_FMA(p, x2, 1.48572235717979e-05f);
+    p = FB_FMA(p, x2, 6.37261928875436e-04f);
+    p = FB_FMA(p, x2, 4.89352455891786e-03f);
+    p = FB_MUL(p, xc);
+    float q = 1.19825839466702e-06f;
+    q = FB_FMA(q, x2, 1.18534705686654e-04f);
+    q = FB_FMA(q, x2, 2.26843463243900e-03f);
+    q = FB_FMA(q, x2, 4.89352518554385e-03f);
+    float r = FB_DIV(p, q);
+    float ax = xc < 0.0f ? -xc : xc;
+    return (ax < 0.0004f) ? xc : r;
+}
+
+/* atanh for |x| <= 1 - 1e-7 (tanh check-node variant, decoding_q.py:356-361):
+ * 0.5 * (log(1 + x) - log(1 - x)) */
+FB_HD float fb_atanhf(float x) {
+    float a = fb_logf(FB_ADD(1.0f, x));
+    float b = fb_logf(FB_SUB(1.0f, x));
+    return FB_MUL(0.5f, FB_SUB(a, b));
+}
+
+#endif /* FBGNN_FB_MATH_H */

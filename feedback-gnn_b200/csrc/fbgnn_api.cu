@@ -1,0 +1,871 @@
+// fbgnn_api.cu -- C ABI (include/fbgnn.h) over the kernels in fbgnn_kernels.cuh.
+// Host-side handle management, graph-table construction, launch configuration and the
+// multi-launch orchestration of the fused Monte-Carlo pipelines.  No CPU compute path:
+// every entry point that does work launches CUDA kernels and fails with FBGNN_E_CUDA when
+// there is no device.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/fbgnn.h"
+#include "fbgnn_kernels.cuh"
+
+using namespace fbgnn;
+
+// ------------------------------------------------------------------ errors -------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                          \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess)                                                            \
+            return fail(FBGNN_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                              \
+    } while (0)
+
+#define REQUIRE(cond, ...)                                   \
+    do {                                                     \
+        if (!(cond)) return fail(FBGNN_E_INVALID, __VA_ARGS__); \
+    } while (0)
+
+// ------------------------------------------------------------------ handles ------------
+struct Workspace {                 // per-context scratch of the fused pipelines
+    int64_t cap_frames = 0;
+    int n = 0, m = 0;
+    uint8_t *vbits = nullptr, *sbits = nullptr, *active[2] = {nullptr, nullptr}, *rounds = nullptr;
+    float *L = nullptr, *P = nullptr, *logit = nullptr;
+    int *list[2] = {nullptr, nullptr};
+    int *list_count = nullptr;     // [2]
+    unsigned long long *counters = nullptr;   // [4]
+    void *hard = nullptr;          // binary pipeline: unused (decisions live in vbits)
+};
+
+struct fbgnn_ctx {
+    int device = 0, num_sms = 0;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int64_t launches = 0;
+    void *flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    char name[256] = {0};
+    Workspace ws;
+};
+
+struct fbgnn_graph {
+    fbgnn_ctx *ctx;
+    SideDev dev;
+    int max_dc = 0, max_dv = 0;
+    bool decodable = true;         // false: only the bit-packed rows exist (dense logical matrices)
+    std::string why_not;
+    std::vector<void *> allocs;
+};
+
+struct fbgnn_code {
+    fbgnn_ctx *ctx;
+    fbgnn_graph *X, *Z;
+    int kx = 0, kz = 0, W = 0;
+    uint32_t *lx_bits = nullptr, *lz_bits = nullptr;
+};
+
+struct fbgnn_gnn {
+    fbgnn_ctx *ctx;
+    int H, M, act, reduce, use_bias;
+    float *weights = nullptr;      // packed GnnLayout<H,M>
+    int total = 0;
+};
+
+static int set_device(fbgnn_ctx *ctx) {
+    CK(cudaSetDevice(ctx->device));
+    return 0;
+}
+
+static int need_decodable(const fbgnn_graph *g) {
+    if (!g->decodable) return fail(FBGNN_E_UNSUPPORTED, "%s", g->why_not.c_str());
+    return 0;
+}
+
+template <typename T> static View2<T> v2(const fbgnn_tensor2 &t) { return View2<T>{(T *)t.ptr, t.s0, t.s1}; }
+template <typename T> static View3<T> v3(const fbgnn_tensor3 &t) { return View3<T>{(T *)t.ptr, t.s0, t.s1, t.s2}; }
+
+// ------------------------------------------------------------------ library / context ---
+extern "C" int fbgnn_version(void) { return FBGNN_VERSION; }
+extern "C" const char *fbgnn_last_error(void) { return g_err.c_str(); }
+
+extern "C" int fbgnn_device_count(int *count) {
+    REQUIRE(count, "count is NULL");
+    CK(cudaGetDeviceCount(count));
+    return 0;
+}
+
+extern "C" int fbgnn_ctx_create(int device, fbgnn_ctx **out) {
+    REQUIRE(out, "ctx is NULL");
+    int count = 0;
+    CK(cudaGetDeviceCount(&count));
+    REQUIRE(device >= 0 && device < count, "device %d out of range (%d devices)", device, count);
+    CK(cudaSetDevice(device));
+    fbgnn_ctx *ctx = new fbgnn_ctx();
+    ctx->device = device;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    snprintf(ctx->name, sizeof ctx->name, "%s", prop.name);
+    CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&ctx->ev0));
+    CK(cudaEventCreate(&ctx->ev1));
+    *out = ctx;
+    return 0;
+}
+
+static void ws_free(Workspace &w) {
+    cudaFree(w.vbits); cudaFree(w.sbits); cudaFree(w.active[0]); cudaFree(w.active[1]);
+    cudaFree(w.rounds); cudaFree(w.L); cudaFree(w.P); cudaFree(w.logit); cudaFree(w.list[0]);
+    cudaFree(w.list[1]); cudaFree(w.list_count); cudaFree(w.counters);
+    w = Workspace();
+}
+
+extern "C" int fbgnn_ctx_destroy(fbgnn_ctx *ctx) {
+    if (!ctx) return 0;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ws_free(ctx->ws);
+    cudaFree(ctx->flush_buf);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return 0;
+}
+
+extern "C" int fbgnn_ctx_sync(fbgnn_ctx *ctx) {
+    REQUIRE(ctx, "ctx is NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+extern "C" int fbgnn_ctx_device(fbgnn_ctx *ctx, int *device, int *num_sms, char *name, int name_len) {
+    REQUIRE(ctx, "ctx is NULL");
+    if (device) *device = ctx->device;
+    if (num_sms) *num_sms = ctx->num_sms;
+    if (name && name_len > 0) snprintf(name, (size_t)name_len, "%s", ctx->name);
+    return 0;
+}
+
+extern "C" int fbgnn_timer_start(fbgnn_ctx *ctx) {
+    REQUIRE(ctx, "ctx is NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    return 0;
+}
+
+extern "C" int fbgnn_timer_stop(fbgnn_ctx *ctx, float *ms) {
+    REQUIRE(ctx && ms, "NULL argument");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(cudaEventSynchronize(ctx->ev1));
+    CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return 0;
+}
+
+extern "C" int fbgnn_launch_count(fbgnn_ctx *ctx, int64_t *launches) {
+    REQUIRE(ctx && launches, "NULL argument");
+    *launches = ctx->launches;
+    return 0;
+}
+
+// ------------------------------------------------------------------ memory --------------
+extern "C" int fbgnn_malloc(fbgnn_ctx *ctx, size_t bytes, void **dptr) {
+    REQUIRE(ctx && dptr, "NULL argument");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
+    if (e == cudaErrorMemoryAllocation) return fail(FBGNN_E_NOMEM, "cudaMalloc(%zu) out of memory", bytes);
+    CK(e);
+    return 0;
+}
+extern "C" int fbgnn_free(fbgnn_ctx *ctx, void *dptr) {
+    REQUIRE(ctx, "ctx is NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(dptr));
+    return 0;
+}
+extern "C" int fbgnn_memset(fbgnn_ctx *ctx, void *dptr, int value, size_t bytes) {
+    REQUIRE(ctx, "ctx is NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    CK(cudaMemsetAsync(dptr, value, bytes, ctx->stream));
+    return 0;
+}
+extern "C" int fbgnn_memcpy_h2d(fbgnn_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    REQUIRE(ctx, "ctx is NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+}
+extern "C" int fbgnn_memcpy_d2h(fbgnn_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    REQUIRE(ctx, "ctx is NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+extern "C" int fbgnn_memcpy_d2d(fbgnn_ctx *ctx, void *dst, const void *src, size_t bytes) {
+    REQUIRE(ctx, "ctx is NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+    return 0;
+}
+extern "C" int fbgnn_host_alloc(size_t bytes, void **hptr) {
+    REQUIRE(hptr, "hptr is NULL");
+    CK(cudaMallocHost(hptr, bytes ? bytes : 1));
+    return 0;
+}
+extern "C" int fbgnn_host_free(void *hptr) {
+    CK(cudaFreeHost(hptr));
+    return 0;
+}
+extern "C" int fbgnn_flush_l2(fbgnn_ctx *ctx) {
+    REQUIRE(ctx, "ctx is NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = (size_t)256 << 20;        // 256 MiB > 126 MB of L2
+        CK(cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+    }
+    k_fill<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>((uint32_t *)ctx->flush_buf,
+                                                      (int64_t)(ctx->flush_bytes / 4), 0u);
+    CK(cudaGetLastError());
+    return 0;
+}
+
+// ------------------------------------------------------------------ graphs --------------
+template <typename T>
+static int upload(fbgnn_graph *g, const std::vector<T> &h, const T **dptr) {
+    void *d = nullptr;
+    CK(cudaMalloc(&d, std::max<size_t>(h.size(), 1) * sizeof(T)));
+    g->allocs.push_back(d);
+    if (!h.empty()) CK(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dptr = (const T *)d;
+    return 0;
+}
+
+static void pack_rows(int32_t n, int32_t m, const int32_t *indptr, const int32_t *indices,
+                      std::vector<uint32_t> &bits) {
+    const int W = (n + 31) / 32;
+    bits.assign((size_t)std::max(m, 0) * W, 0u);
+    for (int r = 0; r < m; r++)
+        for (int k = indptr[r]; k < indptr[r + 1]; k++)
+            bits[(size_t)r * W + (indices[k] >> 5)] ^= 1u << (indices[k] & 31);
+}
+
+static int validate_csr(int32_t n, int32_t m, const int32_t *indptr, const int32_t *indices, const char *what) {
+    REQUIRE(n > 0 && m >= 0, "%s: bad shape (%d x %d)", what, m, n);
+    REQUIRE(indptr && (indices || indptr[m] == 0), "%s: NULL CSR arrays", what);
+    REQUIRE(indptr[0] == 0, "%s: indptr[0] != 0", what);
+    for (int r = 0; r < m; r++) {
+        REQUIRE(indptr[r + 1] >= indptr[r], "%s: indptr not monotone at row %d", what, r);
+        for (int k = indptr[r]; k < indptr[r + 1]; k++) {
+            REQUIRE(indices[k] >= 0 && indices[k] < n, "%s: column index %d out of range in row %d", what, indices[k], r);
+            REQUIRE(k == indptr[r] || indices[k] > indices[k - 1], "%s: row %d not strictly increasing", what, r);
+        }
+    }
+    return 0;
+}
+
+extern "C" int fbgnn_graph_create(fbgnn_ctx *ctx, int32_t n, int32_t m, const int32_t *indptr,
+                                  const int32_t *indices, fbgnn_graph **out) {
+    REQUIRE(ctx && out, "NULL argument");
+    if (int rc = validate_csr(n, m, indptr, indices, "graph")) return rc;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    const int E = indptr[m];
+    fbgnn_graph *g = new fbgnn_graph();
+    g->ctx = ctx;
+    int max_dc = 0, max_dv = 0, min_dc = 1 << 30, min_dv = 1 << 30;
+    for (int c = 0; c < m; c++) {
+        const int dc = indptr[c + 1] - indptr[c];
+        max_dc = std::max(max_dc, dc); min_dc = std::min(min_dc, dc);
+    }
+    char why[256] = {0};
+    if (n > 65535 || m > 65535 || E > 65535)
+        snprintf(why, sizeof why, "matrix too large for the shared-memory resident decoder (n=%d m=%d edges=%d; "
+                 "limit 65535 each)", n, m, E);
+    else if (max_dc > 64)
+        snprintf(why, sizeof why, "check degree %d > 64 is not supported by the decoder", max_dc);
+    g->decodable = why[0] == 0;
+    g->why_not = why;
+    // CN order is the CSR order (sorted by (cn, vn)); VN order = stable counting sort by vn.
+    std::vector<idx_t> cn_ptr, cn_vn, cn_edge, vn_ptr, vn_cn;
+    if (g->decodable) {
+        cn_ptr.resize(m + 1); cn_vn.resize(E); cn_edge.resize(E); vn_ptr.resize(n + 1); vn_cn.resize(E);
+        std::vector<int> deg(n, 0), fill(n, 0);
+        for (int k = 0; k < E; k++) deg[indices[k]]++;
+        int acc = 0;
+        for (int v = 0; v < n; v++) { vn_ptr[v] = (idx_t)acc; fill[v] = acc; acc += deg[v]; }
+        vn_ptr[n] = (idx_t)acc;
+        for (int c = 0; c < m; c++) {
+            cn_ptr[c] = (idx_t)indptr[c];
+            for (int k = indptr[c]; k < indptr[c + 1]; k++) {
+                const int v = indices[k];
+                const int pos = fill[v]++;
+                cn_vn[k] = (idx_t)v;
+                cn_edge[k] = (idx_t)pos;
+                vn_cn[pos] = (idx_t)c;
+            }
+        }
+        cn_ptr[m] = (idx_t)E;
+        for (int v = 0; v < n; v++) { max_dv = std::max(max_dv, deg[v]); min_dv = std::min(min_dv, deg[v]); }
+    }
+    g->max_dc = max_dc; g->max_dv = max_dv;
+    std::vector<uint32_t> bits;
+    pack_rows(n, m, indptr, indices, bits);
+    SideDev &d = g->dev;
+    d.n = n; d.m = m; d.E = E;
+    d.reg_dc = (m > 0 && max_dc == min_dc) ? max_dc : 0;
+    d.reg_dv = (max_dv == min_dv) ? max_dv : 0;
+    int rc = 0;
+    rc |= upload(g, vn_ptr, &d.vn_ptr); rc |= upload(g, vn_cn, &d.vn_cn);
+    rc |= upload(g, cn_ptr, &d.cn_ptr); rc |= upload(g, cn_edge, &d.cn_edge);
+    rc |= upload(g, cn_vn, &d.cn_vn);   rc |= upload(g, bits, &d.bitrows);
+    if (rc) { fbgnn_graph_destroy(g); return FBGNN_E_CUDA; }
+    *out = g;
+    return 0;
+}
+
+extern "C" int fbgnn_graph_destroy(fbgnn_graph *g) {
+    if (!g) return 0;
+    cudaSetDevice(g->ctx->device);
+    for (void *p : g->allocs) cudaFree(p);
+    delete g;
+    return 0;
+}
+
+extern "C" int fbgnn_code_create(fbgnn_ctx *ctx, int32_t n, int32_t m_x, const int32_t *hx_indptr,
+                                 const int32_t *hx_indices, int32_t m_z, const int32_t *hz_indptr,
+                                 const int32_t *hz_indices, int32_t k_x, const int32_t *lx_indptr,
+                                 const int32_t *lx_indices, int32_t k_z, const int32_t *lz_indptr,
+                                 const int32_t *lz_indices, fbgnn_code **out) {
+    REQUIRE(ctx && out, "NULL argument");
+    fbgnn_code *c = new fbgnn_code();
+    c->ctx = ctx;
+    c->X = c->Z = nullptr;
+    int rc = fbgnn_graph_create(ctx, n, m_x, hx_indptr, hx_indices, &c->X);
+    if (!rc) rc = fbgnn_graph_create(ctx, n, m_z, hz_indptr, hz_indices, &c->Z);
+    if (!rc) rc = need_decodable(c->X);
+    if (!rc) rc = need_decodable(c->Z);
+    if (!rc && k_x > 0) rc = validate_csr(n, k_x, lx_indptr, lx_indices, "lx");
+    if (!rc && k_z > 0) rc = validate_csr(n, k_z, lz_indptr, lz_indices, "lz");
+    if (rc) { fbgnn_code_destroy(c); return rc; }
+    c->kx = std::max(k_x, 0); c->kz = std::max(k_z, 0); c->W = (n + 31) / 32;
+    std::vector<uint32_t> bits;
+    if (c->kx) {
+        pack_rows(n, c->kx, lx_indptr, lx_indices, bits);
+        CK(cudaMalloc(&c->lx_bits, bits.size() * 4));
+        CK(cudaMemcpy(c->lx_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    }
+    if (c->kz) {
+        pack_rows(n, c->kz, lz_indptr, lz_indices, bits);
+        CK(cudaMalloc(&c->lz_bits, bits.size() * 4));
+        CK(cudaMemcpy(c->lz_bits, bits.data(), bits.size() * 4, cudaMemcpyHostToDevice));
+    }
+    *out = c;
+    return 0;
+}
+
+extern "C" int fbgnn_code_destroy(fbgnn_code *c) {
+    if (!c) return 0;
+    cudaSetDevice(c->ctx->device);
+    fbgnn_graph_destroy(c->X);
+    fbgnn_graph_destroy(c->Z);
+    cudaFree(c->lx_bits);
+    cudaFree(c->lz_bits);
+    delete c;
+    return 0;
+}
+
+extern "C" int fbgnn_code_edges(fbgnn_code *code, int32_t *e_x, int32_t *e_z) {
+    REQUIRE(code, "code is NULL");
+    if (e_x) *e_x = code->X->dev.E;
+    if (e_z) *e_z = code->Z->dev.E;
+    return 0;
+}
+
+// ------------------------------------------------------------------ launch helpers ------
+// Threads per CTA for the one-frame-per-CTA kernels: the multiple of 32 in [128, 512] that
+// wastes the fewest lanes over the variable-node and check-node passes.
+static int pick_threads(int n_items_a, int n_items_b) {
+    auto eff = [&](int t) {
+        const double pa = (double)((n_items_a + t - 1) / t) * t, pb = (double)((n_items_b + t - 1) / t) * t;
+        return (double)(n_items_a + n_items_b) / (pa + pb);
+    };
+    int best = 256;
+    for (int t = 128; t <= 512; t += 32)
+        if (eff(t) > eff(best) + 0.004) best = t;      // keep 256 unless another size is clearly better
+    return best;
+}
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes, fbgnn_ctx *ctx, const char *what) {
+    if (bytes > ctx->smem_optin)
+        return fail(FBGNN_E_UNSUPPORTED, "%s needs %zu bytes of shared memory per frame, the device offers %zu",
+                    what, bytes, ctx->smem_optin);
+    if (bytes > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return 0;
+}
+
+static size_t bp4_smem(const SideDev &X, const SideDev &Z, bool const_prior) {
+    return sizeof(float) * ((size_t)X.E + Z.E + (const_prior ? 2 : 3) * (size_t)X.n) + X.m + Z.m + X.n + 16;
+}
+
+static int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {
+    if (grid <= 0) return 0;
+    const bool cp = a.llr.ptr == nullptr;
+    const size_t smem = bp4_smem(a.X, a.Z, cp);
+    const int threads = pick_threads(a.X.n, a.X.m + a.Z.m);
+    if (cp) {
+        if (int rc = set_smem(k_bp4<true>, smem, ctx, "quaternary BP")) return rc;
+        k_bp4<true><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+    } else {
+        if (int rc = set_smem(k_bp4<false>, smem, ctx, "quaternary BP")) return rc;
+        k_bp4<false><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+    }
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------ noise sources -------
+extern "C" int fbgnn_pauli_sample(fbgnn_ctx *ctx, int32_t n, int64_t B, const float thr[3], uint64_t seed,
+                                  uint64_t first_frame, fbgnn_tensor2 noise_x, fbgnn_tensor2 noise_z) {
+    REQUIRE(ctx && thr && n > 0 && B >= 0, "bad argument");
+    REQUIRE(noise_x.ptr && noise_z.ptr, "noise outputs are NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    if (B == 0) return 0;
+    SampleArgs a{};
+    a.X.n = n; a.mode = 0;
+    a.thr0 = thr[0]; a.thr1 = thr[1]; a.thr2 = thr[2];
+    a.seed = seed; a.first_frame = first_frame;
+    a.nx_out = v2<uint8_t>(noise_x); a.nz_out = v2<uint8_t>(noise_z);
+    k_sample<<<(unsigned)B, 128, (size_t)n, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+extern "C" int fbgnn_bsc_sample(fbgnn_ctx *ctx, int32_t n, int64_t B, float p, uint64_t seed,
+                                uint64_t first_frame, fbgnn_tensor2 noise) {
+    REQUIRE(ctx && n > 0 && B >= 0 && noise.ptr, "bad argument");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    if (B == 0) return 0;
+    SampleArgs a{};
+    a.X.n = n; a.mode = 1; a.thr0 = p;
+    a.seed = seed; a.first_frame = first_frame;
+    a.nx_out = v2<uint8_t>(noise);
+    k_sample<<<(unsigned)B, 128, (size_t)n, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+extern "C" int fbgnn_syndrome(fbgnn_graph *g, int64_t B, fbgnn_tensor2 noise, fbgnn_tensor2 syndrome) {
+    REQUIRE(g && noise.ptr && syndrome.ptr && B >= 0, "bad argument");
+    if (int rc = need_decodable(g)) return rc;
+    fbgnn_ctx *ctx = g->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    if (B == 0) return 0;
+    SyndromeArgs a{g->dev, v2<const uint8_t>(noise), v2<uint8_t>(syndrome)};
+    k_syndrome<<<(unsigned)B, 128, (size_t)g->dev.n, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+// ------------------------------------------------------------------ decoders ------------
+extern "C" int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                                fbgnn_tensor3 llr, float prior, fbgnn_tensor2 synd_x, fbgnn_tensor2 synd_z,
+                                fbgnn_tensor2 Lx, fbgnn_tensor2 Ly, fbgnn_tensor2 Lz, fbgnn_tensor2 x_hat,
+                                fbgnn_tensor2 z_hat, fbgnn_tensor2 x_logit, fbgnn_tensor2 z_logit,
+                                fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z) {
+    REQUIRE(code, "code is NULL");
+    REQUIRE(cn_type >= 0 && cn_type <= 2, "unknown cn_type %d", cn_type);
+    REQUIRE(num_iter >= 0 && B >= 0, "num_iter and B must be non-negative");
+    REQUIRE(synd_x.ptr && synd_z.ptr, "syndromes are NULL");
+    fbgnn_ctx *ctx = code->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    Bp4Args a{};
+    a.X = code->X->dev; a.Z = code->Z->dev;
+    a.cn_type = cn_type; a.num_iter = num_iter; a.factor = factor;
+    a.llr = v3<const float>(llr); a.prior = prior;
+    a.sx = v2<const uint8_t>(synd_x); a.sz = v2<const uint8_t>(synd_z);
+    a.Lx = v2<float>(Lx); a.Ly = v2<float>(Ly); a.Lz = v2<float>(Lz);
+    a.xh = v2<uint8_t>(x_hat); a.zh = v2<uint8_t>(z_hat);
+    a.xl = v2<float>(x_logit); a.zl = v2<float>(z_logit);
+    a.msg_x = v2<float>(msg_x); a.msg_z = v2<float>(msg_z);
+    return launch_bp4(ctx, a, B);
+}
+
+static size_t bp2_smem(const SideDev &S) { return sizeof(float) * ((size_t)S.E + S.n) + S.m + 16; }
+
+static int launch_bp2(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B) {
+    if (B <= 0) return 0;
+    const size_t smem = bp2_smem(a.S);
+    if (int rc = set_smem(k_bp2, smem, ctx, "binary BP")) return rc;
+    k_bp2<<<(unsigned)B, pick_threads(a.S.n, a.S.m), smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+extern "C" int fbgnn_bp2_decode(fbgnn_graph *g, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                                fbgnn_tensor2 llr, fbgnn_tensor2 synd, fbgnn_tensor2 soft, fbgnn_tensor2 hard) {
+    REQUIRE(g, "graph is NULL");
+    REQUIRE(cn_type >= 0 && cn_type <= 2, "unknown cn_type %d", cn_type);
+    REQUIRE(num_iter >= 0 && B >= 0, "num_iter and B must be non-negative");
+    REQUIRE(llr.ptr, "llr is NULL");
+    REQUIRE(soft.ptr || hard.ptr, "no output requested");
+    if (int rc = need_decodable(g)) return rc;
+    fbgnn_ctx *ctx = g->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    Bp2Args a{};
+    a.S = g->dev; a.cn_type = cn_type; a.num_iter = num_iter; a.factor = factor;
+    a.llr = v2<const float>(llr); a.synd = v2<const uint8_t>(synd);
+    a.soft = v2<float>(soft); a.hard = v2<uint8_t>(hard);
+    return launch_bp2(ctx, a, B);
+}
+
+// ------------------------------------------------------------------ feedback GNN --------
+template <int H, int M>
+static void pack_gnn(std::vector<float> &w, const float *W0, const float *b0, const float *W1x,
+                     const float *b1x, const float *W2x, const float *b2x, const float *W1z,
+                     const float *b1z, const float *W2z, const float *b2z, const float *W3, const float *b3) {
+    typedef GnnLayout<H, M> L;
+    w.assign(L::total, 0.0f);
+    auto put = [&](int off, const float *src, int count) { if (src) std::memcpy(&w[off], src, sizeof(float) * count); };
+    put(L::W1x, W1x, 4 * H); put(L::b1x, b1x, H); put(L::W2x, W2x, H * M); put(L::b2x, b2x, M);
+    put(L::W1z, W1z, 4 * H); put(L::b1z, b1z, H); put(L::W2z, W2z, H * M); put(L::b2z, b2z, M);
+    put(L::W3, W3, (2 * M + 3) * H); put(L::b3, b3, H); put(L::W0, W0, H * 3); put(L::b0, b0, 3);
+}
+
+extern "C" int fbgnn_gnn_create(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t activation, int32_t reduce_op,
+                                const float *W0, const float *b0, const float *W1x, const float *b1x,
+                                const float *W2x, const float *b2x, const float *W1z, const float *b1z,
+                                const float *W2z, const float *b2z, const float *W3, const float *b3,
+                                fbgnn_gnn **out) {
+    REQUIRE(ctx && out, "NULL argument");
+    REQUIRE(W0 && W1x && W2x && W1z && W2z && W3, "weight matrices must not be NULL");
+    REQUIRE(activation >= 0 && activation <= 2, "unknown activation %d", activation);
+    REQUIRE(reduce_op >= 0 && reduce_op <= 3, "unknown reduce_op %d", reduce_op);
+    const bool any_b = b0 || b1x || b2x || b1z || b2z || b3, all_b = b0 && b1x && b2x && b1z && b2z && b3;
+    REQUIRE(any_b == all_b, "either all biases or none must be given");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    std::vector<float> w;
+    if (H == 40 && M == 20) pack_gnn<40, 20>(w, W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3);
+    else if (H == 20 && M == 20) pack_gnn<20, 20>(w, W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3);
+    else if (H == 64 && M == 32) pack_gnn<64, 32>(w, W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3);
+    else return fail(FBGNN_E_UNSUPPORTED, "Feedback_GNN with num_hidden_units=%d, num_msg_dims=%d is not "
+                     "compiled into this build (available: 40/20, 20/20, 64/32)", H, M);
+    fbgnn_gnn *g = new fbgnn_gnn();
+    g->ctx = ctx; g->H = H; g->M = M; g->act = activation; g->reduce = reduce_op; g->use_bias = all_b ? 1 : 0;
+    g->total = (int)w.size();
+    CK(cudaMalloc(&g->weights, w.size() * sizeof(float)));
+    CK(cudaMemcpy(g->weights, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    *out = g;
+    return 0;
+}
+
+extern "C" int fbgnn_gnn_destroy(fbgnn_gnn *g) {
+    if (!g) return 0;
+    cudaSetDevice(g->ctx->device);
+    cudaFree(g->weights);
+    delete g;
+    return 0;
+}
+
+template <int H, int M>
+static int launch_gnn_t(fbgnn_ctx *ctx, const GnnArgs &a) {
+    const size_t smem = sizeof(float) * GnnLayout<H, M>::total;
+    if (int rc = set_smem(k_gnn<H, M>, smem, ctx, "feedback GNN")) return rc;
+    const int64_t items = a.num_frames * a.X.n;
+    int64_t blocks = (items + 127) / 128;
+    blocks = std::min<int64_t>(blocks, (int64_t)ctx->num_sms * 8);
+    k_gnn<H, M><<<(unsigned)blocks, 128, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+static int launch_gnn(fbgnn_ctx *ctx, const fbgnn_gnn *g, GnnArgs &a) {
+    if (a.num_frames <= 0) return 0;
+    a.weights = g->weights; a.act = g->act; a.reduce = g->reduce; a.use_bias = g->use_bias;
+    if (g->H == 40 && g->M == 20) return launch_gnn_t<40, 20>(ctx, a);
+    if (g->H == 20 && g->M == 20) return launch_gnn_t<20, 20>(ctx, a);
+    if (g->H == 64 && g->M == 32) return launch_gnn_t<64, 32>(ctx, a);
+    return fail(FBGNN_E_UNSUPPORTED, "unsupported GNN dimensions");
+}
+
+extern "C" int fbgnn_gnn_forward(fbgnn_code *code, fbgnn_gnn *gnn, int64_t B, fbgnn_tensor3 h_vn,
+                                 fbgnn_tensor2 logit_hx, fbgnn_tensor2 logit_hz, fbgnn_tensor2 synd_x,
+                                 fbgnn_tensor2 synd_z, fbgnn_tensor3 out) {
+    REQUIRE(code && gnn, "NULL handle");
+    REQUIRE(h_vn.ptr && logit_hx.ptr && logit_hz.ptr && synd_x.ptr && synd_z.ptr && out.ptr, "NULL tensor");
+    REQUIRE(B >= 0, "B must be non-negative");
+    fbgnn_ctx *ctx = code->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    GnnArgs a{};
+    a.X = code->X->dev; a.Z = code->Z->dev;
+    a.num_frames = B;
+    a.h_vn = v3<const float>(h_vn);
+    a.logit_hx = v2<const float>(logit_hx); a.logit_hz = v2<const float>(logit_hz);
+    a.sx = v2<const uint8_t>(synd_x); a.sz = v2<const uint8_t>(synd_z);
+    a.out = v3<float>(out);
+    return launch_gnn(ctx, gnn, a);
+}
+
+// ------------------------------------------------------------------ pipelines -----------
+static int ws_reserve(fbgnn_ctx *ctx, int64_t B, int n, int m) {
+    Workspace &w = ctx->ws;
+    if (w.cap_frames >= B && w.n == n && w.m == m) return 0;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ws_free(w);
+    const size_t b = (size_t)B;
+    CK(cudaMalloc(&w.vbits, b * n));
+    CK(cudaMalloc(&w.sbits, b * std::max(m, 1)));
+    CK(cudaMalloc(&w.active[0], b));
+    CK(cudaMalloc(&w.active[1], b));
+    CK(cudaMalloc(&w.rounds, b));
+    CK(cudaMalloc(&w.L, b * 3 * n * sizeof(float)));
+    CK(cudaMalloc(&w.P, b * 3 * n * sizeof(float)));
+    CK(cudaMalloc(&w.logit, b * std::max(m, 1) * sizeof(float)));
+    CK(cudaMalloc(&w.list[0], b * sizeof(int)));
+    CK(cudaMalloc(&w.list[1], b * sizeof(int)));
+    CK(cudaMalloc(&w.list_count, 2 * sizeof(int)));
+    CK(cudaMalloc(&w.counters, 4 * sizeof(unsigned long long)));
+    w.cap_frames = B; w.n = n; w.m = m;
+    return 0;
+}
+
+extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cfg, uint64_t seed,
+                                  uint64_t first_frame, int64_t B, fbgnn_tensor2 noise_x, fbgnn_tensor2 noise_z,
+                                  uint8_t *flags, fbgnn_tensor2 x_diff, fbgnn_tensor2 z_diff, int64_t *counters) {
+    REQUIRE(code && cfg, "NULL argument");
+    REQUIRE(cfg->num_stages >= 1 && cfg->num_iter && cfg->factor && cfg->cn_type, "bad pipeline configuration");
+    REQUIRE(cfg->num_stages == 1 || cfg->gnn, "feedback GNNs missing");
+    REQUIRE((noise_x.ptr == nullptr) == (noise_z.ptr == nullptr), "give both noise_x and noise_z or neither");
+    REQUIRE(B >= 0 && B < ((int64_t)1 << 31), "bad batch size");
+    for (int s = 0; s < cfg->num_stages; s++) {
+        REQUIRE(cfg->cn_type[s] >= 0 && cfg->cn_type[s] <= 2, "unknown cn_type in stage %d", s);
+        REQUIRE(cfg->num_iter[s] >= 0, "negative num_iter in stage %d", s);
+        REQUIRE(s == 0 || cfg->gnn[s - 1], "feedback GNN %d is NULL", s - 1);
+    }
+    fbgnn_ctx *ctx = code->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    const SideDev &X = code->X->dev, &Z = code->Z->dev;
+    const int n = X.n, m = X.m + Z.m;
+    if (counters) std::memset(counters, 0, 4 * sizeof(int64_t));
+    if (B == 0) return 0;
+    if (int rc = ws_reserve(ctx, B, n, m)) return rc;
+    Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(w.rounds, 0, (size_t)B, st));
+    CK(cudaMemsetAsync(w.counters, 0, 4 * sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(w.list_count, 0, 2 * sizeof(int), st));
+
+    // noise + syndromes
+    SampleArgs sa{};
+    sa.X = X; sa.Z = Z; sa.mode = 0;
+    sa.thr0 = cfg->thr[0]; sa.thr1 = cfg->thr[1]; sa.thr2 = cfg->thr[2];
+    sa.seed = seed; sa.first_frame = first_frame;
+    sa.nx_in = v2<const uint8_t>(noise_x); sa.nz_in = v2<const uint8_t>(noise_z);
+    sa.vbits = w.vbits; sa.sbits = w.sbits;
+    k_sample<<<(unsigned)B, 128, (size_t)n, st>>>(sa);
+    CK(cudaGetLastError());
+    ctx->launches++;
+
+    const int S = cfg->num_stages;
+    int64_t cur_count = B;            // frames the current stage runs on
+    const int *cur_list = nullptr;
+    for (int s = 0; s < S; s++) {
+        const bool last = (s == S - 1);
+        if (s > 0) {
+            // feedbacks[s-1]: priors P from the marginals L and the soft syndromes
+            GnnArgs ga{};
+            ga.X = X; ga.Z = Z;
+            ga.frame_list = cur_list; ga.num_frames = cur_count;
+            ga.h_vn = View3<const float>{w.L, 3 * (int64_t)n, 1, n};
+            ga.logit_hx = View2<const float>{w.logit, 1, m};           // z_logit: rows of hx
+            ga.logit_hz = View2<const float>{w.logit + X.m, 1, m};     // x_logit: rows of hz
+            ga.sx = View2<const uint8_t>{w.sbits, 1, m};
+            ga.sz = View2<const uint8_t>{w.sbits + X.m, 1, m};
+            ga.out = View3<float>{w.P, 3 * (int64_t)n, 1, n};
+            if (int rc = launch_gnn(ctx, cfg->gnn[s - 1], ga)) return rc;
+        }
+        Bp4Args a{};
+        a.X = X; a.Z = Z;
+        a.cn_type = cfg->cn_type[s]; a.num_iter = cfg->num_iter[s]; a.factor = cfg->factor[s];
+        a.frame_list = cur_list;
+        if (s > 0) a.llr = View3<const float>{w.P, 3 * (int64_t)n, n, 1};
+        a.prior = cfg->prior;
+        a.sx = View2<const uint8_t>{w.sbits, 1, m};
+        a.sz = View2<const uint8_t>{w.sbits + X.m, 1, m};
+        if (!last) {
+            a.Lx = View2<float>{w.L, 3 * (int64_t)n, 1};
+            a.Ly = View2<float>{w.L + n, 3 * (int64_t)n, 1};
+            a.Lz = View2<float>{w.L + 2 * n, 3 * (int64_t)n, 1};
+            a.zl = View2<float>{w.logit, 1, m};
+            a.xl = View2<float>{w.logit + X.m, 1, m};
+        }
+        a.vbits = w.vbits;
+        a.active_in = (s == 0) ? nullptr : w.active[(s - 1) & 1];
+        a.active_out = w.active[s & 1];
+        a.rounds = last ? nullptr : w.rounds;
+        const bool compact = cfg->skip_inactive && !last;
+        if (compact) {
+            CK(cudaMemsetAsync(w.list_count + (s & 1), 0, sizeof(int), st));
+            a.next_list = w.list[s & 1];
+            a.next_count = w.list_count + (s & 1);
+        }
+        if (int rc = launch_bp4(ctx, a, cur_count)) return rc;
+        if (compact) {
+            int cnt = 0;
+            CK(cudaMemcpyAsync(&cnt, w.list_count + (s & 1), sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            cur_count = cnt;
+            cur_list = w.list[s & 1];
+            if (cur_count == 0) break;
+        }
+    }
+
+    FinalArgs fa{};
+    fa.X = X; fa.Z = Z;
+    fa.lx_bits = code->lx_bits; fa.lz_bits = code->lz_bits; fa.kx = code->kx; fa.kz = code->kz;
+    fa.binary = 0;
+    fa.vbits = w.vbits; fa.rounds = w.rounds; fa.flags = flags;
+    fa.x_diff = v2<uint8_t>(x_diff); fa.z_diff = v2<uint8_t>(z_diff);
+    fa.counters = w.counters;
+    const int W = (n + 31) / 32;
+    k_final<<<(unsigned)B, 128, (size_t)((n + 3) & ~3) + 8 * (size_t)W, st>>>(fa);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (counters) {
+        unsigned long long h[4];
+        CK(cudaMemcpyAsync(h, w.counters, sizeof h, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < 4; i++) counters[i] = (int64_t)h[i];
+    }
+    return 0;
+}
+
+extern "C" int fbgnn_bsc_pipeline_run(fbgnn_graph *g, fbgnn_graph *logical, int32_t cn_type, int32_t num_iter,
+                                      float factor, float llr_const, float p, uint64_t seed, uint64_t first_frame,
+                                      int64_t B, fbgnn_tensor2 noise, uint8_t *flags, int64_t *counters) {
+    REQUIRE(g, "graph is NULL");
+    REQUIRE(cn_type >= 0 && cn_type <= 2, "unknown cn_type %d", cn_type);
+    REQUIRE(num_iter >= 0 && B >= 0 && B < ((int64_t)1 << 31), "bad argument");
+    REQUIRE(!logical || logical->dev.n == g->dev.n, "logical_pcm has %d columns, pcm has %d",
+            logical ? logical->dev.n : 0, g->dev.n);
+    if (int rc = need_decodable(g)) return rc;
+    fbgnn_ctx *ctx = g->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    const SideDev &S = g->dev;
+    const int n = S.n, m = S.m;
+    if (counters) std::memset(counters, 0, 4 * sizeof(int64_t));
+    if (B == 0) return 0;
+    if (int rc = ws_reserve(ctx, B, n, m)) return rc;
+    Workspace &w = ctx->ws;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMemsetAsync(w.counters, 0, 4 * sizeof(unsigned long long), st));
+    SampleArgs sa{};
+    sa.X = S; sa.mode = 1; sa.thr0 = p;
+    sa.seed = seed; sa.first_frame = first_frame;
+    sa.nx_in = v2<const uint8_t>(noise);
+    sa.vbits = w.vbits; sa.sbits = w.sbits;
+    k_sample<<<(unsigned)B, 128, (size_t)n, st>>>(sa);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    Bp2Args a{};
+    a.S = S; a.cn_type = cn_type; a.num_iter = num_iter; a.factor = factor;
+    a.llr_const = llr_const;
+    a.synd = View2<const uint8_t>{w.sbits, 1, m};
+    a.vbits = w.vbits;                 // decision -> bit 2
+    if (int rc = launch_bp2(ctx, a, B)) return rc;
+    FinalArgs fa{};
+    fa.X = S;
+    fa.lx_bits = logical ? logical->dev.bitrows : nullptr;
+    fa.kx = logical ? logical->dev.m : 0;
+    fa.binary = 1;
+    fa.vbits = w.vbits; fa.flags = flags; fa.counters = w.counters;
+    const int W = (n + 31) / 32;
+    k_final<<<(unsigned)B, 128, (size_t)((n + 3) & ~3) + 8 * (size_t)W, st>>>(fa);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    if (counters) {
+        unsigned long long h[4];
+        CK(cudaMemcpyAsync(h, w.counters, sizeof h, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        for (int i = 0; i < 4; i++) counters[i] = (int64_t)h[i];
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------ measurement helpers -
+static int time_probe(fbgnn_ctx *ctx, void (*kernel)(float *, int), int iters, double per_thread_ops, double *rate) {
+    float *d = nullptr;
+    CK(cudaMalloc(&d, 4));
+    const int blocks = ctx->num_sms * 8, threads = 256;
+    kernel<<<blocks, threads, 0, ctx->stream>>>(d, 16);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters);
+        CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        best = std::min(best, ms);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    CK(cudaFree(d));
+    *rate = per_thread_ops * (double)blocks * threads / (best * 1e-3);
+    return 0;
+}
+
+extern "C" int fbgnn_sfu_peak(fbgnn_ctx *ctx, double *evals_per_s) {
+    REQUIRE(ctx && evals_per_s, "NULL argument");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    const int iters = 20000;
+    return time_probe(ctx, k_sfu_peak, iters, 8.0 * iters, evals_per_s);
+}
+
+extern "C" int fbgnn_fma_peak(fbgnn_ctx *ctx, double *instr_per_s) {
+    REQUIRE(ctx && instr_per_s, "NULL argument");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    const int iters = 100000;
+    return time_probe(ctx, k_fma_peak, iters, 8.0 * iters, instr_per_s);
+}
+
+extern "C" int fbgnn_math_probe(fbgnn_ctx *ctx, const char *fn, const float *x, float *y, int64_t n) {
+    REQUIRE(ctx && fn && x && y && n >= 0, "bad argument");
+    static const char *names[] = {"exp", "log", "log1p", "softplus", "phi4", "phi2", "tanh", "atanh"};
+    int id = -1;
+    for (int i = 0; i < 8; i++) if (!std::strcmp(fn, names[i])) id = i;
+    REQUIRE(id >= 0, "unknown probe function '%s'", fn);
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    if (n == 0) return 0;
+    k_math_probe<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(id, x, y, n);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}

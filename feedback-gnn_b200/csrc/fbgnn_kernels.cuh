@@ -1,0 +1,701 @@
+// fbgnn_kernels.cuh -- sm_100a kernels of the BP -> feedback-GNN -> BP hot path.
+//
+// Layout in HBM (fused pipeline workspace, one row per frame):
+//   vbits  u8  [B][n]        bit0 noise_x, bit1 noise_z, bit2 x_hat, bit3 z_hat
+//   sbits  u8  [B][m_x+m_z]  syndrome_x then syndrome_z
+//   L      f32 [B][3][n]     marginals (Lx, Ly, Lz) of the last BP stage
+//   P      f32 [B][3][n]     priors produced by the feedback GNN for the next BP stage
+//   logit  f32 [B][m_x+m_z]  z_logit (rows of hx) then x_logit (rows of hz)
+//   active/rounds/flags u8 [B]
+// Everything that is touched every BP iteration -- both message arrays, the per-variable
+// priors, the syndrome bits -- lives in shared memory of the CTA that owns the frame; HBM is
+// touched once per frame per stage.
+//
+// Arithmetic: float32, fixed evaluation order, all elementary functions from fb_math.h; the
+// kernels are bit-exact against oracle/fbgnn_oracle.c (see tests/).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "fb_math.h"
+
+namespace fbgnn {
+
+typedef uint16_t idx_t;
+
+// Tanner graph of one parity-check matrix, device pointers.
+struct SideDev {
+    int n, m, E;
+    int reg_dv, reg_dc;        // common VN / CN degree if the side is regular, else 0
+    const idx_t *vn_ptr;       // [n+1] edge ranges per VN; edges sorted by (vn, cn) = "VN order"
+    const idx_t *vn_cn;        // [E]   check of each edge, VN order
+    const idx_t *cn_ptr;       // [m+1] edge ranges per CN; edges sorted by (cn, vn) = "CN order"
+    const idx_t *cn_edge;      // [E]   VN-order position of each edge, listed in CN order
+    const idx_t *cn_vn;        // [E]   variable of each edge, listed in CN order
+    const uint32_t *bitrows;   // [m][W] rows bit-packed, W = ceil(n/32)
+};
+
+template <typename T> struct View2 { T *ptr; int64_t s0, s1;
+    __device__ __forceinline__ T &operator()(int64_t i, int64_t j) const { return ptr[i * s0 + j * s1]; } };
+template <typename T> struct View3 { T *ptr; int64_t s0, s1, s2;
+    __device__ __forceinline__ T &operator()(int64_t i, int64_t j, int64_t k) const { return ptr[i * s0 + j * s1 + k * s2]; } };
+
+// ------------------------------------------------------------------ Philox4x32-10 ----
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                              uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
+
+// ------------------------------------------------------------------ check nodes -------
+// Update one check node in place: msg[] holds v2c on entry, c2v on exit.  Two passes over
+// the check's edges; pass 1 parks phi(|m|) in the message slot and the signs in a bit mask
+// (check degree <= 64 is enforced when the graph is created).
+template <bool PHI4>
+__device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge, int k0, int k1,
+                                              float *msg, int synd_bit, int cn_type, float factor) {
+    if (cn_type == 0) {
+        unsigned long long mask = 0ull;
+        int par = synd_bit;
+        float T = 0.0f;
+        for (int k = k0; k < k1; k++) {
+            const int e = cn_edge[k];
+            const float m = msg[e];
+            const int neg = m < 0.0f;
+            mask |= (unsigned long long)neg << (k - k0);
+            par ^= neg;
+            const float a = PHI4 ? fb_phi4f(fabsf(m)) : fb_phi2f(fabsf(m));
+            msg[e] = a;
+            T = FB_ADD(T, a);
+        }
+        for (int k = k0; k < k1; k++) {
+            const int e = cn_edge[k];
+            const float x = FB_SUB(T, msg[e]);
+            float v = PHI4 ? fb_phi4f(x) : fb_phi2f(x);
+            const int s = par ^ (int)((mask >> (k - k0)) & 1ull);
+            v = s ? -v : v;
+            msg[e] = FB_MUL(v, factor);
+        }
+    } else if (cn_type == 1) {
+        float P = 1.0f;
+        for (int k = k0; k < k1; k++) {
+            const int e = cn_edge[k];
+            float t = fb_tanhf(FB_MUL(msg[e], 0.5f));
+            if (t == 0.0f) t = 1e-12f;
+            msg[e] = t;
+            P = FB_MUL(P, t);
+        }
+        P = synd_bit ? -P : P;
+        for (int k = k0; k < k1; k++) {
+            const int e = cn_edge[k];
+            float v = FB_MUL(FB_DIV(1.0f, msg[e]), P);
+            if (fabsf(v) < 1e-7f) v = 0.0f;
+            v = FB_FMIN(FB_FMAX(v, -FB_ATANH_CLIP), FB_ATANH_CLIP);
+            v = FB_MUL(2.0f, fb_atanhf(v));
+            msg[e] = FB_MUL(v, factor);
+        }
+    } else {
+        const float LARGE = 10000.0f;
+        unsigned long long mask = 0ull;
+        int par = synd_bit;
+        float mn = __int_as_float(0x7f800000);
+        for (int k = k0; k < k1; k++) {
+            const int e = cn_edge[k];
+            float m = FB_FMIN(FB_FMAX(msg[e], -FB_LLR_MAX), FB_LLR_MAX);
+            const int neg = m < 0.0f;
+            mask |= (unsigned long long)neg << (k - k0);
+            par ^= neg;
+            const float a = fabsf(m);
+            msg[e] = a;
+            if (a < mn) mn = a;
+        }
+        float mn2 = __int_as_float(0x7f800000), sum = 0.0f;
+        for (int k = k0; k < k1; k++) {
+            const int e = cn_edge[k];
+            float d = FB_SUB(msg[e], mn);
+            if (d == 0.0f) d = LARGE;
+            msg[e] = d;
+            if (d < mn2) mn2 = d;
+            sum = FB_ADD(sum, d);
+        }
+        mn2 = FB_ADD(mn2, mn);
+        const float node_sum = FB_SUB(sum, 19999.0f);
+        const float sg = (node_sum > 0.0f) ? 1.0f : ((node_sum < 0.0f) ? -1.0f : 0.0f);
+        const float dm = FB_MUL(0.5f, FB_SUB(1.0f, sg));
+        const float mne = FB_ADD(FB_MUL(FB_SUB(1.0f, dm), mn), FB_MUL(dm, mn2));
+        for (int k = k0; k < k1; k++) {
+            const int e = cn_edge[k];
+            float v = (msg[e] == LARGE) ? mne : mn;
+            const int s = par ^ (int)((mask >> (k - k0)) & 1ull);
+            v = s ? -v : v;
+            msg[e] = FB_MUL(v, factor);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ quaternary BP -----
+struct Bp4Args {
+    SideDev X, Z;
+    int cn_type, num_iter;
+    float factor;
+    const int *frame_list;              // optional: CTA i decodes frame frame_list[i]
+    View3<const float> llr;             // (b, k, v); ptr == nullptr -> constant prior
+    float prior;
+    View2<const uint8_t> sx, sz;        // (c, b)
+    View2<float> Lx, Ly, Lz;            // (b, v)   optional
+    View2<uint8_t> xh, zh;              // (b, v)   optional (layer mode)
+    View2<float> xl, zl;                // (row, b) optional: x_logit over hz rows, z_logit over hx rows
+    View2<float> msg_x, msg_z;          // (b, e)   optional dump of the final c2v messages
+    // pipeline mode (vbits != nullptr): decision + activity bookkeeping of feedback_gnn.py:322-340
+    uint8_t *vbits;                     // [B][n], bits 2,3 receive the decision of active frames
+    const uint8_t *active_in;           // [B] or nullptr (= all active)
+    uint8_t *active_out;                // [B]
+    uint8_t *rounds;                    // [B] incremented when the frame stays active (or nullptr)
+    int *next_list, *next_count;        // optional compaction of still-active frames
+};
+
+// One CTA decodes one frame.  Dynamic shared memory:
+//   float msg_x[E_x], msg_z[E_z], pri[CONST_PRIOR ? 2n : 3n];  u8 sbx[m_x], sbz[m_z], dec[n]
+template <bool CONST_PRIOR>
+__global__ void k_bp4(const Bp4Args a) {
+    extern __shared__ float smem[];
+    const SideDev &X = a.X, &Z = a.Z;
+    const int n = X.n, T = blockDim.x, tid = threadIdx.x;
+    const int64_t b = a.frame_list ? a.frame_list[blockIdx.x] : blockIdx.x;
+    float *mx = smem, *mz = mx + X.E, *pri = mz + Z.E;
+    uint8_t *sbx = (uint8_t *)(pri + (CONST_PRIOR ? 2 : 3) * n), *sbz = sbx + X.m, *dec = sbz + Z.m;
+
+    for (int e = tid; e < X.E + Z.E; e += T) mx[e] = 0.0f;
+    if (!CONST_PRIOR)
+        for (int i = tid; i < 3 * n; i += T) pri[i] = a.llr(b, i / n, i % n);
+    for (int c = tid; c < X.m; c += T) sbx[c] = a.sx(c, b);
+    for (int c = tid; c < Z.m; c += T) sbz[c] = a.sz(c, b);
+    __syncthreads();
+
+    for (int it = 0; it < a.num_iter; it++) {
+        // variable nodes (decoding_q.py:227-275)
+        for (int v = tid; v < n; v += T) {
+            const int x0 = X.vn_ptr[v], x1 = X.vn_ptr[v + 1], z0 = Z.vn_ptr[v], z1 = Z.vn_ptr[v + 1];
+            float Sx = 0.0f, Sz = 0.0f;
+            for (int e = x0; e < x1; e++) Sx = FB_ADD(Sx, mx[e]);
+            for (int e = z0; e < z1; e++) Sz = FB_ADD(Sz, mz[e]);
+            const float px = CONST_PRIOR ? a.prior : pri[v];
+            const float py = CONST_PRIOR ? a.prior : pri[n + v];
+            const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
+            const float ly = FB_ADD(FB_ADD(Sz, Sx), py);
+            const float lx = FB_ADD(Sz, px);
+            const float lz = FB_ADD(Sx, pz);
+            const float num_hx = fb_softplusf(-lx), num_hz = fb_softplusf(-lz);
+            for (int e = x0; e < x1; e++) {
+                const float m = mx[e];
+                mx[e] = FB_SUB(num_hx, fb_logaddexpf(-FB_SUB(lz, m), -FB_SUB(ly, m)));
+            }
+            for (int e = z0; e < z1; e++) {
+                const float m = mz[e];
+                mz[e] = FB_SUB(num_hz, fb_logaddexpf(-FB_SUB(lx, m), -FB_SUB(ly, m)));
+            }
+        }
+        __syncthreads();
+        // check nodes of both sides as one index space
+        for (int c = tid; c < X.m + Z.m; c += T) {
+            if (c < X.m)
+                cn_update_one<true>(X.cn_edge, X.cn_ptr[c], X.cn_ptr[c + 1], mx, sbx[c], a.cn_type, a.factor);
+            else
+                cn_update_one<true>(Z.cn_edge, Z.cn_ptr[c - X.m], Z.cn_ptr[c - X.m + 1], mz, sbz[c - X.m],
+                                    a.cn_type, a.factor);
+        }
+        __syncthreads();
+    }
+
+    if (a.msg_x.ptr) for (int e = tid; e < X.E; e += T) a.msg_x(b, e) = mx[e];
+    if (a.msg_z.ptr) for (int e = tid; e < Z.E; e += T) a.msg_z(b, e) = mz[e];
+
+    // marginals, decision, per-variable terms of the soft syndromes (decoding_q.py:771-790,455-464)
+    const bool want_logits = a.xl.ptr != nullptr || a.zl.ptr != nullptr;
+    for (int v = tid; v < n; v += T) {
+        float Sx = 0.0f, Sz = 0.0f;
+        for (int e = X.vn_ptr[v]; e < X.vn_ptr[v + 1]; e++) Sx = FB_ADD(Sx, mx[e]);
+        for (int e = Z.vn_ptr[v]; e < Z.vn_ptr[v + 1]; e++) Sz = FB_ADD(Sz, mz[e]);
+        const float px = CONST_PRIOR ? a.prior : pri[v];
+        const float py = CONST_PRIOR ? a.prior : pri[n + v];
+        const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
+        const float ly = FB_ADD(FB_ADD(Sz, Sx), py);
+        const float lx = FB_ADD(Sz, px);
+        const float lz = FB_ADD(Sx, pz);
+        if (a.Lx.ptr) a.Lx(b, v) = lx;
+        if (a.Ly.ptr) a.Ly(b, v) = ly;
+        if (a.Lz.ptr) a.Lz(b, v) = lz;
+        int d = 0;
+        float best = 0.0f;
+        if (lx < best) { best = lx; d = 1; }
+        if (lz < best) { best = lz; d = 2; }
+        if (ly < best) { best = ly; d = 3; }
+        if (want_logits) {
+            const float llr_zp = FB_SUB(fb_softplusf(-lx), fb_logaddexpf(-lz, -ly));
+            const float llr_xp = FB_SUB(fb_softplusf(-lz), fb_logaddexpf(-lx, -ly));
+            d |= (llr_xp < 0.0f) << 2;
+            d |= (llr_zp < 0.0f) << 3;
+            pri[v] = fb_phi4f(fabsf(llr_xp));
+            pri[n + v] = fb_phi4f(fabsf(llr_zp));
+        }
+        dec[v] = (uint8_t)d;
+    }
+    __syncthreads();
+
+    // soft syndromes per check row and the syndrome match of the decision
+    int mismatch = 0;
+    for (int c = tid; c < X.m + Z.m; c += T) {
+        const bool isx = c < X.m;                       // hx row: z_logit from llr_z', checks z_hat
+        const SideDev &S = isx ? X : Z;
+        const int cc = isx ? c : c - X.m;
+        const float *scr = isx ? pri + n : pri;
+        const int sbit = isx ? 3 : 2, dbit = isx ? 1 : 0;
+        int par = 0, dpar = 0;
+        float Tsum = 0.0f;
+        for (int k = S.cn_ptr[cc]; k < S.cn_ptr[cc + 1]; k++) {
+            const int v = S.cn_vn[k];
+            const int dv = dec[v];
+            par ^= (dv >> sbit) & 1;
+            dpar ^= (dv >> dbit) & 1;
+            if (want_logits) Tsum = FB_ADD(Tsum, scr[v]);
+        }
+        mismatch |= dpar ^ (isx ? sbx[cc] : sbz[cc]);
+        if (want_logits) {
+            float val = fb_phi4f(Tsum);
+            val = par ? -val : val;
+            if (isx) { if (a.zl.ptr) a.zl(cc, b) = val; }
+            else     { if (a.xl.ptr) a.xl(cc, b) = val; }
+        }
+    }
+    if (a.xh.ptr) for (int v = tid; v < n; v += T) a.xh(b, v) = dec[v] & 1;
+    if (a.zh.ptr) for (int v = tid; v < n; v += T) a.zh(b, v) = (dec[v] >> 1) & 1;
+    if (a.vbits) {
+        mismatch = __syncthreads_or(mismatch);
+        const int act_in = a.active_in ? a.active_in[b] : 1;
+        if (act_in) {
+            uint8_t *vb = a.vbits + b * n;
+            for (int v = tid; v < n; v += T) vb[v] = (vb[v] & 3) | ((dec[v] & 3) << 2);
+        }
+        if (tid == 0) {
+            const int act_out = act_in && mismatch;
+            a.active_out[b] = (uint8_t)act_out;
+            if (a.rounds && act_out) a.rounds[b] += 1;
+            if (a.next_list && act_out) a.next_list[atomicAdd(a.next_count, 1)] = (int)b;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ binary BP ---------
+struct Bp2Args {
+    SideDev S;
+    int cn_type, num_iter;
+    float factor;
+    View2<const float> llr;             // (b, v) logits; ptr == nullptr -> constant llr_const
+    float llr_const;
+    View2<const uint8_t> synd;          // (c, b) optional
+    View2<float> soft;                  // (b, v) optional
+    View2<uint8_t> hard;                // (b, v) optional
+    uint8_t *vbits;                     // optional [B][n]: the hard decision goes to bit 2 (pipeline mode)
+};
+
+// smem: float msg[E], llr[n]; u8 sb[m]
+__global__ void k_bp2(const Bp2Args a) {
+    extern __shared__ float smem[];
+    const SideDev &S = a.S;
+    const int n = S.n, T = blockDim.x, tid = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    float *msg = smem, *llr = msg + S.E;
+    uint8_t *sb = (uint8_t *)(llr + n);
+    for (int e = tid; e < S.E; e += T) msg[e] = 0.0f;
+    for (int v = tid; v < n; v += T) {
+        float l = a.llr.ptr ? a.llr(b, v) : a.llr_const;
+        l = FB_FMIN(FB_FMAX(l, -FB_LLR_MAX), FB_LLR_MAX);
+        llr[v] = -l;
+    }
+    for (int c = tid; c < S.m; c += T) sb[c] = a.synd.ptr ? a.synd(c, b) : 0;
+    __syncthreads();
+    for (int it = 0; it < a.num_iter; it++) {
+        for (int v = tid; v < n; v += T) {
+            const int e0 = S.vn_ptr[v], e1 = S.vn_ptr[v + 1];
+            float s = 0.0f;
+            for (int e = e0; e < e1; e++) s = FB_ADD(s, msg[e]);
+            s = FB_ADD(s, llr[v]);
+            for (int e = e0; e < e1; e++) msg[e] = FB_SUB(s, msg[e]);
+        }
+        __syncthreads();
+        for (int c = tid; c < S.m; c += T)
+            cn_update_one<false>(S.cn_edge, S.cn_ptr[c], S.cn_ptr[c + 1], msg, sb[c], a.cn_type, a.factor);
+        __syncthreads();
+    }
+    for (int v = tid; v < n; v += T) {
+        float s = 0.0f;
+        for (int e = S.vn_ptr[v]; e < S.vn_ptr[v + 1]; e++) s = FB_ADD(s, msg[e]);
+        const float x = -FB_ADD(llr[v], s);
+        if (a.soft.ptr) a.soft(b, v) = x;
+        if (a.hard.ptr) a.hard(b, v) = (uint8_t)(0.0f < x);
+        if (a.vbits) a.vbits[b * n + v] = (uint8_t)((a.vbits[b * n + v] & 3) | ((0.0f < x) ? 4 : 0));
+    }
+}
+
+// ------------------------------------------------------------------ feedback GNN ------
+struct GnnArgs {
+    SideDev X, Z;
+    const float *weights;               // packed, see GnnLayout
+    int act, reduce, use_bias;
+    const int *frame_list;
+    int64_t num_frames;                 // frames to process (list length or B)
+    View3<const float> h_vn;            // (b, v, k)
+    View2<const float> logit_hx, logit_hz;   // (row, b)
+    View2<const uint8_t> sx, sz;        // (c, b)
+    View3<float> out;                   // (b, v, k)
+};
+
+// packed weight layout (floats): each block padded to a multiple of 4 floats
+template <int H, int M> struct GnnLayout {
+    static constexpr int pad4(int x) { return (x + 3) & ~3; }
+    static constexpr int W1x = 0;
+    static constexpr int b1x = W1x + pad4(4 * H);
+    static constexpr int W2x = b1x + pad4(H);
+    static constexpr int b2x = W2x + pad4(H * M);
+    static constexpr int W1z = b2x + pad4(M);
+    static constexpr int b1z = W1z + pad4(4 * H);
+    static constexpr int W2z = b1z + pad4(H);
+    static constexpr int b2z = W2z + pad4(H * M);
+    static constexpr int W3 = b2z + pad4(M);
+    static constexpr int b3 = W3 + pad4((2 * M + 3) * H);
+    static constexpr int W0 = b3 + pad4(H);
+    static constexpr int b0 = W0 + pad4(H * 3);
+    static constexpr int total = b0 + pad4(3);
+};
+
+__device__ __forceinline__ float gnn_act(int act, float x) {
+    if (act == 0) return fb_tanhf(x);
+    if (act == 1) return x > 0.0f ? x : 0.0f;
+    return x;
+}
+
+// messages of one side into one variable node, reduced (feedback_gnn.py:175-184)
+template <int H, int M>
+__device__ __forceinline__ void gnn_side(const SideDev &S, const float *__restrict__ W1,
+                                         const float *__restrict__ b1, const float *__restrict__ W2,
+                                         const float *__restrict__ b2, const View2<const float> &logit,
+                                         const View2<const uint8_t> &synd, int64_t b, int v, float f1,
+                                         float f2, float f3, int act, int reduce, int use_bias,
+                                         float *red) {
+    const int e0 = S.vn_ptr[v], e1 = S.vn_ptr[v + 1];
+#pragma unroll
+    for (int i = 0; i < M; i++) red[i] = 0.0f;
+    for (int e = e0; e < e1; e++) {
+        const int c = S.vn_cn[e];
+        const float lg = logit(c, b);
+        const float hc = synd(c, b) ? -lg : lg;
+        float acc[M];
+#pragma unroll
+        for (int i = 0; i < M; i++) acc[i] = 0.0f;
+#pragma unroll 2
+        for (int j = 0; j < H; j += 4) {
+            const float4 w0 = *reinterpret_cast<const float4 *>(W1 + 0 * H + j);
+            const float4 w1 = *reinterpret_cast<const float4 *>(W1 + 1 * H + j);
+            const float4 w2 = *reinterpret_cast<const float4 *>(W1 + 2 * H + j);
+            const float4 w3 = *reinterpret_cast<const float4 *>(W1 + 3 * H + j);
+            const float4 bb = *reinterpret_cast<const float4 *>(b1 + j);
+            float h[4];
+            h[0] = FB_FMA(f3, w3.x, FB_FMA(f2, w2.x, FB_FMA(f1, w1.x, FB_FMA(hc, w0.x, 0.0f))));
+            h[1] = FB_FMA(f3, w3.y, FB_FMA(f2, w2.y, FB_FMA(f1, w1.y, FB_FMA(hc, w0.y, 0.0f))));
+            h[2] = FB_FMA(f3, w3.z, FB_FMA(f2, w2.z, FB_FMA(f1, w1.z, FB_FMA(hc, w0.z, 0.0f))));
+            h[3] = FB_FMA(f3, w3.w, FB_FMA(f2, w2.w, FB_FMA(f1, w1.w, FB_FMA(hc, w0.w, 0.0f))));
+            if (use_bias) { h[0] = FB_ADD(h[0], bb.x); h[1] = FB_ADD(h[1], bb.y); h[2] = FB_ADD(h[2], bb.z); h[3] = FB_ADD(h[3], bb.w); }
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const float hv = gnn_act(act, h[jj]);
+                const float *w2r = W2 + (j + jj) * M;
+#pragma unroll
+                for (int i = 0; i < M; i += 4) {
+                    const float4 w = *reinterpret_cast<const float4 *>(w2r + i);
+                    acc[i + 0] = FB_FMA(hv, w.x, acc[i + 0]);
+                    acc[i + 1] = FB_FMA(hv, w.y, acc[i + 1]);
+                    acc[i + 2] = FB_FMA(hv, w.z, acc[i + 2]);
+                    acc[i + 3] = FB_FMA(hv, w.w, acc[i + 3]);
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < M; i++) {
+            const float mval = use_bias ? FB_ADD(acc[i], b2[i]) : acc[i];
+            if (e == e0) red[i] = (reduce <= 1) ? FB_ADD(0.0f, mval) : mval;
+            else if (reduce <= 1) red[i] = FB_ADD(red[i], mval);
+            else if (reduce == 2) red[i] = (mval > red[i]) ? mval : red[i];
+            else red[i] = (mval < red[i]) ? mval : red[i];
+        }
+    }
+    if (reduce == 0 && e1 > e0) {
+        const float dg = (float)(e1 - e0);
+#pragma unroll
+        for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], dg);
+    }
+}
+
+// One thread per (frame, variable node); the 3 923 weights are staged in shared memory and
+// read as broadcast float4s.  Requires H % 4 == 0 and M % 4 == 0.
+template <int H, int M>
+__global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
+    typedef GnnLayout<H, M> Lay;
+    extern __shared__ float w[];
+    for (int i = threadIdx.x; i < Lay::total; i += blockDim.x) w[i] = a.weights[i];
+    __syncthreads();
+    const int n = a.X.n;
+    const int64_t items = a.num_frames * n;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items;
+         it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t fi = it / n;
+        const int v = (int)(it - fi * n);
+        const int64_t b = a.frame_list ? a.frame_list[fi] : fi;
+        const float f1 = a.h_vn(b, v, 0), f2 = a.h_vn(b, v, 1), f3 = a.h_vn(b, v, 2);
+        float in[2 * M + 3];
+        gnn_side<H, M>(a.X, w + Lay::W1x, w + Lay::b1x, w + Lay::W2x, w + Lay::b2x, a.logit_hx, a.sx, b, v,
+                       f1, f2, f3, a.act, a.reduce, a.use_bias, in);
+        gnn_side<H, M>(a.Z, w + Lay::W1z, w + Lay::b1z, w + Lay::W2z, w + Lay::b2z, a.logit_hz, a.sz, b, v,
+                       f1, f2, f3, a.act, a.reduce, a.use_bias, in + M);
+        in[2 * M] = f1; in[2 * M + 1] = f2; in[2 * M + 2] = f3;
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+#pragma unroll 1
+        for (int j = 0; j < H; j += 4) {
+            float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 2 * M + 3; k++) {
+                const float4 wv = *reinterpret_cast<const float4 *>(w + Lay::W3 + k * H + j);
+                h0 = FB_FMA(in[k], wv.x, h0);
+                h1 = FB_FMA(in[k], wv.y, h1);
+                h2 = FB_FMA(in[k], wv.z, h2);
+                h3 = FB_FMA(in[k], wv.w, h3);
+            }
+            if (a.use_bias) {
+                const float4 bb = *reinterpret_cast<const float4 *>(w + Lay::b3 + j);
+                h0 = FB_ADD(h0, bb.x); h1 = FB_ADD(h1, bb.y); h2 = FB_ADD(h2, bb.z); h3 = FB_ADD(h3, bb.w);
+            }
+            const float hh[4] = { gnn_act(a.act, h0), gnn_act(a.act, h1), gnn_act(a.act, h2), gnn_act(a.act, h3) };
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) {
+                const float *w0 = w + Lay::W0 + (j + jj) * 3;
+                o0 = FB_FMA(hh[jj], w0[0], o0);
+                o1 = FB_FMA(hh[jj], w0[1], o1);
+                o2 = FB_FMA(hh[jj], w0[2], o2);
+            }
+        }
+        if (a.use_bias) {
+            o0 = FB_ADD(o0, w[Lay::b0 + 0]); o1 = FB_ADD(o1, w[Lay::b0 + 1]); o2 = FB_ADD(o2, w[Lay::b0 + 2]);
+        }
+        a.out(b, v, 0) = o0; a.out(b, v, 1) = o1; a.out(b, v, 2) = o2;
+    }
+}
+
+// ------------------------------------------------------------------ noise + syndrome --
+struct SampleArgs {
+    SideDev X, Z;                       // Z.n == 0 for the binary (single pcm) pipeline
+    int mode;                           // 0 Pauli depolarising, 1 BSC
+    float thr0, thr1, thr2;             // Pauli thresholds, or thr0 = p for BSC
+    uint64_t seed, first_frame;
+    View2<const uint8_t> nx_in, nz_in;  // optional given noise (b, v)
+    uint8_t *vbits;                     // [B][n] out: bit0 noise_x (or BSC noise), bit1 noise_z
+    uint8_t *sbits;                     // [B][m_x+m_z] out (may be nullptr)
+    View2<uint8_t> nx_out, nz_out;      // optional separate outputs (Pauli / BSC layer API)
+};
+
+// smem: u8 nb[n]
+__global__ void k_sample(const SampleArgs a) {
+    extern __shared__ uint8_t nb[];
+    const int n = a.X.n, T = blockDim.x, tid = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    const uint64_t frame = a.first_frame + (uint64_t)b;
+    if (a.nx_in.ptr) {
+        for (int v = tid; v < n; v += T)
+            nb[v] = (a.nx_in(b, v) ? 1 : 0) | ((a.nz_in.ptr && a.nz_in(b, v)) ? 2 : 0);
+    } else {
+        for (int q4 = tid; q4 < (n + 3) / 4; q4 += T) {
+            uint32_t r[4];
+            philox4x32_10((uint32_t)frame, (uint32_t)(frame >> 32), (uint32_t)q4, (uint32_t)a.mode,
+                          (uint32_t)a.seed, (uint32_t)(a.seed >> 32), r);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int q = q4 * 4 + j;
+                if (q < n) {
+                    const float u = u01(r[j]);
+                    int bits;
+                    if (a.mode == 0) bits = (u < a.thr0 ? 1 : 0) | ((u >= a.thr1 && u < a.thr2) ? 2 : 0);
+                    else bits = (u < a.thr0) ? 1 : 0;
+                    nb[q] = (uint8_t)bits;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (a.vbits) for (int v = tid; v < n; v += T) a.vbits[b * n + v] = nb[v];
+    if (a.nx_out.ptr) for (int v = tid; v < n; v += T) a.nx_out(b, v) = nb[v] & 1;
+    if (a.nz_out.ptr) for (int v = tid; v < n; v += T) a.nz_out(b, v) = (nb[v] >> 1) & 1;
+    if (a.sbits) {
+        uint8_t *sb = a.sbits + b * (a.X.m + a.Z.m);
+        for (int c = tid; c < a.X.m + a.Z.m; c += T) {
+            const bool isx = c < a.X.m;                  // syndrome_x = hx . noise_z (bit1);
+            const SideDev &S = isx ? a.X : a.Z;          // syndrome_z = hz . noise_x (bit0)
+            const int cc = isx ? c : c - a.X.m;
+            const int bit = (isx && a.mode == 0) ? 1 : 0;
+            int par = 0;
+            for (int k = S.cn_ptr[cc]; k < S.cn_ptr[cc + 1]; k++) par ^= (nb[S.cn_vn[k]] >> bit) & 1;
+            sb[c] = (uint8_t)par;
+        }
+    }
+}
+
+struct SyndromeArgs {
+    SideDev S;
+    View2<const uint8_t> noise;         // (b, v)
+    View2<uint8_t> synd;                // (c, b)
+};
+__global__ void k_syndrome(const SyndromeArgs a) {
+    extern __shared__ uint8_t nb[];
+    const int64_t b = blockIdx.x;
+    for (int v = threadIdx.x; v < a.S.n; v += blockDim.x) nb[v] = a.noise(b, v) & 1;
+    __syncthreads();
+    for (int c = threadIdx.x; c < a.S.m; c += blockDim.x) {
+        int par = 0;
+        for (int k = a.S.cn_ptr[c]; k < a.S.cn_ptr[c + 1]; k++) par ^= nb[a.S.cn_vn[k]];
+        a.synd(c, b) = (uint8_t)par;
+    }
+}
+
+// ------------------------------------------------------------------ final checks ------
+struct FinalArgs {
+    SideDev X, Z;                       // binary pipeline: X = pcm, Z.n == 0
+    const uint32_t *lx_bits, *lz_bits;  // [k][W] logical operators (binary: lx_bits = logical pcm rows)
+    int kx, kz;
+    int binary;
+    const uint8_t *vbits;               // [B][n]  (binary: bit0 noise, bit2 hard decision)
+    const uint8_t *rounds;              // [B] or nullptr
+    uint8_t *flags;                     // [B] or nullptr
+    View2<uint8_t> x_diff, z_diff;      // optional (b, v)
+    unsigned long long *counters;       // [4] device: frames, flagged, block, stage-0 failures
+};
+
+// smem: u8 d[n]; u32 xw[W], zw[W]
+__global__ void k_final(const FinalArgs a) {
+    extern __shared__ uint8_t dsm[];
+    const int n = a.X.n, T = blockDim.x, tid = threadIdx.x, W = (n + 31) / 32;
+    const int64_t b = blockIdx.x;
+    uint8_t *d = dsm;
+    uint32_t *xw = (uint32_t *)(dsm + ((n + 3) & ~3)), *zw = xw + W;
+    // residual error after correction (feedback_gnn.py:346-347): bit0 x_diff, bit1 z_diff
+    const int nround = ((n + 31) / 32) * 32;
+    for (int v = tid; v < nround; v += T) {
+        int bits = 0;
+        if (v < n) {
+            const int vb = a.vbits[b * n + v];
+            bits = ((vb >> 2) ^ vb) & 3;
+            d[v] = (uint8_t)bits;
+            if (a.x_diff.ptr) a.x_diff(b, v) = bits & 1;
+            if (a.z_diff.ptr) a.z_diff(b, v) = (bits >> 1) & 1;
+        }
+        const uint32_t bx = __ballot_sync(0xffffffffu, bits & 1), bz = __ballot_sync(0xffffffffu, bits & 2);
+        if ((tid & 31) == 0) { xw[v >> 5] = bx; zw[v >> 5] = bz; }
+    }
+    __syncthreads();
+    int flagged = 0;
+    for (int c = tid; c < a.X.m + a.Z.m; c += T) {
+        const bool isx = c < a.X.m;                      // hx checks z_diff (quaternary) / the noise (binary)
+        const SideDev &S = isx ? a.X : a.Z;
+        const int cc = isx ? c : c - a.X.m;
+        const int bit = (isx && !a.binary) ? 1 : 0;
+        int par = 0;
+        for (int k = S.cn_ptr[cc]; k < S.cn_ptr[cc + 1]; k++) par ^= (d[S.cn_vn[k]] >> bit) & 1;
+        flagged |= par;
+    }
+    // logical operators: any(lz . x_diff) or any(lx . z_diff); one warp per row
+    int logical = 0;
+    const int warp = tid >> 5, lane = tid & 31, nwarps = T >> 5;
+    for (int r = warp; r < a.kx + a.kz; r += nwarps) {
+        const bool isz = r >= a.kx;                      // rows of lz act on x_diff
+        const uint32_t *row = isz ? a.lz_bits + (int64_t)(r - a.kx) * W : a.lx_bits + (int64_t)r * W;
+        const uint32_t *dw = (isz || a.binary) ? xw : zw;
+        uint32_t acc = 0;
+        for (int wi = lane; wi < W; wi += 32) acc ^= row[wi] & dw[wi];
+        acc = __reduce_xor_sync(0xffffffffu, acc);
+        logical |= __popc(acc) & 1;
+    }
+    flagged = __syncthreads_or(flagged);
+    logical = __syncthreads_or(logical);
+    if (tid == 0) {
+        const int blk = flagged | logical | ((a.binary && a.kx == 0) ? flagged : 0);
+        const int rnd = a.rounds ? a.rounds[b] : 0;
+        if (a.flags) a.flags[b] = (uint8_t)((flagged ? 1 : 0) | (blk ? 2 : 0) | (rnd << 2));
+        if (a.counters) {
+            atomicAdd(a.counters + 0, 1ull);
+            if (flagged) atomicAdd(a.counters + 1, 1ull);
+            if (blk) atomicAdd(a.counters + 2, 1ull);
+            if (rnd > 0) atomicAdd(a.counters + 3, 1ull);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ probes ------------
+__global__ void k_math_probe(int fn, const float *x, float *y, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = x[i];
+    float r;
+    switch (fn) {
+        case 0: r = fb_expf(v); break;
+        case 1: r = fb_logf(v); break;
+        case 2: r = fb_log1pf_pos(v); break;
+        case 3: r = fb_softplusf(v); break;
+        case 4: r = fb_phi4f(v); break;
+        case 5: r = fb_phi2f(v); break;
+        case 6: r = fb_tanhf(v); break;
+        default: r = fb_atanhf(v); break;
+    }
+    y[i] = r;
+}
+
+// MUFU throughput: chains of ex2.approx, 8 independent chains per thread
+__global__ void k_sfu_peak(float *out, int iters) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = -1.0f - 0.001f * (float)(threadIdx.x + j);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(v[j]));
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += v[j];
+    if (s == 123.456f) out[0] = s;
+}
+
+// FP32 FMA issue rate: 8 independent FFMA chains per thread
+__global__ void k_fma_peak(float *out, int iters) {
+    float v[8];
+    const float a = 0.999f + 1e-6f * (float)threadIdx.x, c = 1e-3f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) v[j] = 0.5f + 0.01f * (float)j;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = __fmaf_rn(v[j], a, c);
+    }
+    float s = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 8; j++) s += v[j];
+    if (s == 123.456f) out[0] = s;
+}
+
+__global__ void k_fill(uint32_t *p, int64_t n, uint32_t v) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = v;
+}
+
+}  // namespace fbgnn

@@ -1,0 +1,151 @@
+"""Quaternary (BP4) syndrome decoder for CSS codes -- the ``QLDPCBPDecoder`` layer.
+
+Same constructor arguments and call contract as the reference's Keras layer
+(``sionna/fec/ldpc/decoding_q.py:14-111`` ``__init__``, ``:661-797`` ``call``); the decoding
+itself runs in the CUDA kernel ``k_bp4`` behind ``fbgnn_bp4_decode`` (messages resident in
+shared memory for all ``num_iter`` iterations).
+
+    decoder = QLDPCBPDecoder(code, num_iter=64, normalization_factor=1.0,
+                             cn_type="boxplus-phi", stage_one=True)
+    llrx, llry, llrz, x_hat, z_hat, x_logit, z_logit = decoder((llr_ch, syndrome_x, syndrome_z))
+
+Inputs: ``llr_ch`` float32 ``[B,3,n]`` (x, y, z priors, ``log p_I/p_P``), ``syndrome_x``
+``[m_x,B]`` and ``syndrome_z`` ``[m_z,B]`` with 0/1 entries.  Each may be a numpy array (copied
+to the GPU) or a DLPack-capable CUDA tensor / ``DeviceArray`` (used in place).  If any input
+is a device tensor the outputs are ``DeviceArray`` objects, otherwise numpy arrays with the
+reference's dtypes (``x_hat`` int64, ``z_hat`` float64).
+"""
+import numpy as np
+
+from . import _ffi
+
+CN_TYPES = {"boxplus-phi": 0, "boxplus": 1, "minsum": 2}
+
+
+def _is_device(x):
+    return isinstance(x, _ffi.DeviceArray) or (
+        not isinstance(x, np.ndarray) and hasattr(x, "__dlpack_device__") and x.__dlpack_device__()[0] == 2)
+
+
+class QLDPCBPDecoder:
+    def __init__(self,
+                 code,
+                 trainable=False,
+                 cn_type='boxplus',
+                 hard_out=True,
+                 track_exit=False,
+                 num_iter=32,
+                 normalization_factor=0.625,
+                 output_dtype=np.float32,
+                 loss_type='boxplus-phi',
+                 stage_one=False,
+                 stage_two=False,
+                 ctx=None,
+                 **kwargs):
+        if cn_type not in CN_TYPES:
+            raise ValueError('Unknown node type.')
+        if trainable or stage_two:
+            raise NotImplementedError("trainable / stage_two (per-iteration soft syndromes for training) "
+                                      "are outside the inference hot path of this build")
+        self._code = code
+        self._cn_type = cn_type
+        self._hard_out = hard_out
+        self._track_exit = track_exit
+        self._num_iter = int(num_iter)
+        self._normalization_factor = float(normalization_factor)
+        self._output_dtype = output_dtype
+        self._loss_type = loss_type
+        self._stage_one = stage_one
+        self._stage_two = stage_two
+        self._trainable = trainable
+        self._num_cns_x = code.hx.shape[0]
+        self._num_cns_z = code.hz.shape[0]
+        self._num_vns = code.hx.shape[1]
+        self._ctx = ctx
+        self._dev = None
+
+    # properties the evaluation model reads to fuse the pipeline
+    @property
+    def num_iter(self):
+        return self._num_iter
+
+    @property
+    def normalization_factor(self):
+        return self._normalization_factor
+
+    @property
+    def cn_type(self):
+        return self._cn_type
+
+    @property
+    def code(self):
+        return self._code
+
+    def _device(self):
+        if self._dev is None:
+            self._dev = _ffi.device_code(self._code, self._ctx)
+        return self._dev
+
+    def __call__(self, inputs):
+        llr_ch, syndrome_x, syndrome_z = inputs
+        dev = self._device()
+        ctx = dev.ctx
+        n, mx, mz = dev.n, dev.mx, dev.mz
+        on_device = any(_is_device(t) for t in (llr_ch, syndrome_x, syndrome_z))
+        if not _is_device(llr_ch):
+            llr_ch = np.asarray(llr_ch)
+            if llr_ch.dtype != np.float32:
+                raise TypeError('Invalid input dtype.')
+        llr = ctx.asarray(llr_ch, np.float32)
+        if llr.ndim != 3 or llr.shape[1] != 3 or llr.shape[2] != n:
+            raise ValueError('Last dimension must be of length n.')
+        B = llr.shape[0]
+        sx = ctx.asarray(_to_u8(syndrome_x), np.uint8)
+        sz = ctx.asarray(_to_u8(syndrome_z), np.uint8)
+        if sx.shape != (mx, B) or sz.shape != (mz, B):
+            raise ValueError(f"syndromes must have shapes [{mx},{B}] and [{mz},{B}]")
+        out = self.decode_device(llr, sx, sz, want_logits=self._stage_one)
+        Lx, Ly, Lz, xh, zh, xl, zl = out
+        if self._stage_one:
+            if on_device:
+                return Lx, Ly, Lz, xh, zh, xl, zl
+            return (Lx.numpy(), Ly.numpy(), Lz.numpy(), xh.numpy().astype(np.int64),
+                    zh.numpy().astype(np.float64), xl.numpy(), zl.numpy())
+        if on_device:
+            return xh, zh
+        return xh.numpy().astype(np.int64), zh.numpy().astype(np.float64)
+
+    call = __call__
+
+    def decode_device(self, llr, sx, sz, want_logits=True, want_msgs=False, prior=None):
+        """Device-level entry: ``llr`` DeviceArray [B,3,n] (or None with a scalar ``prior``),
+        syndromes DeviceArray [m,B].  Returns DeviceArrays (Lx, Ly, Lz [B,n] f32, x_hat, z_hat
+        [B,n] u8, x_logit [m_z,B], z_logit [m_x,B] f32 or None) (+ msg_x, msg_z [B,E])."""
+        dev = self._device()
+        ctx = dev.ctx
+        n, mx, mz = dev.n, dev.mx, dev.mz
+        B = sx.shape[1]
+        Lx, Ly, Lz = (ctx.empty((B, n), np.float32) for _ in range(3))
+        xh, zh = ctx.empty((B, n), np.uint8), ctx.empty((B, n), np.uint8)
+        xl = zl = None
+        if want_logits:
+            # frame-major storage, exposed in the reference's [m, B] orientation
+            xl = ctx.empty((B, mz), np.float32).T
+            zl = ctx.empty((B, mx), np.float32).T
+        msgs = ()
+        if want_msgs:
+            msgs = (ctx.empty((B, dev.Ex), np.float32), ctx.empty((B, dev.Ez), np.float32))
+        t2 = lambda a: a.t2() if a is not None else _ffi.NULL2
+        _ffi.call("fbgnn_bp4_decode", dev.handle, CN_TYPES[self._cn_type], self._num_iter,
+                  self._normalization_factor, B,
+                  llr.t3() if llr is not None else _ffi.NULL3, float(prior or 0.0),
+                  sx.t2(), sz.t2(), Lx.t2(), Ly.t2(), Lz.t2(), xh.t2(), zh.t2(), t2(xl), t2(zl),
+                  msgs[0].t2() if want_msgs else _ffi.NULL2, msgs[1].t2() if want_msgs else _ffi.NULL2)
+        return (Lx, Ly, Lz, xh, zh, xl, zl) + msgs
+
+
+def _to_u8(s):
+    if _is_device(s):
+        return s
+    s = np.asarray(s)
+    return s.astype(np.uint8) if s.dtype != np.uint8 else s

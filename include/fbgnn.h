@@ -1,0 +1,221 @@
+/* fbgnn.h -- C ABI of libfbgnn.so: the B200 (sm_100a) implementation of Feedback-GNN's
+ * BP -> feedback-GNN -> BP hot path.
+ *
+ * The reference (gongaa/Feedback-GNN) has no FFI of its own: its "operator API" for this
+ * path is the Python call surface of a handful of Keras layers/models.  Each entry point
+ * below is what a binding for one of those calls needs; the Python host side
+ * (feedback-gnn_b200/fbgnn/) binds them with ctypes and mirrors the reference classes.
+ *
+ *   fbgnn_code_create        <- css_code / QLDPCBPDecoder.__init__ edge tables
+ *                               sionna/fec/ldpc/codes_q.py:8-49, decoding_q.py:58-94
+ *   fbgnn_graph_create       <- LDPCBPDecoder.__init__ edge tables       decoding.py:325-347
+ *   fbgnn_bp4_decode         <- QLDPCBPDecoder.call                      decoding_q.py:661-797
+ *   fbgnn_bp2_decode         <- LDPCBPDecoder.call (is_syndrome)         decoding.py:875-1048
+ *   fbgnn_gnn_create/_forward<- Feedback_GNN.build / .call, set_weights  feedback_gnn.py:110-188
+ *   fbgnn_pauli_sample       <- Pauli.call (non-wt branch)               channel/pauli.py:98-108
+ *   fbgnn_bsc_sample         <- BinarySymmetricChannel.call              channel/discrete_channel.py:385-396
+ *   fbgnn_syndrome           <- int_mod_2(tf.matmul(H, noise))           feedback_gnn.py:308-309
+ *   fbgnn_pipeline_run       <- Sandwich_BP_GNN_Evaluation_Model.call    feedback_gnn.py:293-361
+ *   fbgnn_bsc_pipeline_run   <- BP_BSC_Model.call                        feedback_gnn.py:207-229
+ *
+ * Conventions
+ *   - Every function returns 0 on success or a negative FBGNN_E_* code; the message is
+ *     available from fbgnn_last_error() (thread-local).  No exception crosses the ABI.
+ *   - Handles are opaque, created/destroyed by the caller, and not thread-safe
+ *     individually: use one context per GPU per host thread.
+ *   - All tensor arguments are DEVICE pointers on the context's GPU (the host side moves
+ *     numpy arrays with fbgnn_memcpy_* and exchanges device tensors zero-copy via DLPack);
+ *     they are borrowed for the duration of the call.  A tensor is described by its base
+ *     pointer and explicit ELEMENT strides (fbgnn_tensor2/3), so the reference's layouts
+ *     ([B,3,n] priors, [m,B] syndromes/logits, transposed views) need no copies.
+ *   - Work is enqueued on the context's stream; functions that return host data
+ *     synchronise that stream, the others are asynchronous (fbgnn_ctx_sync to wait).
+ *   - There is no CPU fallback: without a CUDA device every compute entry point fails
+ *     with FBGNN_E_CUDA.
+ */
+#ifndef FBGNN_H
+#define FBGNN_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FBGNN_VERSION 100            /* 0.1.0 */
+
+#define FBGNN_OK            0
+#define FBGNN_E_INVALID    -1        /* bad argument */
+#define FBGNN_E_CUDA       -2        /* CUDA runtime error (message has the detail) */
+#define FBGNN_E_UNSUPPORTED -3       /* valid request this build cannot serve (e.g. code too large) */
+#define FBGNN_E_NOMEM      -4
+
+/* check-node update of the BP decoders (cn_type of the reference's decoders) */
+#define FBGNN_CN_PHI     0           /* "boxplus-phi" */
+#define FBGNN_CN_TANH    1           /* "boxplus"     */
+#define FBGNN_CN_MINSUM  2           /* "minsum"      */
+
+/* Feedback_GNN options */
+#define FBGNN_ACT_TANH   0
+#define FBGNN_ACT_RELU   1
+#define FBGNN_ACT_LINEAR 2
+#define FBGNN_REDUCE_MEAN 0
+#define FBGNN_REDUCE_SUM  1
+#define FBGNN_REDUCE_MAX  2
+#define FBGNN_REDUCE_MIN  3
+
+typedef struct fbgnn_ctx   fbgnn_ctx;     /* one GPU: stream, scratch, timers            */
+typedef struct fbgnn_graph fbgnn_graph;   /* Tanner graph of one parity-check matrix     */
+typedef struct fbgnn_code  fbgnn_code;    /* CSS code: graphs of hx, hz + logicals lx,lz */
+typedef struct fbgnn_gnn   fbgnn_gnn;     /* one Feedback_GNN weight set                 */
+
+/* strided views (strides in ELEMENTS; ptr == NULL means "absent") */
+typedef struct { void *ptr; int64_t s0, s1; } fbgnn_tensor2;
+typedef struct { void *ptr; int64_t s0, s1, s2; } fbgnn_tensor3;
+
+/* ---- library / context ------------------------------------------------------------ */
+int fbgnn_version(void);
+const char *fbgnn_last_error(void);
+int fbgnn_device_count(int *count);
+int fbgnn_ctx_create(int device, fbgnn_ctx **ctx);
+int fbgnn_ctx_destroy(fbgnn_ctx *ctx);
+int fbgnn_ctx_sync(fbgnn_ctx *ctx);
+int fbgnn_ctx_device(fbgnn_ctx *ctx, int *device, int *num_sms, char *name, int name_len);
+/* CUDA-event timer on the context's stream (what bench.py times kernels with) */
+int fbgnn_timer_start(fbgnn_ctx *ctx);
+int fbgnn_timer_stop(fbgnn_ctx *ctx, float *elapsed_ms);          /* synchronises */
+/* number of kernel launches this context has enqueued so far */
+int fbgnn_launch_count(fbgnn_ctx *ctx, int64_t *launches);
+
+/* ---- memory ------------------------------------------------------------------------ */
+int fbgnn_malloc(fbgnn_ctx *ctx, size_t bytes, void **dptr);
+int fbgnn_free(fbgnn_ctx *ctx, void *dptr);
+int fbgnn_memset(fbgnn_ctx *ctx, void *dptr, int value, size_t bytes);             /* async */
+int fbgnn_memcpy_h2d(fbgnn_ctx *ctx, void *dst, const void *src, size_t bytes);   /* async w.r.t. host only for pinned src */
+int fbgnn_memcpy_d2h(fbgnn_ctx *ctx, void *dst, const void *src, size_t bytes);   /* synchronises */
+int fbgnn_memcpy_d2d(fbgnn_ctx *ctx, void *dst, const void *src, size_t bytes);   /* async */
+int fbgnn_host_alloc(size_t bytes, void **hptr);                                  /* pinned */
+int fbgnn_host_free(void *hptr);
+/* write a buffer larger than L2 (bench.py uses it between timed iterations) */
+int fbgnn_flush_l2(fbgnn_ctx *ctx);
+
+/* ---- code / graph ------------------------------------------------------------------- */
+/* CSR of a binary matrix: indptr[rows+1], indices[nnz] (column indices, increasing per row),
+ * host pointers, copied. */
+int fbgnn_graph_create(fbgnn_ctx *ctx, int32_t n, int32_t m, const int32_t *indptr,
+                       const int32_t *indices, fbgnn_graph **graph);
+int fbgnn_graph_destroy(fbgnn_graph *graph);
+/* hx [m_x,n], hz [m_z,n], logical operators lx [k_x,n], lz [k_z,n], all CSR, host pointers */
+int fbgnn_code_create(fbgnn_ctx *ctx, int32_t n,
+                      int32_t m_x, const int32_t *hx_indptr, const int32_t *hx_indices,
+                      int32_t m_z, const int32_t *hz_indptr, const int32_t *hz_indices,
+                      int32_t k_x, const int32_t *lx_indptr, const int32_t *lx_indices,
+                      int32_t k_z, const int32_t *lz_indptr, const int32_t *lz_indices,
+                      fbgnn_code **code);
+int fbgnn_code_destroy(fbgnn_code *code);
+/* number of edges of hx and hz (message array lengths) */
+int fbgnn_code_edges(fbgnn_code *code, int32_t *e_x, int32_t *e_z);
+
+/* ---- noise sources ------------------------------------------------------------------- */
+/* Pauli.call, non-wt branch.  thr = {px, px - py, (px + pz) - py} as float32.  Uniforms
+ * come from Philox4x32-10: key = seed, counter = (global frame id, qubit/4, stream 0).
+ * noise_x/noise_z: uint8 [B,n] views. */
+int fbgnn_pauli_sample(fbgnn_ctx *ctx, int32_t n, int64_t B, const float thr[3], uint64_t seed,
+                       uint64_t first_frame, fbgnn_tensor2 noise_x, fbgnn_tensor2 noise_z);
+/* Bernoulli(p) flips (stream 1 of the same generator). noise: uint8 [B,n] */
+int fbgnn_bsc_sample(fbgnn_ctx *ctx, int32_t n, int64_t B, float p, uint64_t seed,
+                     uint64_t first_frame, fbgnn_tensor2 noise);
+/* syndrome[c,b] = XOR_{v in row c} noise[b,v].  noise: uint8 view indexed (b,v);
+ * syndrome: uint8 view indexed (c,b). */
+int fbgnn_syndrome(fbgnn_graph *graph, int64_t B, fbgnn_tensor2 noise, fbgnn_tensor2 syndrome);
+
+/* ---- decoders ------------------------------------------------------------------------ */
+/* QLDPCBPDecoder.call.
+ *   llr        float32 view indexed (b, k in {x,y,z}, v); NULL ptr -> constant `prior`
+ *   synd_x/z   uint8 views indexed (c, b)
+ *   Lx,Ly,Lz   float32 views indexed (b, v)                       (marginals)
+ *   x_hat,z_hat uint8 views indexed (b, v)                        (argmin decision)
+ *   x_logit    float32 view indexed (row of hz, b), z_logit (row of hx, b): the stage_one
+ *              soft syndromes; NULL ptr -> not computed
+ *   msg_x/msg_z float32 views indexed (b, edge) receiving the final check-to-variable
+ *              messages in VN-sorted edge order (teacher-forced parity tests); NULL -> skipped
+ */
+int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                     fbgnn_tensor3 llr, float prior, fbgnn_tensor2 synd_x, fbgnn_tensor2 synd_z,
+                     fbgnn_tensor2 Lx, fbgnn_tensor2 Ly, fbgnn_tensor2 Lz,
+                     fbgnn_tensor2 x_hat, fbgnn_tensor2 z_hat,
+                     fbgnn_tensor2 x_logit, fbgnn_tensor2 z_logit,
+                     fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z);
+
+/* LDPCBPDecoder.call with is_syndrome.  llr: float32 logits (b,v); synd: uint8 (c,b) or
+ * NULL ptr (no syndrome); soft: float32 (b,v) output logits; hard: uint8 (b,v) or NULL. */
+int fbgnn_bp2_decode(fbgnn_graph *graph, int32_t cn_type, int32_t num_iter, float factor,
+                     int64_t B, fbgnn_tensor2 llr, fbgnn_tensor2 synd, fbgnn_tensor2 soft,
+                     fbgnn_tensor2 hard);
+
+/* ---- feedback GNN --------------------------------------------------------------------- */
+/* Weights in Keras get_weights() order, host float32 pointers (copied); bias pointers may
+ * be NULL when use_bias is False.  Shapes: W0[H,3] b0[3] W1x[4,H] b1x[H] W2x[H,M] b2x[M]
+ * W1z[4,H] b1z[H] W2z[H,M] b2z[M] W3[2M+3,H] b3[H].  This build supports 2-layer MLPs. */
+int fbgnn_gnn_create(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t activation, int32_t reduce_op,
+                     const float *W0, const float *b0, const float *W1x, const float *b1x,
+                     const float *W2x, const float *b2x, const float *W1z, const float *b1z,
+                     const float *W2z, const float *b2z, const float *W3, const float *b3,
+                     fbgnn_gnn **gnn);
+int fbgnn_gnn_destroy(fbgnn_gnn *gnn);
+/* Feedback_GNN.call.  h_vn float32 (b, v, k); logit_hx (row of hx, b), logit_hz (row of hz, b);
+ * synd_x/z uint8 (c, b); out float32 (b, v, k). */
+int fbgnn_gnn_forward(fbgnn_code *code, fbgnn_gnn *gnn, int64_t B, fbgnn_tensor3 h_vn,
+                      fbgnn_tensor2 logit_hx, fbgnn_tensor2 logit_hz, fbgnn_tensor2 synd_x,
+                      fbgnn_tensor2 synd_z, fbgnn_tensor3 out);
+
+/* ---- fused Monte-Carlo pipelines ------------------------------------------------------- */
+typedef struct {
+    int32_t num_stages;        /* num_layers of the reference = 1 + GNN rounds              */
+    const int32_t *num_iter;   /* [num_stages] host                                          */
+    const float *factor;       /* [num_stages] host                                          */
+    const int32_t *cn_type;    /* [num_stages] host                                          */
+    fbgnn_gnn *const *gnn;     /* [num_stages-1] host array of handles                       */
+    float prior;               /* log(3(1-p0)/p0) as float32                                 */
+    float thr[3];              /* Pauli thresholds, see fbgnn_pauli_sample                   */
+    int32_t skip_inactive;     /* 0: all frames run all rounds (reference-equivalent work)   */
+                               /* 1: frames whose decision matches the syndrome stop early   */
+                               /*    (result-identical; the reference masks the scatter)     */
+} fbgnn_pipeline_cfg;
+
+/* Sandwich_BP_GNN_Evaluation_Model.call on global frames [first_frame, first_frame+B).
+ *   noise_x/noise_z  optional uint8 (b,v) device views used instead of sampling
+ *   flags            optional uint8 [B] device: bit0 flagged, bit1 block error,
+ *                    bits 2..7 number of GNN rounds the frame was active in
+ *   x_diff/z_diff    optional uint8 (b,v) device views: residual error after correction
+ *   counters         optional HOST int64[4]: {frames, flagged, block errors, frames that
+ *                    failed stage 0}; when given, the call synchronises
+ */
+int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cfg, uint64_t seed,
+                       uint64_t first_frame, int64_t B, fbgnn_tensor2 noise_x,
+                       fbgnn_tensor2 noise_z, uint8_t *flags, fbgnn_tensor2 x_diff,
+                       fbgnn_tensor2 z_diff, int64_t *counters);
+
+/* BP_BSC_Model.call: Bernoulli(p) noise, syndrome with `graph`, binary BP from the constant
+ * logit llr_const, residual syndrome + logical check against `logical` (may be NULL: block
+ * error = flagged).  flags/counters as above. */
+int fbgnn_bsc_pipeline_run(fbgnn_graph *graph, fbgnn_graph *logical, int32_t cn_type,
+                           int32_t num_iter, float factor, float llr_const, float p, uint64_t seed,
+                           uint64_t first_frame, int64_t B, fbgnn_tensor2 noise, uint8_t *flags,
+                           int64_t *counters);
+
+/* ---- measurement helpers ---------------------------------------------------------------- */
+/* Measured MUFU (ex2.approx) throughput of the device in transcendental evaluations / s:
+ * the SFU roofline denominator of SURVEY.md 8(d). */
+int fbgnn_sfu_peak(fbgnn_ctx *ctx, double *evals_per_s);
+/* Measured FP32 FMA issue rate (thread-instructions / s), the bound of the exact-arithmetic path */
+int fbgnn_fma_peak(fbgnn_ctx *ctx, double *instr_per_s);
+/* Elementwise probes of the arithmetic specification (tests): fn in {"exp","log","log1p",
+ * "softplus","phi4","phi2","tanh","atanh"}; x,y device float32 [n]. */
+int fbgnn_math_probe(fbgnn_ctx *ctx, const char *fn, const float *x, float *y, int64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FBGNN_H */

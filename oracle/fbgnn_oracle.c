@@ -1,0 +1,697 @@
+/* fbgnn_oracle.c -- CPU ORACLE for the BP -> feedback-GNN -> BP hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product (feedback-gnn_b200/) calls, links or
+ * imports this file; it is used by tests/, by __graft_entry__.smoke() and by bench.py's
+ * cpu_baseline / --impl reference legs as the CHECKER and the CPU baseline.
+ *
+ * It is a plain-C restatement of the reference's algorithm, function by function:
+ *   orc_bp4      QLDPCBPDecoder.call            sionna/fec/ldpc/decoding_q.py:661-797
+ *                  _vn_update                   decoding_q.py:227-275
+ *                  _cn_update_phi / _phi        decoding_q.py:365-431
+ *                  _cn_update_tanh              decoding_q.py:313-363
+ *                  _cn_update_minsum            decoding_q.py:539-644
+ *                  cal_logit/_cn_update_phi_loss decoding_q.py:433-471
+ *   orc_bp2      LDPCBPDecoder.call (syndrome)  sionna/fec/ldpc/decoding.py:875-1048
+ *                  _vn_update 511-535, _cn_update_phi 635-690, _phi 625-633
+ *   orc_gnn      Feedback_GNN.call              sionna/fec/ldpc/feedback_gnn.py:161-188, gnn.py:31-69
+ *   orc_pauli    Pauli.call (non-wt)            sionna/channel/pauli.py:98-108
+ *   orc_pipeline Sandwich_BP_GNN_Evaluation_Model.call   feedback_gnn.py:293-361
+ *   orc_bsc_pipeline BP_BSC_Model.call          feedback_gnn.py:207-229
+ *
+ * PARITY STATUS: "parity unpinned" by a live run of the reference -- TensorFlow is not
+ * installable in this image, so the reference cannot be executed.  The
+ * oracle is pinned instead by the reference's stored notebook outputs: the deterministic
+ * known answers (phi values, first-stage marginal extrema of examples/n1270.ipynb cell 12)
+ * and the logical-error-rate tables (binomial confidence intervals); see tests/.
+ *
+ * Arithmetic: float32 throughout, every elementary function taken from
+ * feedback-gnn_b200/csrc/fb_math.h (the arithmetic specification shared with the CUDA
+ * kernels, which makes GPU-vs-oracle comparisons bit-exact).  An independent numpy
+ * restatement (oracle/np_oracle.py, numpy's own exp/log/tanh) cross-checks that header.
+ *
+ * Edge ordering (the reference leaves it to an unstable argsort, decoding_q.py:63-85):
+ * VN order = edges sorted by (vn, cn); CN order = edges sorted by (cn, vn); all sums and
+ * products run sequentially in that order.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "fb_math.h"
+
+#define ORC_CN_PHI    0
+#define ORC_CN_TANH   1
+#define ORC_CN_MINSUM 2
+
+typedef struct {
+    int32_t n, m, E;
+    const int32_t *vn_ptr;   /* [n+1] edge ranges per VN, edges sorted by (vn, cn)          */
+    const int32_t *vn_cn;    /* [E]   check index of each edge (VN order)                   */
+    const int32_t *cn_ptr;   /* [m+1] edge ranges per CN, edges sorted by (cn, vn)          */
+    const int32_t *cn_edge;  /* [E]   position in VN order of each edge listed in CN order  */
+    const int32_t *cn_vn;    /* [E]   variable index of each edge listed in CN order        */
+} orc_side_t;
+
+typedef struct {             /* sparse rows of a binary matrix (perp matrices, logicals)    */
+    int32_t m;
+    const int32_t *ptr;      /* [m+1] */
+    const int32_t *col;      /* [nnz] increasing within a row */
+} orc_rows_t;
+
+typedef struct {             /* Feedback_GNN weights, Keras get_weights() order             */
+    int32_t H, M;            /* hidden units, message dims                                  */
+    int32_t act;             /* 0 tanh, 1 relu, 2 linear                                    */
+    int32_t reduce;          /* 0 mean, 1 sum, 2 max, 3 min                                 */
+    const float *W0, *b0;    /* [H,3], [3]     _llr_inv_embed                               */
+    const float *W1x, *b1x;  /* [4,H], [H]     vn_msg_mlp_x layer 0                         */
+    const float *W2x, *b2x;  /* [H,M], [M]     vn_msg_mlp_x layer 1                         */
+    const float *W1z, *b1z, *W2z, *b2z;
+    const float *W3, *b3;    /* [2M+3,H], [H]  vn_embed_mlp                                 */
+} orc_gnn_t;
+
+/* ---------------------------------------------------------------- Philox4x32-10 ---- */
+/* Salmon et al., "Parallel random numbers: as easy as 1, 2, 3" (SC'11). */
+static void philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; r++) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+void orc_philox4x32_10(const uint32_t *ctr, const uint32_t *key, uint32_t *out) {
+    philox4x32_10(ctr, key, out);
+}
+
+/* uniform in [0,1) of qubit q of global frame f: word (q & 3) of Philox(ctr = {f_lo, f_hi,
+ * q >> 2, stream}, key = {seed_lo, seed_hi}), top 24 bits scaled by 2^-24. */
+static float frame_uniform(uint64_t seed, uint64_t frame, uint32_t q, uint32_t stream) {
+    uint32_t ctr[4] = { (uint32_t)frame, (uint32_t)(frame >> 32), q >> 2, stream };
+    uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    uint32_t r[4];
+    philox4x32_10(ctr, key, r);
+    return (float)(r[q & 3] >> 8) * 5.9604644775390625e-08f;
+}
+
+/* Pauli.call, non-wt branch (pauli.py:98-108).  thr = {px, px - py, (px + pz) - py} in f32. */
+static void pauli_frame(uint64_t seed, uint64_t frame, int n, const float thr[3],
+                        uint8_t *nx, uint8_t *nz) {
+    for (int q = 0; q < n; q++) {
+        float u = frame_uniform(seed, frame, (uint32_t)q, 0u);
+        nx[q] = (uint8_t)(u < thr[0]);
+        nz[q] = (uint8_t)((u >= thr[1]) && (u < thr[2]));
+    }
+}
+
+void orc_pauli(uint64_t seed, uint64_t first_frame, int64_t B, int n, const float *thr,
+               uint8_t *noise_x, uint8_t *noise_z) {
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < B; b++)
+        pauli_frame(seed, first_frame + (uint64_t)b, n, thr, noise_x + b * n, noise_z + b * n);
+}
+
+/* BinarySymmetricChannel (discrete_channel.py:385-396): a Bernoulli(p) flip per bit.  The
+ * reference draws it with a Gumbel-softmax trick; statistically it is u < p. */
+static void bsc_frame(uint64_t seed, uint64_t frame, int n, float p, uint8_t *noise) {
+    for (int q = 0; q < n; q++)
+        noise[q] = (uint8_t)(frame_uniform(seed, frame, (uint32_t)q, 1u) < p);
+}
+
+void orc_bsc(uint64_t seed, uint64_t first_frame, int64_t B, int n, float p, uint8_t *noise) {
+#pragma omp parallel for schedule(static)
+    for (int64_t b = 0; b < B; b++)
+        bsc_frame(seed, first_frame + (uint64_t)b, n, p, noise + b * n);
+}
+
+/* syndrome of one frame: s[c] = XOR over the check's variables (int_mod_2(H @ e)) */
+static void syndrome_frame(const orc_side_t *S, const uint8_t *e, uint8_t *s) {
+    for (int c = 0; c < S->m; c++) {
+        uint8_t a = 0;
+        for (int k = S->cn_ptr[c]; k < S->cn_ptr[c + 1]; k++) a ^= e[S->cn_vn[k]];
+        s[c] = a;
+    }
+}
+
+static int rows_any_parity(const orc_rows_t *R, const uint8_t *e) {
+    for (int r = 0; r < R->m; r++) {
+        uint8_t a = 0;
+        for (int k = R->ptr[r]; k < R->ptr[r + 1]; k++) a ^= e[R->col[k]];
+        if (a) return 1;
+    }
+    return 0;
+}
+
+/* ---------------------------------------------------------------- check nodes ------ */
+/* One side, all checks.  msg holds v2c on entry and c2v on exit (VN order, in place).
+ * phi4 != 0 selects the quaternary decoder's phi, else the binary decoder's. */
+static void cn_update(const orc_side_t *S, int cn_type, int phi4, float factor,
+                      const uint8_t *synd, float *msg, float *work) {
+    for (int c = 0; c < S->m; c++) {
+        const int k0 = S->cn_ptr[c], k1 = S->cn_ptr[c + 1];
+        const float ssign = (synd && synd[c]) ? -1.0f : 1.0f;
+        if (cn_type == ORC_CN_PHI) {
+            /* decoding_q.py:392-429 */
+            float sgn = 1.0f, T = 0.0f;
+            for (int k = k0; k < k1; k++) {
+                float m = msg[S->cn_edge[k]];
+                if (m < 0.0f) sgn = -sgn;
+                float a = phi4 ? fb_phi4f(fabsf(m)) : fb_phi2f(fabsf(m));
+                work[k - k0] = a;
+                T = FB_ADD(T, a);
+            }
+            sgn = sgn * ssign;
+            for (int k = k0; k < k1; k++) {
+                int e = S->cn_edge[k];
+                float s = (msg[e] < 0.0f) ? -sgn : sgn;
+                float x = FB_SUB(T, work[k - k0]);
+                float v = phi4 ? fb_phi4f(x) : fb_phi2f(x);
+                msg[e] = FB_MUL(FB_MUL(s, v), factor);
+            }
+        } else if (cn_type == ORC_CN_TANH) {
+            /* decoding_q.py:327-361 */
+            float P = 1.0f;
+            for (int k = k0; k < k1; k++) {
+                float t = fb_tanhf(FB_MUL(msg[S->cn_edge[k]], 0.5f));
+                if (t == 0.0f) t = 1e-12f;
+                work[k - k0] = t;
+                P = FB_MUL(P, t);
+            }
+            P = FB_MUL(P, ssign);
+            for (int k = k0; k < k1; k++) {
+                float v = FB_MUL(FB_DIV(1.0f, work[k - k0]), P);
+                if (fabsf(v) < 1e-7f) v = 0.0f;
+                v = FB_FMIN(FB_FMAX(v, -FB_ATANH_CLIP), FB_ATANH_CLIP);
+                v = FB_MUL(2.0f, fb_atanhf(v));
+                msg[S->cn_edge[k]] = FB_MUL(v, factor);
+            }
+        } else {
+            /* min-sum, decoding_q.py:551-642 */
+            const float LARGE = 10000.0f;
+            float sgn = 1.0f, mn = INFINITY;
+            for (int k = k0; k < k1; k++) {
+                float m = msg[S->cn_edge[k]];
+                m = FB_FMIN(FB_FMAX(m, -FB_LLR_MAX), FB_LLR_MAX);
+                if (m < 0.0f) sgn = -sgn;
+                float a = fabsf(m);
+                work[k - k0] = a;
+                if (a < mn) mn = a;
+            }
+            sgn = sgn * ssign;
+            float mn2 = INFINITY, sum = 0.0f;
+            for (int k = k0; k < k1; k++) {
+                float d = FB_SUB(work[k - k0], mn);
+                if (d == 0.0f) d = LARGE;
+                work[k - k0] = d;
+                if (d < mn2) mn2 = d;
+                sum = FB_ADD(sum, d);
+            }
+            mn2 = FB_ADD(mn2, mn);
+            float node_sum = FB_SUB(sum, 2.0f * LARGE - 1.0f);
+            float sg = (node_sum > 0.0f) ? 1.0f : ((node_sum < 0.0f) ? -1.0f : 0.0f);
+            float dm = FB_MUL(0.5f, FB_SUB(1.0f, sg));
+            float mne = FB_ADD(FB_MUL(FB_SUB(1.0f, dm), mn), FB_MUL(dm, mn2));
+            for (int k = k0; k < k1; k++) {
+                int e = S->cn_edge[k];
+                float m = msg[e];
+                float s = (m < 0.0f) ? -sgn : sgn;
+                float v = (work[k - k0] == LARGE) ? mne : mn;
+                msg[e] = FB_MUL(FB_MUL(s, v), factor);
+            }
+        }
+    }
+}
+
+static int max_cn_degree(const orc_side_t *S) {
+    int d = 1;
+    for (int c = 0; c < S->m; c++) {
+        int k = S->cn_ptr[c + 1] - S->cn_ptr[c];
+        if (k > d) d = k;
+    }
+    return d;
+}
+
+/* ---------------------------------------------------------------- quaternary BP ---- */
+/* marginals of one frame (decoding_q.py:244-251) */
+static void bp4_marginals(const orc_side_t *X, const orc_side_t *Z, const float *mx,
+                          const float *mz, const float *llrx, const float *llry,
+                          const float *llrz, float *Lx, float *Ly, float *Lz) {
+    for (int v = 0; v < X->n; v++) {
+        float Sx = 0.0f, Sz = 0.0f;
+        for (int e = X->vn_ptr[v]; e < X->vn_ptr[v + 1]; e++) Sx = FB_ADD(Sx, mx[e]);
+        for (int e = Z->vn_ptr[v]; e < Z->vn_ptr[v + 1]; e++) Sz = FB_ADD(Sz, mz[e]);
+        Ly[v] = FB_ADD(FB_ADD(Sz, Sx), llry[v]);
+        Lx[v] = FB_ADD(Sz, llrx[v]);
+        Lz[v] = FB_ADD(Sx, llrz[v]);
+    }
+}
+
+/* soft syndromes of one frame (cal_logit, decoding_q.py:455-471).  rows_x: rows of
+ * _pcm_x_perp evaluated on llr_x'; rows_z: rows of _pcm_z_perp evaluated on llr_z'. */
+static void bp4_logits(int n, const orc_rows_t *rows_x, const orc_rows_t *rows_z,
+                       const float *Lx, const float *Ly, const float *Lz,
+                       float *x_logit, float *z_logit, float *wa, float *wb) {
+    /* wa = llr_x', wb = llr_z' */
+    for (int v = 0; v < n; v++) {
+        wb[v] = FB_SUB(fb_softplusf(-Lx[v]), fb_logaddexpf(-Lz[v], -Ly[v]));
+        wa[v] = FB_SUB(fb_softplusf(-Lz[v]), fb_logaddexpf(-Lx[v], -Ly[v]));
+    }
+    for (int side = 0; side < 2; side++) {
+        const orc_rows_t *R = side ? rows_z : rows_x;
+        const float *l = side ? wb : wa;
+        float *out = side ? z_logit : x_logit;
+        if (!R || !out) continue;
+        for (int r = 0; r < R->m; r++) {
+            float sgn = 1.0f, T = 0.0f;
+            for (int k = R->ptr[r]; k < R->ptr[r + 1]; k++) {
+                float m = l[R->col[k]];
+                if (m < 0.0f) sgn = -sgn;
+                T = FB_ADD(T, fb_phi4f(fabsf(m)));
+            }
+            out[r] = FB_MUL(sgn, fb_phi4f(T));
+        }
+    }
+}
+
+/* One frame of QLDPCBPDecoder.call.  mx/mz: work [E_x]/[E_z]; on exit they hold the c2v
+ * messages of the last iteration (VN order). */
+static void bp4_frame(const orc_side_t *X, const orc_side_t *Z, int cn_type, int num_iter,
+                      float factor, const float *llrx, const float *llry, const float *llrz,
+                      const uint8_t *sx, const uint8_t *sz, float *mx, float *mz,
+                      float *Lx, float *Ly, float *Lz, uint8_t *xh, uint8_t *zh, float *work) {
+    const int n = X->n;
+    memset(mx, 0, sizeof(float) * (size_t)X->E);
+    memset(mz, 0, sizeof(float) * (size_t)Z->E);
+    for (int it = 0; it < num_iter; it++) {
+        /* VN update, decoding_q.py:227-275 */
+        for (int v = 0; v < n; v++) {
+            float Sx = 0.0f, Sz = 0.0f;
+            for (int e = X->vn_ptr[v]; e < X->vn_ptr[v + 1]; e++) Sx = FB_ADD(Sx, mx[e]);
+            for (int e = Z->vn_ptr[v]; e < Z->vn_ptr[v + 1]; e++) Sz = FB_ADD(Sz, mz[e]);
+            float ly = FB_ADD(FB_ADD(Sz, Sx), llry[v]);
+            float lx = FB_ADD(Sz, llrx[v]);
+            float lz = FB_ADD(Sx, llrz[v]);
+            float num_hx = fb_softplusf(-lx);
+            float num_hz = fb_softplusf(-lz);
+            for (int e = X->vn_ptr[v]; e < X->vn_ptr[v + 1]; e++) {
+                float a = FB_SUB(lz, mx[e]), b = FB_SUB(ly, mx[e]);
+                mx[e] = FB_SUB(num_hx, fb_logaddexpf(-a, -b));
+            }
+            for (int e = Z->vn_ptr[v]; e < Z->vn_ptr[v + 1]; e++) {
+                float a = FB_SUB(lx, mz[e]), b = FB_SUB(ly, mz[e]);
+                mz[e] = FB_SUB(num_hz, fb_logaddexpf(-a, -b));
+            }
+        }
+        cn_update(X, cn_type, 1, factor, sx, mx, work);
+        cn_update(Z, cn_type, 1, factor, sz, mz, work);
+    }
+    bp4_marginals(X, Z, mx, mz, llrx, llry, llrz, Lx, Ly, Lz);
+    /* argmin over [0, Lx, Lz, Ly], first minimum wins (decoding_q.py:786-790) */
+    for (int v = 0; v < n; v++) {
+        int d = 0;
+        float best = 0.0f;
+        if (Lx[v] < best) { best = Lx[v]; d = 1; }
+        if (Lz[v] < best) { best = Lz[v]; d = 2; }
+        if (Ly[v] < best) { best = Ly[v]; d = 3; }
+        xh[v] = (uint8_t)(d & 1);
+        zh[v] = (uint8_t)(d >> 1);
+    }
+}
+
+/* Batched QLDPCBPDecoder.call with the reference's tensor layouts:
+ *   llr [B,3,n] (or NULL: the scalar `prior` is used for all three), synd_x [m_x,B],
+ *   synd_z [m_z,B] (uint8 0/1), outputs Lx,Ly,Lz [B,n] f32, x_hat,z_hat [B,n] u8,
+ *   x_logit [rows_x.m, B], z_logit [rows_z.m, B] (may be NULL), msg_x [B,E_x], msg_z
+ *   [B,E_z] final c2v messages (may be NULL). */
+void orc_bp4(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *rows_x,
+             const orc_rows_t *rows_z, int cn_type, int num_iter, float factor, int64_t B,
+             const float *llr, float prior, const uint8_t *synd_x, const uint8_t *synd_z,
+             float *Lx, float *Ly, float *Lz, uint8_t *x_hat, uint8_t *z_hat,
+             float *x_logit, float *z_logit, float *msg_x, float *msg_z) {
+    const int n = X->n, mxn = X->m, mzn = Z->m;
+    int wd = max_cn_degree(X), wz = max_cn_degree(Z);
+    if (wz > wd) wd = wz;
+#pragma omp parallel
+    {
+        float *mx = (float *)malloc(sizeof(float) * (size_t)(X->E + 1));
+        float *mz = (float *)malloc(sizeof(float) * (size_t)(Z->E + 1));
+        float *pri = (float *)malloc(sizeof(float) * 3 * (size_t)n);
+        float *work = (float *)malloc(sizeof(float) * (size_t)wd);
+        float *wa = (float *)malloc(sizeof(float) * 2 * (size_t)n);
+        uint8_t *sx = (uint8_t *)malloc((size_t)mxn + 1), *sz = (uint8_t *)malloc((size_t)mzn + 1);
+        float *xl = (float *)malloc(sizeof(float) * (size_t)((rows_x ? rows_x->m : 0) + 1));
+        float *zl = (float *)malloc(sizeof(float) * (size_t)((rows_z ? rows_z->m : 0) + 1));
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t b = 0; b < B; b++) {
+            for (int v = 0; v < 3 * n; v++) pri[v] = llr ? llr[b * 3 * n + v] : prior;
+            for (int c = 0; c < mxn; c++) sx[c] = synd_x[(int64_t)c * B + b];
+            for (int c = 0; c < mzn; c++) sz[c] = synd_z[(int64_t)c * B + b];
+            bp4_frame(X, Z, cn_type, num_iter, factor, pri, pri + n, pri + 2 * n, sx, sz, mx, mz,
+                      Lx + b * n, Ly + b * n, Lz + b * n, x_hat + b * n, z_hat + b * n, work);
+            if (x_logit || z_logit) {
+                bp4_logits(n, x_logit ? rows_x : NULL, z_logit ? rows_z : NULL, Lx + b * n,
+                           Ly + b * n, Lz + b * n, xl, zl, wa, wa + n);
+                if (x_logit) for (int r = 0; r < rows_x->m; r++) x_logit[(int64_t)r * B + b] = xl[r];
+                if (z_logit) for (int r = 0; r < rows_z->m; r++) z_logit[(int64_t)r * B + b] = zl[r];
+            }
+            if (msg_x) memcpy(msg_x + b * X->E, mx, sizeof(float) * (size_t)X->E);
+            if (msg_z) memcpy(msg_z + b * Z->E, mz, sizeof(float) * (size_t)Z->E);
+        }
+        free(mx); free(mz); free(pri); free(work); free(wa); free(sx); free(sz); free(xl); free(zl);
+    }
+}
+
+/* ---------------------------------------------------------------- binary BP -------- */
+/* One frame of LDPCBPDecoder.call with is_syndrome (decoding.py:905-1034).  `logit` is the
+ * layer input (log p1/p0); returns the soft output (logits) in `soft` and the hard decision
+ * (1 if logit > 0) in `hard`. */
+static void bp2_frame(const orc_side_t *S, int cn_type, int num_iter, float factor,
+                      const float *logit, const uint8_t *synd, float *msg, float *soft,
+                      uint8_t *hard, float *work, float *llr) {
+    const int n = S->n;
+    for (int v = 0; v < n; v++) {
+        float l = FB_FMIN(FB_FMAX(logit[v], -FB_LLR_MAX), FB_LLR_MAX);   /* decoding.py:918-920 */
+        llr[v] = -l;                                                   /* decoding.py:940 */
+    }
+    memset(msg, 0, sizeof(float) * (size_t)S->E);
+    for (int it = 0; it < num_iter; it++) {
+        for (int v = 0; v < n; v++) {                                  /* decoding.py:511-535 */
+            float s = 0.0f;
+            for (int e = S->vn_ptr[v]; e < S->vn_ptr[v + 1]; e++) s = FB_ADD(s, msg[e]);
+            s = FB_ADD(s, llr[v]);
+            for (int e = S->vn_ptr[v]; e < S->vn_ptr[v + 1]; e++) msg[e] = FB_SUB(s, msg[e]);
+        }
+        cn_update(S, cn_type, 0, factor, synd, msg, work);
+    }
+    for (int v = 0; v < n; v++) {                                      /* decoding.py:1026-1034 */
+        float s = 0.0f;
+        for (int e = S->vn_ptr[v]; e < S->vn_ptr[v + 1]; e++) s = FB_ADD(s, msg[e]);
+        float x = -FB_ADD(llr[v], s);
+        soft[v] = x;
+        hard[v] = (uint8_t)(0.0f < x);
+    }
+}
+
+/* llr [B,n] logits, synd [m,B] or NULL, soft [B,n], hard [B,n] */
+void orc_bp2(const orc_side_t *S, int cn_type, int num_iter, float factor, int64_t B,
+             const float *llr, const uint8_t *synd, float *soft, uint8_t *hard) {
+    const int n = S->n, m = S->m;
+    int wd = max_cn_degree(S);
+#pragma omp parallel
+    {
+        float *msg = (float *)malloc(sizeof(float) * (size_t)(S->E + 1));
+        float *work = (float *)malloc(sizeof(float) * (size_t)wd);
+        float *l = (float *)malloc(sizeof(float) * (size_t)n);
+        uint8_t *s = (uint8_t *)malloc((size_t)m + 1);
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t b = 0; b < B; b++) {
+            if (synd) for (int c = 0; c < m; c++) s[c] = synd[(int64_t)c * B + b];
+            bp2_frame(S, cn_type, num_iter, factor, llr + b * n, synd ? s : NULL, msg,
+                      soft + b * n, hard + b * n, work, l);
+        }
+        free(msg); free(work); free(l); free(s);
+    }
+}
+
+/* ---------------------------------------------------------------- feedback GNN ----- */
+static float gnn_act(int act, float x) {
+    if (act == 0) return fb_tanhf(x);
+    if (act == 1) return x > 0.0f ? x : 0.0f;
+    return x;
+}
+
+/* messages of one side into one variable node, reduced (feedback_gnn.py:175-184) */
+static void gnn_side(const orc_side_t *S, const orc_gnn_t *G, const float *W1, const float *b1,
+                     const float *W2, const float *b2, const float *h_cn, int v,
+                     const float f3[3], float *red, float *hid, float *msg) {
+    const int H = G->H, M = G->M;
+    const int e0 = S->vn_ptr[v], e1 = S->vn_ptr[v + 1];
+    for (int e = e0; e < e1; e++) {
+        const float f[4] = { h_cn[S->vn_cn[e]], f3[0], f3[1], f3[2] };
+        for (int j = 0; j < H; j++) {
+            float a = 0.0f;
+            for (int k = 0; k < 4; k++) a = FB_FMA(f[k], W1[k * H + j], a);
+            if (b1) a = FB_ADD(a, b1[j]);
+            hid[j] = gnn_act(G->act, a);
+        }
+        for (int i = 0; i < M; i++) {
+            float a = 0.0f;
+            for (int j = 0; j < H; j++) a = FB_FMA(hid[j], W2[j * M + i], a);
+            if (b2) a = FB_ADD(a, b2[i]);
+            msg[i] = a;
+        }
+        for (int i = 0; i < M; i++) {
+            if (e == e0) red[i] = (G->reduce <= 1) ? FB_ADD(0.0f, msg[i]) : msg[i];
+            else if (G->reduce <= 1) red[i] = FB_ADD(red[i], msg[i]);
+            else if (G->reduce == 2) red[i] = (msg[i] > red[i]) ? msg[i] : red[i];
+            else red[i] = (msg[i] < red[i]) ? msg[i] : red[i];
+        }
+    }
+    if (e1 == e0) for (int i = 0; i < M; i++) red[i] = 0.0f;
+    if (G->reduce == 0 && e1 > e0)
+        for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], (float)(e1 - e0));
+}
+
+/* One frame of Feedback_GNN.call.  logit_hx [m_x] pairs with hx rows, logit_hz [m_z] with hz
+ * rows (the caller passes the decoder's z_logit and x_logit, feedback_gnn.py:335). */
+static void gnn_frame(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t *G,
+                      const float *Lx, const float *Ly, const float *Lz, const float *logit_hx,
+                      const float *logit_hz, const uint8_t *sx, const uint8_t *sz,
+                      float *ox, float *oy, float *oz, float *work) {
+    const int n = X->n, H = G->H, M = G->M;
+    float *hcx = work, *hcz = hcx + X->m, *in = hcz + Z->m, *hid = in + 2 * M + 3, *msg = hid + H;
+    for (int c = 0; c < X->m; c++) hcx[c] = FB_MUL(logit_hx[c], sx[c] ? -1.0f : 1.0f);
+    for (int c = 0; c < Z->m; c++) hcz[c] = FB_MUL(logit_hz[c], sz[c] ? -1.0f : 1.0f);
+    for (int v = 0; v < n; v++) {
+        const float f3[3] = { Lx[v], Ly[v], Lz[v] };
+        gnn_side(X, G, G->W1x, G->b1x, G->W2x, G->b2x, hcx, v, f3, in, hid, msg);
+        gnn_side(Z, G, G->W1z, G->b1z, G->W2z, G->b2z, hcz, v, f3, in + M, hid, msg);
+        in[2 * M] = f3[0]; in[2 * M + 1] = f3[1]; in[2 * M + 2] = f3[2];
+        for (int j = 0; j < H; j++) {
+            float a = 0.0f;
+            for (int k = 0; k < 2 * M + 3; k++) a = FB_FMA(in[k], G->W3[k * H + j], a);
+            if (G->b3) a = FB_ADD(a, G->b3[j]);
+            hid[j] = gnn_act(G->act, a);
+        }
+        float o[3];
+        for (int i = 0; i < 3; i++) {
+            float a = 0.0f;
+            for (int j = 0; j < H; j++) a = FB_FMA(hid[j], G->W0[j * 3 + i], a);
+            if (G->b0) a = FB_ADD(a, G->b0[i]);
+            o[i] = a;
+        }
+        ox[v] = o[0]; oy[v] = o[1]; oz[v] = o[2];
+    }
+}
+
+static size_t gnn_work_floats(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t *G) {
+    return (size_t)X->m + (size_t)Z->m + 2 * (size_t)G->M + 3 + (size_t)G->H + (size_t)G->M + 8;
+}
+
+/* h_vn [B,n,3], logit_hx [m_x,B], logit_hz [m_z,B], synd_* [m,B], out [B,n,3] */
+void orc_gnn(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t *G, int64_t B,
+             const float *h_vn, const float *logit_hx, const float *logit_hz,
+             const uint8_t *synd_x, const uint8_t *synd_z, float *out) {
+    const int n = X->n;
+#pragma omp parallel
+    {
+        float *work = (float *)malloc(sizeof(float) * gnn_work_floats(X, Z, G));
+        float *L = (float *)malloc(sizeof(float) * 6 * (size_t)n);
+        float *lx = (float *)malloc(sizeof(float) * (size_t)(X->m + Z->m + 2));
+        uint8_t *s = (uint8_t *)malloc((size_t)(X->m + Z->m + 2));
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t b = 0; b < B; b++) {
+            for (int v = 0; v < n; v++)
+                for (int k = 0; k < 3; k++) L[k * n + v] = h_vn[(b * n + v) * 3 + k];
+            for (int c = 0; c < X->m; c++) { lx[c] = logit_hx[(int64_t)c * B + b]; s[c] = synd_x[(int64_t)c * B + b]; }
+            for (int c = 0; c < Z->m; c++) { lx[X->m + c] = logit_hz[(int64_t)c * B + b]; s[X->m + c] = synd_z[(int64_t)c * B + b]; }
+            gnn_frame(X, Z, G, L, L + n, L + 2 * n, lx, lx + X->m, s, s + X->m,
+                      L + 3 * n, L + 4 * n, L + 5 * n, work);
+            for (int v = 0; v < n; v++)
+                for (int k = 0; k < 3; k++) out[(b * n + v) * 3 + k] = L[(3 + k) * n + v];
+        }
+        free(work); free(L); free(lx); free(s);
+    }
+}
+
+/* ---------------------------------------------------------------- pipelines -------- */
+typedef struct {
+    int32_t num_stages;          /* num_layers of the reference: 1 + number of GNN rounds     */
+    const int32_t *num_iter;     /* [num_stages] BP iterations of decoders[i]                 */
+    const float *factor;         /* [num_stages] normalization_factor of decoders[i]          */
+    const int32_t *cn_type;      /* [num_stages]                                              */
+    const orc_gnn_t *const *gnn; /* [num_stages-1] feedbacks[i]                               */
+    float prior;                 /* log(3 (1 - p0) / p0), feedback_gnn.py:311-312              */
+    int32_t skip_inactive;       /* 0: every frame runs every round (reference behaviour);     */
+                                 /* 1: stop a frame once its decision matches the syndrome     */
+                                 /*    (result-identical, the scatter is masked: 339-340)      */
+} orc_pipe_cfg_t;
+
+/* flags bit0 = flagged (residual syndrome non-zero), bit1 = block error (ls_hat non-zero),
+ * bits 2..7 = number of GNN rounds the frame was still active in. */
+static uint8_t pipeline_frame(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *lx,
+                              const orc_rows_t *lz, const orc_pipe_cfg_t *cfg,
+                              const uint8_t *nx, const uint8_t *nz, float *fw, uint8_t *bw,
+                              uint8_t *x_diff, uint8_t *z_diff) {
+    const int n = X->n;
+    float *mx = fw, *mz = mx + X->E, *pri = mz + Z->E, *L = pri + 3 * n, *xl = L + 3 * n,
+          *zl = xl + Z->m, *wa = zl + X->m, *work = wa + 2 * n;
+    uint8_t *sx = bw, *sz = sx + X->m, *xh = sz + Z->m, *zh = xh + n, *xh2 = zh + n,
+            *zh2 = xh2 + n, *t = zh2 + n;
+    const orc_rows_t rows_x = { Z->m, Z->cn_ptr, Z->cn_vn };   /* stage_one: _pcm_x_perp = hz */
+    const orc_rows_t rows_z = { X->m, X->cn_ptr, X->cn_vn };   /*            _pcm_z_perp = hx */
+    syndrome_frame(X, nz, sx);                 /* syndrome_x = hx . noise_z, feedback_gnn.py:308 */
+    syndrome_frame(Z, nx, sz);                 /* syndrome_z = hz . noise_x                      */
+    for (int v = 0; v < 3 * n; v++) pri[v] = cfg->prior;
+    bp4_frame(X, Z, cfg->cn_type[0], cfg->num_iter[0], cfg->factor[0], pri, pri + n, pri + 2 * n,
+              sx, sz, mx, mz, L, L + n, L + 2 * n, xh, zh, work);
+    int active = 1, rounds = 0;
+    for (int i = 1; i < cfg->num_stages; i++) {
+        int mismatch = 0;                      /* feedback_gnn.py:324-330 */
+        syndrome_frame(Z, xh, t);
+        for (int c = 0; c < Z->m; c++) mismatch |= (t[c] != sz[c]);
+        syndrome_frame(X, zh, t);
+        for (int c = 0; c < X->m; c++) mismatch |= (t[c] != sx[c]);
+        active = active && mismatch;
+        if (!active && cfg->skip_inactive) break;
+        if (active) rounds++;
+        bp4_logits(n, &rows_x, &rows_z, L, L + n, L + 2 * n, xl, zl, wa, wa + n);
+        /* feedbacks[i-1]((h_vn, logit_hz_perp, logit_hx_perp, ...)): z_logit pairs with hx */
+        gnn_frame(X, Z, cfg->gnn[i - 1], L, L + n, L + 2 * n, zl, xl, sx, sz, pri, pri + n,
+                  pri + 2 * n, work);
+        bp4_frame(X, Z, cfg->cn_type[i], cfg->num_iter[i], cfg->factor[i], pri, pri + n,
+                  pri + 2 * n, sx, sz, mx, mz, L, L + n, L + 2 * n, xh2, zh2, work);
+        if (active) { memcpy(xh, xh2, (size_t)n); memcpy(zh, zh2, (size_t)n); }
+    }
+    for (int v = 0; v < n; v++) { xh[v] ^= nx[v]; zh[v] ^= nz[v]; }   /* x_diff, z_diff: 346-347 */
+    if (x_diff) memcpy(x_diff, xh, (size_t)n);
+    if (z_diff) memcpy(z_diff, zh, (size_t)n);
+    int flagged = 0;
+    syndrome_frame(Z, xh, t);
+    for (int c = 0; c < Z->m; c++) flagged |= t[c];
+    syndrome_frame(X, zh, t);
+    for (int c = 0; c < X->m; c++) flagged |= t[c];
+    /* any(hx_perp . x_diff) == any(hz . x_diff) or any(lz . x_diff)    */
+    int blk = flagged | rows_any_parity(lz, xh) | rows_any_parity(lx, zh);
+    return (uint8_t)((flagged ? 1 : 0) | (blk ? 2 : 0) | (rounds << 2));
+}
+
+static size_t pipe_float_work(const orc_side_t *X, const orc_side_t *Z, const orc_pipe_cfg_t *cfg) {
+    size_t g = 0;
+    for (int i = 0; i + 1 < cfg->num_stages; i++) {
+        size_t w = gnn_work_floats(X, Z, cfg->gnn[i]);
+        if (w > g) g = w;
+    }
+    int wd = max_cn_degree(X), wz = max_cn_degree(Z);
+    if (wz > wd) wd = wz;
+    if ((size_t)wd > g) g = (size_t)wd;
+    return (size_t)X->E + (size_t)Z->E + 8 * (size_t)X->n + (size_t)X->m + (size_t)Z->m + g + 16;
+}
+
+/* Sandwich_BP_GNN_Evaluation_Model.call on frames [first_frame, first_frame + B).
+ * thr: Pauli thresholds {px, px-py, (px+pz)-py} (float32).  If noise_x/noise_z are given
+ * ([B,n] u8) they are used instead of sampling.  Outputs: flags [B]; counters[4] =
+ * {frames, flagged, block errors, frames whose stage-0 decision missed the syndrome};
+ * optional x_diff/z_diff [B,n]. */
+void orc_pipeline(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *lx,
+                  const orc_rows_t *lz, const orc_pipe_cfg_t *cfg, const float *thr,
+                  uint64_t seed, uint64_t first_frame, int64_t B, const uint8_t *noise_x,
+                  const uint8_t *noise_z, uint8_t *flags, int64_t *counters, uint8_t *x_diff,
+                  uint8_t *z_diff) {
+    const int n = X->n;
+    int64_t c_flag = 0, c_blk = 0, c_s1 = 0;
+#pragma omp parallel reduction(+ : c_flag, c_blk, c_s1)
+    {
+        float *fw = (float *)malloc(sizeof(float) * pipe_float_work(X, Z, cfg));
+        uint8_t *bw = (uint8_t *)malloc((size_t)(X->m + Z->m) * 2 + 8 * (size_t)n + 64);
+        uint8_t *nx = (uint8_t *)malloc((size_t)n), *nz = (uint8_t *)malloc((size_t)n);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t b = 0; b < B; b++) {
+            if (noise_x) { memcpy(nx, noise_x + b * n, (size_t)n); memcpy(nz, noise_z + b * n, (size_t)n); }
+            else pauli_frame(seed, first_frame + (uint64_t)b, n, thr, nx, nz);
+            uint8_t f = pipeline_frame(X, Z, lx, lz, cfg, nx, nz, fw, bw,
+                                       x_diff ? x_diff + b * n : NULL, z_diff ? z_diff + b * n : NULL);
+            if (flags) flags[b] = f;
+            c_flag += f & 1; c_blk += (f >> 1) & 1; c_s1 += ((f >> 2) > 0);
+        }
+        free(fw); free(bw); free(nx); free(nz);
+    }
+    if (counters) { counters[0] = B; counters[1] = c_flag; counters[2] = c_blk; counters[3] = c_s1; }
+}
+
+/* BP_BSC_Model.call (feedback_gnn.py:207-229) on one side: noise ~ Bernoulli(p), syndrome,
+ * binary BP from the constant logit -log((1-p0)/p0), residual syndrome with the same pcm and
+ * logical check with `logical` rows.  flags as in orc_pipeline (bits 0,1). */
+void orc_bsc_pipeline(const orc_side_t *S, const orc_rows_t *logical, int cn_type, int num_iter,
+                      float factor, float llr_const, float p, uint64_t seed, uint64_t first_frame,
+                      int64_t B, const uint8_t *noise_in, uint8_t *flags, int64_t *counters) {
+    const int n = S->n, m = S->m;
+    int wd = max_cn_degree(S);
+    int64_t c_flag = 0, c_blk = 0;
+#pragma omp parallel reduction(+ : c_flag, c_blk)
+    {
+        float *msg = (float *)malloc(sizeof(float) * (size_t)(S->E + 1));
+        float *work = (float *)malloc(sizeof(float) * (size_t)wd);
+        float *fl = (float *)malloc(sizeof(float) * 3 * (size_t)n);
+        uint8_t *by = (uint8_t *)malloc(2 * (size_t)n + 2 * (size_t)m + 8);
+        uint8_t *noise = by, *hard = by + n, *s = hard + n, *t = s + m;
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t b = 0; b < B; b++) {
+            if (noise_in) memcpy(noise, noise_in + b * n, (size_t)n);
+            else bsc_frame(seed, first_frame + (uint64_t)b, n, p, noise);
+            syndrome_frame(S, noise, s);
+            for (int v = 0; v < n; v++) fl[v] = llr_const;
+            bp2_frame(S, cn_type, num_iter, factor, fl, s, msg, fl + n, hard, work, fl + 2 * n);
+            for (int v = 0; v < n; v++) hard[v] ^= noise[v];
+            int flagged = 0;
+            syndrome_frame(S, hard, t);
+            for (int c = 0; c < m; c++) flagged |= t[c];
+            int blk = logical ? rows_any_parity(logical, hard) : flagged;
+            uint8_t f = (uint8_t)((flagged ? 1 : 0) | (blk ? 2 : 0));
+            if (flags) flags[b] = f;
+            c_flag += f & 1; c_blk += (f >> 1) & 1;
+        }
+        free(msg); free(work); free(fl); free(by);
+    }
+    if (counters) { counters[0] = B; counters[1] = c_flag; counters[2] = c_blk; counters[3] = 0; }
+}
+
+/* ---------------------------------------------------------------- math probes ------ */
+#define ORC_VEC(name, fn) \
+    void name(const float *x, float *y, int64_t n) { for (int64_t i = 0; i < n; i++) y[i] = fn(x[i]); }
+ORC_VEC(orc_expf, fb_expf)
+ORC_VEC(orc_logf, fb_logf)
+ORC_VEC(orc_log1pf_pos, fb_log1pf_pos)
+ORC_VEC(orc_softplusf, fb_softplusf)
+ORC_VEC(orc_phi4f, fb_phi4f)
+ORC_VEC(orc_phi2f, fb_phi2f)
+ORC_VEC(orc_tanhf, fb_tanhf)
+ORC_VEC(orc_atanhf, fb_atanhf)
+void orc_logaddexpf(const float *a, const float *b, float *y, int64_t n) {
+    for (int64_t i = 0; i < n; i++) y[i] = fb_logaddexpf(a[i], b[i]);
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void orc_set_num_threads(int t) {
+#ifdef _OPENMP
+    omp_set_num_threads(t);
+#else
+    (void)t;
+#endif
+}
