@@ -496,3 +496,30 @@ def device_code(code, ctx=None):
         ent = (code, Code(code, ctx))
         _code_cache[key] = ent
     return ent[1]
+
+
+# ----------------------------------------------------------------------------- pinned host memory ---
+class PinnedArray:
+    """numpy view of page-locked host memory (so H2D / D2H copies run at full PCIe rate)."""
+
+    def __init__(self, shape, dtype):
+        dtype = np.dtype(dtype)
+        count = int(np.prod(shape))
+        self._ptr = C.c_void_p()
+        call("fbgnn_host_alloc", max(count * dtype.itemsize, 1), C.byref(self._ptr))
+        buf = (C.c_uint8 * max(count * dtype.itemsize, 1)).from_address(self._ptr.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+
+    def __del__(self):
+        try:
+            if self._ptr:
+                self.array = None
+                lib().fbgnn_host_free(self._ptr)
+        except Exception:
+            pass
+
+
+def copy_h2d_async(ctx, dst, host_array):
+    """Enqueue a host->device copy of a C-contiguous host array into a contiguous DeviceArray."""
+    assert dst.is_contiguous() and host_array.flags.c_contiguous and dst.nbytes == host_array.nbytes
+    call("fbgnn_memcpy_h2d", ctx.handle, dst.ptr, host_array.ctypes.data_as(C.c_void_p), host_array.nbytes)

@@ -105,7 +105,7 @@ class Feedback_GNN:
         return int(sum(w.size for w in self._weights))
 
     def _drop_handle(self):
-        if self._handle is not None:
+        if getattr(self, "_handle", None) is not None:
             try:
                 _ffi.lib().fbgnn_gnn_destroy(self._handle)
             except Exception:
