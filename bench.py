@@ -99,18 +99,19 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, smax, reasons = [], [], set()
+        sm, smax, pw, reasons = [], [], [], set()
         for r in self.rows:
             if len(r) < 9:
                 continue
             try:
-                sm.append(float(r[1])); smax.append(float(r[2]))
+                sm.append(float(r[1])); smax.append(float(r[2])); pw.append(float(r[3]))
             except ValueError:
                 continue
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "sm_min_mhz": min(sm) if sm else None, "power_w_max": max(pw) if pw else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 

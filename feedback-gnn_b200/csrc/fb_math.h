@@ -88,11 +88,10 @@ FB_HD float fb_expf_core(float x) {
     return FB_I2F(FB_F2I(p) + (int32_t)((uint32_t)n << 23));
 }
 
-/* exp(x) for any finite x <= 88: results below 2^-126 are flushed to +0. */
+/* exp(x) for any finite x <= 88; arguments below -87 are clamped (exp(-87) = 1.6e-38 is the
+ * smallest value returned, still a normal float32). */
 FB_HD float fb_expf(float x) {
-    float xc = FB_FMAX(x, -87.0f);
-    float e = fb_expf_core(xc);
-    return (x < -87.0f) ? 0.0f : e;
+    return fb_expf_core(FB_FMAX(x, -87.0f));
 }
 
 /* ---- log ------------------------------------------------------------------------- */
@@ -100,9 +99,9 @@ FB_HD float fb_expf(float x) {
  * f = m - 1, log(1+f) = f - f^2/2 + f^3 P(f), plus e*ln2 split in two parts. */
 FB_HD float fb_logf(float x) {
     int32_t ix = FB_F2I(x);
-    int32_t e = (ix - 0x3f3504f3) >> 23;              /* arithmetic shift */
-    float m = FB_I2F(ix - (int32_t)((uint32_t)e << 23));
-    float fe = (float)e;
+    int32_t eb = (ix - 0x3f3504f3) & (int32_t)0xff800000;   /* e * 2^23 */
+    float m = FB_I2F(ix - eb);
+    float fe = (float)eb;                                   /* exact: |e| <= 128 */
     float f = FB_SUB(m, 1.0f);
     float z = FB_MUL(f, f);
     float p = 7.0376836292e-2f;
@@ -114,11 +113,11 @@ FB_HD float fb_logf(float x) {
     p = FB_FMA(p, f, 2.0000714765e-1f);
     p = FB_FMA(p, f, -2.4999993993e-1f);
     p = FB_FMA(p, f, 3.3333331174e-1f);
-    float y = FB_MUL(FB_MUL(p, f), z);                /* f^3 P(f) */
-    y = FB_FMA(fe, -2.12194440e-4f, y);
+    float y = FB_MUL(FB_MUL(p, f), z);                      /* f^3 P(f) */
+    y = FB_FMA(fe, -2.12194440e-4f * 1.1920928955078125e-7f, y);      /* e * ln2_lo (constants carry 2^-23) */
     y = FB_FMA(z, -0.5f, y);
     float r = FB_ADD(f, y);
-    return FB_FMA(fe, 0.693359375f, r);
+    return FB_FMA(fe, 0.693359375f * 1.1920928955078125e-7f, r);      /* + e * ln2_hi */
 }
 
 /* crude reciprocal (relative error < 1e-3) used only to scale a half-ulp correction */
@@ -141,12 +140,18 @@ FB_HD float fb_log1pf_pos(float e) {
 }
 
 /* ---- TensorFlow composites ------------------------------------------------------- */
+/* log1p(e) for e >= 1: log(fl(1 + e)); the rounding of the sum costs at most half an ulp */
+FB_HD float fb_log1pf_ge1(float e) {
+    return fb_logf(FB_ADD(1.0f, e));
+}
+
 /* tf.math.softplus */
 FB_HD float fb_softplusf(float x) {
-    float e = fb_expf(x > FB_SOFTPLUS_THR ? 0.0f : x);
-    if (x > FB_SOFTPLUS_THR) return x;
-    if (x < -FB_SOFTPLUS_THR) return e;
-    return fb_log1pf_pos(e);
+    float xc = FB_FMIN(x, FB_SOFTPLUS_THR);                 /* keeps exp finite; unused when x is large */
+    float e = fb_expf(xc);
+    float l = fb_log1pf_pos(e);
+    float r = (x < -FB_SOFTPLUS_THR) ? e : l;
+    return (x > FB_SOFTPLUS_THR) ? x : r;
 }
 
 /* tf.reduce_logsumexp over the two values (a, b); both finite. */
@@ -161,8 +166,8 @@ FB_HD float fb_logaddexpf(float a, float b) {
 /* quaternary decoder phi, decoding_q.py:365-373: softplus(x) - log(exp(x) - 1) after clipping */
 FB_HD float fb_phi4f(float x) {
     x = FB_FMIN(FB_FMAX(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI);
-    float e = fb_expf_core(x);
-    float sp = (x > FB_SOFTPLUS_THR) ? x : fb_log1pf_pos(e);
+    float e = fb_expf_core(x);                              /* e >= 1 */
+    float sp = (x > FB_SOFTPLUS_THR) ? x : fb_log1pf_ge1(e);
     return FB_SUB(sp, fb_logf(FB_SUB(e, 1.0f)));
 }
 
@@ -174,7 +179,9 @@ FB_HD float fb_phi2f(float x) {
 }
 
 /* tanh: rational approximation x*P(x^2)/Q(x^2) on the clamped argument (the scheme Eigen's
- * float tanh, i.e. the TF CPU kernel, uses). */
+ * float tanh, i.e. the TF CPU kernel, uses).  Q stays in [4.8e-3, 0.91], so the quotient is
+ * formed branch-free with a fixed sequence: bit-trick seed, one Newton step (1.4e-2), then the
+ * series 1/(1-e) = 1 + e + e^2 + e^3. */
 FB_HD float fb_tanhf(float x) {
     float xc = FB_FMIN(FB_FMAX(x, -7.90531110763549805f), 7.90531110763549805f);
     float x2 = FB_MUL(xc, xc);
@@ -190,9 +197,13 @@ FB_HD float fb_tanhf(float x) {
     q = FB_FMA(q, x2, 1.18534705686654e-04f);
     q = FB_FMA(q, x2, 2.26843463243900e-03f);
     q = FB_FMA(q, x2, 4.89352518554385e-03f);
-    float r = FB_DIV(p, q);
-    float ax = xc < 0.0f ? -xc : xc;
-    return (ax < 0.0004f) ? xc : r;
+    float y = FB_I2F(0x7EF311C7 - FB_F2I(q));
+    y = FB_MUL(y, FB_FMA(-q, y, 2.0f));
+    float e = FB_FMA(-q, y, 1.0f);
+    float r0 = FB_MUL(p, y);
+    float t = FB_FMA(e, e, e);
+    t = FB_FMA(t, e, e);
+    return FB_FMA(r0, t, r0);
 }
 
 /* atanh for |x| <= 1 - 1e-7 (tanh check-node variant, decoding_q.py:356-361):

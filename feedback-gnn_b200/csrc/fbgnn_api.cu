@@ -125,6 +125,12 @@ extern "C" int fbgnn_ctx_create(int device, fbgnn_ctx **out) {
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     snprintf(ctx->name, sizeof ctx->name, "%s", prop.name);
     CK(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        CK(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CK(cudaEventCreate(&ctx->ev0));
     CK(cudaEventCreate(&ctx->ev1));
     *out = ctx;
@@ -189,19 +195,21 @@ extern "C" int fbgnn_launch_count(fbgnn_ctx *ctx, int64_t *launches) {
 }
 
 // ------------------------------------------------------------------ memory --------------
+// Stream-ordered allocation from the device's default memory pool (kept cached: the release
+// threshold is raised at context creation), so per-call output tensors cost no cudaMalloc.
 extern "C" int fbgnn_malloc(fbgnn_ctx *ctx, size_t bytes, void **dptr) {
     REQUIRE(ctx && dptr, "NULL argument");
     if (set_device(ctx)) return FBGNN_E_CUDA;
-    cudaError_t e = cudaMalloc(dptr, bytes ? bytes : 1);
-    if (e == cudaErrorMemoryAllocation) return fail(FBGNN_E_NOMEM, "cudaMalloc(%zu) out of memory", bytes);
+    cudaError_t e = cudaMallocAsync(dptr, bytes ? bytes : 1, ctx->stream);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); return fail(FBGNN_E_NOMEM, "cudaMallocAsync(%zu) out of memory", bytes); }
     CK(e);
     return 0;
 }
 extern "C" int fbgnn_free(fbgnn_ctx *ctx, void *dptr) {
     REQUIRE(ctx, "ctx is NULL");
+    if (!dptr) return 0;
     if (set_device(ctx)) return FBGNN_E_CUDA;
-    CK(cudaStreamSynchronize(ctx->stream));
-    CK(cudaFree(dptr));
+    CK(cudaFreeAsync(dptr, ctx->stream));
     return 0;
 }
 extern "C" int fbgnn_memset(fbgnn_ctx *ctx, void *dptr, int value, size_t bytes) {
@@ -429,21 +437,33 @@ static size_t bp4_smem(const SideDev &X, const SideDev &Z, bool const_prior) {
     return sizeof(float) * ((size_t)X.E + Z.E + (const_prior ? 2 : 3) * (size_t)X.n) + X.m + Z.m + X.n + 16;
 }
 
+template <bool CP, int DV, int DC>
+static int launch_bp4_t(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t smem, int threads) {
+    if (int rc = set_smem(k_bp4<CP, DV, DC>, smem, ctx, "quaternary BP")) return rc;
+    k_bp4<CP, DV, DC><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 static int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {
     if (grid <= 0) return 0;
     const bool cp = a.llr.ptr == nullptr;
     const size_t smem = bp4_smem(a.X, a.Z, cp);
     const int threads = pick_threads(a.X.n, a.X.m + a.Z.m);
-    if (cp) {
-        if (int rc = set_smem(k_bp4<true>, smem, ctx, "quaternary BP")) return rc;
-        k_bp4<true><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
-    } else {
-        if (int rc = set_smem(k_bp4<false>, smem, ctx, "quaternary BP")) return rc;
-        k_bp4<false><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
-    }
-    CK(cudaGetLastError());
-    ctx->launches++;
-    return 0;
+    // both sides regular with the same degrees -> unrolled instantiation
+    int dv = 0, dc = 0;
+    if (a.X.reg_dv && a.X.reg_dv == a.Z.reg_dv && a.X.reg_dc && a.X.reg_dc == a.Z.reg_dc) { dv = a.X.reg_dv; dc = a.X.reg_dc; }
+#define FBGNN_BP4_CASE(V, C)                                                                        \
+    if (dv == V && dc == C)                                                                         \
+        return cp ? launch_bp4_t<true, V, C>(ctx, a, grid, smem, threads)                           \
+                  : launch_bp4_t<false, V, C>(ctx, a, grid, smem, threads);
+    FBGNN_BP4_CASE(3, 6)
+    FBGNN_BP4_CASE(4, 8)
+    FBGNN_BP4_CASE(5, 10)
+#undef FBGNN_BP4_CASE
+    return cp ? launch_bp4_t<true, 0, 0>(ctx, a, grid, smem, threads)
+              : launch_bp4_t<false, 0, 0>(ctx, a, grid, smem, threads);
 }
 
 // ------------------------------------------------------------------ noise sources -------
@@ -593,14 +613,14 @@ extern "C" int fbgnn_gnn_destroy(fbgnn_gnn *g) {
     return 0;
 }
 
-template <int H, int M>
+template <int H, int M, int DV, bool TB>
 static int launch_gnn_t(fbgnn_ctx *ctx, const GnnArgs &a) {
     const size_t smem = sizeof(float) * GnnLayout<H, M>::total;
-    if (int rc = set_smem(k_gnn<H, M>, smem, ctx, "feedback GNN")) return rc;
+    if (int rc = set_smem(k_gnn<H, M, DV, TB>, smem, ctx, "feedback GNN")) return rc;
     const int64_t items = a.num_frames * a.X.n;
     int64_t blocks = (items + 127) / 128;
     blocks = std::min<int64_t>(blocks, (int64_t)ctx->num_sms * 8);
-    k_gnn<H, M><<<(unsigned)blocks, 128, smem, ctx->stream>>>(a);
+    k_gnn<H, M, DV, TB><<<(unsigned)blocks, 128, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -609,9 +629,15 @@ static int launch_gnn_t(fbgnn_ctx *ctx, const GnnArgs &a) {
 static int launch_gnn(fbgnn_ctx *ctx, const fbgnn_gnn *g, GnnArgs &a) {
     if (a.num_frames <= 0) return 0;
     a.weights = g->weights; a.act = g->act; a.reduce = g->reduce; a.use_bias = g->use_bias;
-    if (g->H == 40 && g->M == 20) return launch_gnn_t<40, 20>(ctx, a);
-    if (g->H == 20 && g->M == 20) return launch_gnn_t<20, 20>(ctx, a);
-    if (g->H == 64 && g->M == 32) return launch_gnn_t<64, 32>(ctx, a);
+    const bool reg3 = a.X.reg_dv == 3 && a.Z.reg_dv == 3;      // the (3,6)-regular GHP / bivariate codes
+    const bool tb = g->act == FBGNN_ACT_TANH && g->use_bias;   // the shipped configuration
+    if (g->H == 40 && g->M == 20) {
+        if (reg3 && tb) return launch_gnn_t<40, 20, 3, true>(ctx, a);
+        if (reg3) return launch_gnn_t<40, 20, 3, false>(ctx, a);
+        return tb ? launch_gnn_t<40, 20, 0, true>(ctx, a) : launch_gnn_t<40, 20, 0, false>(ctx, a);
+    }
+    if (g->H == 20 && g->M == 20) return launch_gnn_t<20, 20, 0, false>(ctx, a);
+    if (g->H == 64 && g->M == 32) return launch_gnn_t<64, 32, 0, false>(ctx, a);
     return fail(FBGNN_E_UNSUPPORTED, "unsupported GNN dimensions");
 }
 

@@ -141,6 +141,62 @@ __device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge,
     }
 }
 
+// ------------------------------------------------------------------ regular fast path --
+// (DV, DC)-regular sides (every variable in DV checks, every check on DC variables): the edge
+// ranges are v*DV.. and c*DC.., all loops unroll, the phi values and signs of a check stay in
+// registers and the DC (or 2*DV) independent phi / logaddexp chains give the scheduler ILP.
+// Operation order is exactly that of the generic path (and of the oracle).
+template <int DC>
+__device__ __forceinline__ void cn_phi_regular(const idx_t *__restrict__ cn_edge, int c, float *msg,
+                                               int synd_bit, float factor) {
+    int e[DC];
+    float a[DC];
+    uint32_t neg = 0;
+    int par = synd_bit;
+#pragma unroll
+    for (int k = 0; k < DC; k++) e[k] = cn_edge[c * DC + k];
+#pragma unroll
+    for (int k = 0; k < DC; k++) {
+        const float m = msg[e[k]];
+        const uint32_t sgn = (m < 0.0f) ? 1u : 0u;
+        neg |= sgn << k;
+        par ^= (int)sgn;
+        a[k] = fb_phi4f(fabsf(m));
+    }
+    float T = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DC; k++) T = FB_ADD(T, a[k]);
+#pragma unroll
+    for (int k = 0; k < DC; k++) {
+        float v = fb_phi4f(FB_SUB(T, a[k]));
+        const uint32_t s = ((uint32_t)par ^ (neg >> k)) & 1u;
+        v = __int_as_float(__float_as_int(v) ^ (int)(s << 31));
+        msg[e[k]] = FB_MUL(v, factor);
+    }
+}
+
+template <int DV>
+__device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, float px, float py, float pz) {
+    float ax[DV], az[DV];
+#pragma unroll
+    for (int k = 0; k < DV; k++) { ax[k] = mx[v * DV + k]; az[k] = mz[v * DV + k]; }
+    float Sx = 0.0f, Sz = 0.0f;
+#pragma unroll
+    for (int k = 0; k < DV; k++) Sx = FB_ADD(Sx, ax[k]);
+#pragma unroll
+    for (int k = 0; k < DV; k++) Sz = FB_ADD(Sz, az[k]);
+    const float ly = FB_ADD(FB_ADD(Sz, Sx), py);
+    const float lx = FB_ADD(Sz, px);
+    const float lz = FB_ADD(Sx, pz);
+    const float num_hx = fb_softplusf(-lx), num_hz = fb_softplusf(-lz);
+#pragma unroll
+    for (int k = 0; k < DV; k++)
+        mx[v * DV + k] = FB_SUB(num_hx, fb_logaddexpf(-FB_SUB(lz, ax[k]), -FB_SUB(ly, ax[k])));
+#pragma unroll
+    for (int k = 0; k < DV; k++)
+        mz[v * DV + k] = FB_SUB(num_hz, fb_logaddexpf(-FB_SUB(lx, az[k]), -FB_SUB(ly, az[k])));
+}
+
 // ------------------------------------------------------------------ quaternary BP -----
 struct Bp4Args {
     SideDev X, Z;
@@ -164,8 +220,8 @@ struct Bp4Args {
 
 // One CTA decodes one frame.  Dynamic shared memory:
 //   float msg_x[E_x], msg_z[E_z], pri[CONST_PRIOR ? 2n : 3n];  u8 sbx[m_x], sbz[m_z], dec[n]
-template <bool CONST_PRIOR>
-__global__ void k_bp4(const Bp4Args a) {
+template <bool CONST_PRIOR, int DV, int DC>
+__global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     extern __shared__ float smem[];
     const SideDev &X = a.X, &Z = a.Z;
     const int n = X.n, T = blockDim.x, tid = threadIdx.x;
@@ -180,16 +236,21 @@ __global__ void k_bp4(const Bp4Args a) {
     for (int c = tid; c < Z.m; c += T) sbz[c] = a.sz(c, b);
     __syncthreads();
 
+    const bool fast = DV > 0 && a.cn_type == 0;     // regular graph + boxplus-phi: unrolled path
     for (int it = 0; it < a.num_iter; it++) {
         // variable nodes (decoding_q.py:227-275)
         for (int v = tid; v < n; v += T) {
+            const float px = CONST_PRIOR ? a.prior : pri[v];
+            const float py = CONST_PRIOR ? a.prior : pri[n + v];
+            const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
+            if (DV > 0) {
+                vn_update_regular<(DV > 0 ? DV : 1)>(v, mx, mz, px, py, pz);
+                continue;
+            }
             const int x0 = X.vn_ptr[v], x1 = X.vn_ptr[v + 1], z0 = Z.vn_ptr[v], z1 = Z.vn_ptr[v + 1];
             float Sx = 0.0f, Sz = 0.0f;
             for (int e = x0; e < x1; e++) Sx = FB_ADD(Sx, mx[e]);
             for (int e = z0; e < z1; e++) Sz = FB_ADD(Sz, mz[e]);
-            const float px = CONST_PRIOR ? a.prior : pri[v];
-            const float py = CONST_PRIOR ? a.prior : pri[n + v];
-            const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
             const float ly = FB_ADD(FB_ADD(Sz, Sx), py);
             const float lx = FB_ADD(Sz, px);
             const float lz = FB_ADD(Sx, pz);
@@ -206,11 +267,16 @@ __global__ void k_bp4(const Bp4Args a) {
         __syncthreads();
         // check nodes of both sides as one index space
         for (int c = tid; c < X.m + Z.m; c += T) {
-            if (c < X.m)
-                cn_update_one<true>(X.cn_edge, X.cn_ptr[c], X.cn_ptr[c + 1], mx, sbx[c], a.cn_type, a.factor);
-            else
-                cn_update_one<true>(Z.cn_edge, Z.cn_ptr[c - X.m], Z.cn_ptr[c - X.m + 1], mz, sbz[c - X.m],
-                                    a.cn_type, a.factor);
+            const bool isx = c < X.m;
+            const int cc = isx ? c : c - X.m;
+            float *msg = isx ? mx : mz;
+            const int sb = isx ? sbx[cc] : sbz[cc];
+            if (fast) {
+                cn_phi_regular<(DC > 0 ? DC : 1)>(isx ? X.cn_edge : Z.cn_edge, cc, msg, sb, a.factor);
+            } else {
+                const SideDev &S = isx ? X : Z;
+                cn_update_one<true>(S.cn_edge, S.cn_ptr[cc], S.cn_ptr[cc + 1], msg, sb, a.cn_type, a.factor);
+            }
         }
         __syncthreads();
     }
@@ -382,76 +448,26 @@ __device__ __forceinline__ float gnn_act(int act, float x) {
     return x;
 }
 
-// messages of one side into one variable node, reduced (feedback_gnn.py:175-184)
-template <int H, int M>
-__device__ __forceinline__ void gnn_side(const SideDev &S, const float *__restrict__ W1,
-                                         const float *__restrict__ b1, const float *__restrict__ W2,
-                                         const float *__restrict__ b2, const View2<const float> &logit,
-                                         const View2<const uint8_t> &synd, int64_t b, int v, float f1,
-                                         float f2, float f3, int act, int reduce, int use_bias,
-                                         float *red) {
-    const int e0 = S.vn_ptr[v], e1 = S.vn_ptr[v + 1];
-#pragma unroll
-    for (int i = 0; i < M; i++) red[i] = 0.0f;
-    for (int e = e0; e < e1; e++) {
-        const int c = S.vn_cn[e];
-        const float lg = logit(c, b);
-        const float hc = synd(c, b) ? -lg : lg;
-        float acc[M];
-#pragma unroll
-        for (int i = 0; i < M; i++) acc[i] = 0.0f;
-#pragma unroll 2
-        for (int j = 0; j < H; j += 4) {
-            const float4 w0 = *reinterpret_cast<const float4 *>(W1 + 0 * H + j);
-            const float4 w1 = *reinterpret_cast<const float4 *>(W1 + 1 * H + j);
-            const float4 w2 = *reinterpret_cast<const float4 *>(W1 + 2 * H + j);
-            const float4 w3 = *reinterpret_cast<const float4 *>(W1 + 3 * H + j);
-            const float4 bb = *reinterpret_cast<const float4 *>(b1 + j);
-            float h[4];
-            h[0] = FB_FMA(f3, w3.x, FB_FMA(f2, w2.x, FB_FMA(f1, w1.x, FB_FMA(hc, w0.x, 0.0f))));
-            h[1] = FB_FMA(f3, w3.y, FB_FMA(f2, w2.y, FB_FMA(f1, w1.y, FB_FMA(hc, w0.y, 0.0f))));
-            h[2] = FB_FMA(f3, w3.z, FB_FMA(f2, w2.z, FB_FMA(f1, w1.z, FB_FMA(hc, w0.z, 0.0f))));
-            h[3] = FB_FMA(f3, w3.w, FB_FMA(f2, w2.w, FB_FMA(f1, w1.w, FB_FMA(hc, w0.w, 0.0f))));
-            if (use_bias) { h[0] = FB_ADD(h[0], bb.x); h[1] = FB_ADD(h[1], bb.y); h[2] = FB_ADD(h[2], bb.z); h[3] = FB_ADD(h[3], bb.w); }
-#pragma unroll
-            for (int jj = 0; jj < 4; jj++) {
-                const float hv = gnn_act(act, h[jj]);
-                const float *w2r = W2 + (j + jj) * M;
-#pragma unroll
-                for (int i = 0; i < M; i += 4) {
-                    const float4 w = *reinterpret_cast<const float4 *>(w2r + i);
-                    acc[i + 0] = FB_FMA(hv, w.x, acc[i + 0]);
-                    acc[i + 1] = FB_FMA(hv, w.y, acc[i + 1]);
-                    acc[i + 2] = FB_FMA(hv, w.z, acc[i + 2]);
-                    acc[i + 3] = FB_FMA(hv, w.w, acc[i + 3]);
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < M; i++) {
-            const float mval = use_bias ? FB_ADD(acc[i], b2[i]) : acc[i];
-            if (e == e0) red[i] = (reduce <= 1) ? FB_ADD(0.0f, mval) : mval;
-            else if (reduce <= 1) red[i] = FB_ADD(red[i], mval);
-            else if (reduce == 2) red[i] = (mval > red[i]) ? mval : red[i];
-            else red[i] = (mval < red[i]) ? mval : red[i];
-        }
-    }
-    if (reduce == 0 && e1 > e0) {
-        const float dg = (float)(e1 - e0);
-#pragma unroll
-        for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], dg);
-    }
-}
-
-// One thread per (frame, variable node); the 3 923 weights are staged in shared memory and
-// read as broadcast float4s.  Requires H % 4 == 0 and M % 4 == 0.
-template <int H, int M>
+// One thread per (frame, variable node); the 3 923 weights are staged in shared memory and read
+// as broadcast loads.  Messages of one side into the variable node are computed and reduced as in
+// feedback_gnn.py:175-184; the arithmetic and its order are those of oracle/fbgnn_oracle.c.
+//   DV > 0 : both sides are DV-regular -- the DV edges of a side are processed together, so each
+//            weight fetched feeds DV FMAs and the DV tanh chains overlap;  DV == 0 : edge by edge.
+//   TANH_BIAS : compile-time specialisation of the shipped configuration (tanh, use_bias=True);
+//            otherwise activation / bias are run-time switches.
+// The two sides share ONE copy of the inner loop (side loop not unrolled) and the loop over hidden
+// units is not unrolled: the hot loop body stays ~2 KB, inside the instruction cache.
+// Requires H % 4 == 0 and M % 4 == 0.
+template <int H, int M, int DV, bool TANH_BIAS>
 __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
     typedef GnnLayout<H, M> Lay;
     extern __shared__ float w[];
     for (int i = threadIdx.x; i < Lay::total; i += blockDim.x) w[i] = a.weights[i];
     __syncthreads();
+    constexpr int NE = DV > 0 ? DV : 1;
     const int n = a.X.n;
+    const int act = TANH_BIAS ? 0 : a.act;
+    const bool use_bias = TANH_BIAS ? true : (a.use_bias != 0);
     const int64_t items = a.num_frames * n;
     for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items;
          it += (int64_t)gridDim.x * blockDim.x) {
@@ -460,10 +476,79 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
         const int64_t b = a.frame_list ? a.frame_list[fi] : fi;
         const float f1 = a.h_vn(b, v, 0), f2 = a.h_vn(b, v, 1), f3 = a.h_vn(b, v, 2);
         float in[2 * M + 3];
-        gnn_side<H, M>(a.X, w + Lay::W1x, w + Lay::b1x, w + Lay::W2x, w + Lay::b2x, a.logit_hx, a.sx, b, v,
-                       f1, f2, f3, a.act, a.reduce, a.use_bias, in);
-        gnn_side<H, M>(a.Z, w + Lay::W1z, w + Lay::b1z, w + Lay::W2z, w + Lay::b2z, a.logit_hz, a.sz, b, v,
-                       f1, f2, f3, a.act, a.reduce, a.use_bias, in + M);
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            const SideDev &S = side ? a.Z : a.X;
+            const float *W1 = w + (side ? Lay::W1z : Lay::W1x), *b1 = w + (side ? Lay::b1z : Lay::b1x);
+            const float *W2 = w + (side ? Lay::W2z : Lay::W2x), *b2 = w + (side ? Lay::b2z : Lay::b2x);
+            const View2<const float> &logit = side ? a.logit_hz : a.logit_hx;
+            const View2<const uint8_t> &synd = side ? a.sz : a.sx;
+            const int e0 = DV > 0 ? v * DV : S.vn_ptr[v], e1 = DV > 0 ? e0 + DV : S.vn_ptr[v + 1];
+            float red[M];
+#pragma unroll
+            for (int i = 0; i < M; i++) red[i] = 0.0f;
+            for (int eb = e0; eb < e1; eb += NE) {
+                float hc[NE];
+#pragma unroll
+                for (int k = 0; k < NE; k++) {
+                    const int c = S.vn_cn[eb + k];
+                    const float lg = logit(c, b);
+                    hc[k] = synd(c, b) ? -lg : lg;
+                }
+                float acc[NE][M];
+#pragma unroll
+                for (int k = 0; k < NE; k++)
+#pragma unroll
+                    for (int i = 0; i < M; i++) acc[k][i] = 0.0f;
+#pragma unroll 1
+                for (int j = 0; j < H; j++) {
+                    // features [h_cn, Lx, Ly, Lz]: the per-variable terms first, the check term last
+                    const float base = FB_FMA(f3, W1[3 * H + j], FB_FMA(f2, W1[2 * H + j], FB_FMA(f1, W1[H + j], 0.0f)));
+                    const float w0 = W1[j], bj = b1[j];
+                    float hv[NE];
+#pragma unroll
+                    for (int k = 0; k < NE; k++) {
+                        float t = FB_FMA(hc[k], w0, base);
+                        if (use_bias) t = FB_ADD(t, bj);
+                        hv[k] = gnn_act(act, t);
+                    }
+                    const float *w2r = W2 + j * M;
+#pragma unroll
+                    for (int i = 0; i < M; i += 4) {
+                        const float4 wv = *reinterpret_cast<const float4 *>(w2r + i);
+#pragma unroll
+                        for (int k = 0; k < NE; k++) {
+                            acc[k][i + 0] = FB_FMA(hv[k], wv.x, acc[k][i + 0]);
+                            acc[k][i + 1] = FB_FMA(hv[k], wv.y, acc[k][i + 1]);
+                            acc[k][i + 2] = FB_FMA(hv[k], wv.z, acc[k][i + 2]);
+                            acc[k][i + 3] = FB_FMA(hv[k], wv.w, acc[k][i + 3]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < NE; k++) {
+                    const bool first = (eb + k == e0);
+#pragma unroll
+                    for (int i = 0; i < M; i++) {
+                        const float mval = use_bias ? FB_ADD(acc[k][i], b2[i]) : acc[k][i];
+                        if (first) red[i] = (a.reduce <= 1) ? FB_ADD(0.0f, mval) : mval;
+                        else if (a.reduce <= 1) red[i] = FB_ADD(red[i], mval);
+                        else if (a.reduce == 2) red[i] = (mval > red[i]) ? mval : red[i];
+                        else red[i] = (mval < red[i]) ? mval : red[i];
+                    }
+                }
+            }
+            if (a.reduce == 0 && e1 > e0) {
+                const float dg = (float)(e1 - e0);
+#pragma unroll
+                for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], dg);
+            }
+#pragma unroll
+            for (int i = 0; i < M; i++) {
+                if (side == 0) in[i] = red[i];
+                else in[M + i] = red[i];
+            }
+        }
         in[2 * M] = f1; in[2 * M + 1] = f2; in[2 * M + 2] = f3;
         float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
 #pragma unroll 1
@@ -477,11 +562,11 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
                 h2 = FB_FMA(in[k], wv.z, h2);
                 h3 = FB_FMA(in[k], wv.w, h3);
             }
-            if (a.use_bias) {
+            if (use_bias) {
                 const float4 bb = *reinterpret_cast<const float4 *>(w + Lay::b3 + j);
                 h0 = FB_ADD(h0, bb.x); h1 = FB_ADD(h1, bb.y); h2 = FB_ADD(h2, bb.z); h3 = FB_ADD(h3, bb.w);
             }
-            const float hh[4] = { gnn_act(a.act, h0), gnn_act(a.act, h1), gnn_act(a.act, h2), gnn_act(a.act, h3) };
+            const float hh[4] = { gnn_act(act, h0), gnn_act(act, h1), gnn_act(act, h2), gnn_act(act, h3) };
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
                 const float *w0 = w + Lay::W0 + (j + jj) * 3;
@@ -490,7 +575,7 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
                 o2 = FB_FMA(hh[jj], w0[2], o2);
             }
         }
-        if (a.use_bias) {
+        if (use_bias) {
             o0 = FB_ADD(o0, w[Lay::b0 + 0]); o1 = FB_ADD(o1, w[Lay::b0 + 1]); o2 = FB_ADD(o2, w[Lay::b0 + 2]);
         }
         a.out(b, v, 0) = o0; a.out(b, v, 1) = o1; a.out(b, v, 2) = o2;

@@ -437,10 +437,13 @@ static void gnn_side(const orc_side_t *S, const orc_gnn_t *G, const float *W1, c
     const int H = G->H, M = G->M;
     const int e0 = S->vn_ptr[v], e1 = S->vn_ptr[v + 1];
     for (int e = e0; e < e1; e++) {
-        const float f[4] = { h_cn[S->vn_cn[e]], f3[0], f3[1], f3[2] };
+        /* features [h_cn[c], Lx, Ly, Lz] (feedback_gnn.py:175-178); the three per-variable terms
+         * are accumulated first, the check-node term last */
+        const float hc = h_cn[S->vn_cn[e]];
         for (int j = 0; j < H; j++) {
             float a = 0.0f;
-            for (int k = 0; k < 4; k++) a = FB_FMA(f[k], W1[k * H + j], a);
+            for (int k = 0; k < 3; k++) a = FB_FMA(f3[k], W1[(k + 1) * H + j], a);
+            a = FB_FMA(hc, W1[j], a);
             if (b1) a = FB_ADD(a, b1[j]);
             hid[j] = gnn_act(G->act, a);
         }
