@@ -122,6 +122,8 @@ def cpu_reference_run(code, frames, steps=1, warmup=0, seed=2):
     import fbgnn as F
     g = O.CodeGraph(code)
     G = O.Gnn(F.read_weights(os.path.join(F.WEIGHTS_DIR, WEIGHTS)))
+    # torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    O.lib().orc_set_num_threads(os.cpu_count() or 1)
     threads = O.num_threads()
     kw = dict(num_iters=NUM_ITERS, gnns=[G] * N_G, p=P_NOISE, p0=P0, seed=seed, skip_inactive=False)
     for i in range(warmup):
