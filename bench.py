@@ -223,6 +223,24 @@ def main():
     total_frames = args.steps * B * world
     value = total_frames / (ms * 1e-3)
 
+    # ---- the opt-in MUFU arithmetic on the same workload (not the parity path; reported beside it)
+    ctx.set_math("fast")
+    for _ in range(2):
+        model.run(B, P_NOISE, want_flags=False, want_diff=False)
+    barrier()
+    ctx.timer_start()
+    fast_steps = max(3, min(args.steps, 5))
+    fast_counters = np.zeros(4, np.int64)
+    for _ in range(fast_steps):
+        fast_counters += model.run(B, P_NOISE, want_flags=False, want_diff=False, want_counters=True)["counters"]
+    fast_ms = ctx.timer_stop()
+    ctx.set_math("exact")
+    if dist is not None:
+        t = torch.tensor([fast_ms], device=f"cuda:{local_rank}")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        fast_ms = float(t.item())
+    fast_value = fast_steps * B * world / (fast_ms * 1e-3)
+
     # ---- end to end through the public API with host buffers
     nx_h = _ffi.PinnedArray((B, N_Q), np.uint8)
     nz_h = _ffi.PinnedArray((B, N_Q), np.uint8)
@@ -321,6 +339,12 @@ def main():
                     "d2h_bytes_per_step": B + 32, "steps": e2e_steps,
                     "path": "Sandwich_BP_GNN_Evaluation_Model.run(noise=host samples) -> flags/counters on host"},
             "gpu_launches": int(launches),
+            "fast_math": {"value": fast_value, "unit": "frames/s", "steps": fast_steps,
+                          "block_errors": int(fast_counters[2]), "frames": int(fast_counters[0]),
+                          "sfu_frac": fast_value * TE_PER_FRAME / sfu_peak,
+                          "note": "opt-in Context.set_math('fast'): MUFU ex2/lg2/rcp instead of the bit-exact software "
+                                  "libm. NOT a parity path: not bit-exact and its logical error rate is lower than "
+                                  "the reference's (tests/test_gpu_fastmath.py); informational only"},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)

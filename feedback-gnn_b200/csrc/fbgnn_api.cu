@@ -59,6 +59,7 @@ struct fbgnn_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     int64_t launches = 0;
+    int math_mode = FBGNN_MATH_EXACT;
     void *flush_buf = nullptr;
     size_t flush_bytes = 0;
     char name[256] = {0};
@@ -185,6 +186,19 @@ extern "C" int fbgnn_timer_stop(fbgnn_ctx *ctx, float *ms) {
     CK(cudaEventRecord(ctx->ev1, ctx->stream));
     CK(cudaEventSynchronize(ctx->ev1));
     CK(cudaEventElapsedTime(ms, ctx->ev0, ctx->ev1));
+    return 0;
+}
+
+extern "C" int fbgnn_ctx_set_math(fbgnn_ctx *ctx, int32_t mode) {
+    REQUIRE(ctx, "ctx is NULL");
+    REQUIRE(mode == FBGNN_MATH_EXACT || mode == FBGNN_MATH_FAST, "unknown math mode %d", mode);
+    ctx->math_mode = mode;
+    return 0;
+}
+
+extern "C" int fbgnn_ctx_get_math(fbgnn_ctx *ctx, int32_t *mode) {
+    REQUIRE(ctx && mode, "NULL argument");
+    *mode = ctx->math_mode;
     return 0;
 }
 
@@ -437,13 +451,22 @@ static size_t bp4_smem(const SideDev &X, const SideDev &Z, bool const_prior) {
     return sizeof(float) * ((size_t)X.E + Z.E + (const_prior ? 2 : 3) * (size_t)X.n) + X.m + Z.m + X.n + 16;
 }
 
-template <bool CP, int DV, int DC>
+template <bool CP, int DV, int DC, typename MATH>
 static int launch_bp4_t(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t smem, int threads) {
-    if (int rc = set_smem(k_bp4<CP, DV, DC>, smem, ctx, "quaternary BP")) return rc;
-    k_bp4<CP, DV, DC><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+    if (int rc = set_smem(k_bp4<CP, DV, DC, MATH>, smem, ctx, "quaternary BP")) return rc;
+    k_bp4<CP, DV, DC, MATH><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->launches++;
     return 0;
+}
+
+template <int DV, int DC>
+static int launch_bp4_m(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t smem, int threads, bool cp) {
+    if (ctx->math_mode == FBGNN_MATH_FAST)
+        return cp ? launch_bp4_t<true, DV, DC, MathFast>(ctx, a, grid, smem, threads)
+                  : launch_bp4_t<false, DV, DC, MathFast>(ctx, a, grid, smem, threads);
+    return cp ? launch_bp4_t<true, DV, DC, MathExact>(ctx, a, grid, smem, threads)
+              : launch_bp4_t<false, DV, DC, MathExact>(ctx, a, grid, smem, threads);
 }
 
 static int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {
@@ -454,16 +477,10 @@ static int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {
     // both sides regular with the same degrees -> unrolled instantiation
     int dv = 0, dc = 0;
     if (a.X.reg_dv && a.X.reg_dv == a.Z.reg_dv && a.X.reg_dc && a.X.reg_dc == a.Z.reg_dc) { dv = a.X.reg_dv; dc = a.X.reg_dc; }
-#define FBGNN_BP4_CASE(V, C)                                                                        \
-    if (dv == V && dc == C)                                                                         \
-        return cp ? launch_bp4_t<true, V, C>(ctx, a, grid, smem, threads)                           \
-                  : launch_bp4_t<false, V, C>(ctx, a, grid, smem, threads);
-    FBGNN_BP4_CASE(3, 6)
-    FBGNN_BP4_CASE(4, 8)
-    FBGNN_BP4_CASE(5, 10)
-#undef FBGNN_BP4_CASE
-    return cp ? launch_bp4_t<true, 0, 0>(ctx, a, grid, smem, threads)
-              : launch_bp4_t<false, 0, 0>(ctx, a, grid, smem, threads);
+    if (dv == 3 && dc == 6) return launch_bp4_m<3, 6>(ctx, a, grid, smem, threads, cp);
+    if (dv == 4 && dc == 8) return launch_bp4_m<4, 8>(ctx, a, grid, smem, threads, cp);
+    if (dv == 5 && dc == 10) return launch_bp4_m<5, 10>(ctx, a, grid, smem, threads, cp);
+    return launch_bp4_m<0, 0>(ctx, a, grid, smem, threads, cp);
 }
 
 // ------------------------------------------------------------------ noise sources -------
@@ -538,14 +555,28 @@ extern "C" int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_i
 
 static size_t bp2_smem(const SideDev &S) { return sizeof(float) * ((size_t)S.E + S.n) + S.m + 16; }
 
-static int launch_bp2(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B) {
-    if (B <= 0) return 0;
-    const size_t smem = bp2_smem(a.S);
-    if (int rc = set_smem(k_bp2, smem, ctx, "binary BP")) return rc;
-    k_bp2<<<(unsigned)B, pick_threads(a.S.n, a.S.m), smem, ctx->stream>>>(a);
+template <int DV, int DC, typename MATH>
+static int launch_bp2_t(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B, size_t smem) {
+    if (int rc = set_smem(k_bp2<DV, DC, MATH>, smem, ctx, "binary BP")) return rc;
+    k_bp2<DV, DC, MATH><<<(unsigned)B, pick_threads(a.S.n, a.S.m), smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->launches++;
     return 0;
+}
+
+template <int DV, int DC>
+static int launch_bp2_m(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B, size_t smem) {
+    return ctx->math_mode == FBGNN_MATH_FAST ? launch_bp2_t<DV, DC, MathFast>(ctx, a, B, smem)
+                                             : launch_bp2_t<DV, DC, MathExact>(ctx, a, B, smem);
+}
+
+static int launch_bp2(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B) {
+    if (B <= 0) return 0;
+    const size_t smem = bp2_smem(a.S);
+    if (a.S.reg_dv == 3 && a.S.reg_dc == 6) return launch_bp2_m<3, 6>(ctx, a, B, smem);
+    if (a.S.reg_dv == 4 && a.S.reg_dc == 8) return launch_bp2_m<4, 8>(ctx, a, B, smem);
+    if (a.S.reg_dv == 5 && a.S.reg_dc == 10) return launch_bp2_m<5, 10>(ctx, a, B, smem);
+    return launch_bp2_m<0, 0>(ctx, a, B, smem);
 }
 
 extern "C" int fbgnn_bp2_decode(fbgnn_graph *g, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
@@ -613,17 +644,23 @@ extern "C" int fbgnn_gnn_destroy(fbgnn_gnn *g) {
     return 0;
 }
 
-template <int H, int M, int DV, bool TB>
+template <int H, int M, int DV, bool TB, typename MATH>
 static int launch_gnn_t(fbgnn_ctx *ctx, const GnnArgs &a) {
     const size_t smem = sizeof(float) * GnnLayout<H, M>::total;
-    if (int rc = set_smem(k_gnn<H, M, DV, TB>, smem, ctx, "feedback GNN")) return rc;
+    if (int rc = set_smem(k_gnn<H, M, DV, TB, MATH>, smem, ctx, "feedback GNN")) return rc;
     const int64_t items = a.num_frames * a.X.n;
     int64_t blocks = (items + 127) / 128;
     blocks = std::min<int64_t>(blocks, (int64_t)ctx->num_sms * 8);
-    k_gnn<H, M, DV, TB><<<(unsigned)blocks, 128, smem, ctx->stream>>>(a);
+    k_gnn<H, M, DV, TB, MATH><<<(unsigned)blocks, 128, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->launches++;
     return 0;
+}
+
+template <int H, int M, int DV, bool TB>
+static int launch_gnn_m(fbgnn_ctx *ctx, const GnnArgs &a) {
+    return ctx->math_mode == FBGNN_MATH_FAST ? launch_gnn_t<H, M, DV, TB, MathFast>(ctx, a)
+                                             : launch_gnn_t<H, M, DV, TB, MathExact>(ctx, a);
 }
 
 static int launch_gnn(fbgnn_ctx *ctx, const fbgnn_gnn *g, GnnArgs &a) {
@@ -632,12 +669,12 @@ static int launch_gnn(fbgnn_ctx *ctx, const fbgnn_gnn *g, GnnArgs &a) {
     const bool reg3 = a.X.reg_dv == 3 && a.Z.reg_dv == 3;      // the (3,6)-regular GHP / bivariate codes
     const bool tb = g->act == FBGNN_ACT_TANH && g->use_bias;   // the shipped configuration
     if (g->H == 40 && g->M == 20) {
-        if (reg3 && tb) return launch_gnn_t<40, 20, 3, true>(ctx, a);
-        if (reg3) return launch_gnn_t<40, 20, 3, false>(ctx, a);
-        return tb ? launch_gnn_t<40, 20, 0, true>(ctx, a) : launch_gnn_t<40, 20, 0, false>(ctx, a);
+        if (reg3 && tb) return launch_gnn_m<40, 20, 3, true>(ctx, a);
+        if (reg3) return launch_gnn_m<40, 20, 3, false>(ctx, a);
+        return tb ? launch_gnn_m<40, 20, 0, true>(ctx, a) : launch_gnn_m<40, 20, 0, false>(ctx, a);
     }
-    if (g->H == 20 && g->M == 20) return launch_gnn_t<20, 20, 0, false>(ctx, a);
-    if (g->H == 64 && g->M == 32) return launch_gnn_t<64, 32, 0, false>(ctx, a);
+    if (g->H == 20 && g->M == 20) return launch_gnn_m<20, 20, 0, false>(ctx, a);
+    if (g->H == 64 && g->M == 32) return launch_gnn_m<64, 32, 0, false>(ctx, a);
     return fail(FBGNN_E_UNSUPPORTED, "unsupported GNN dimensions");
 }
 

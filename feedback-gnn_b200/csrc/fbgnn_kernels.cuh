@@ -55,11 +55,60 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 
 __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
 
+// ------------------------------------------------------------------ math policies -----
+// MathExact: the arithmetic specification (fb_math.h) -- software exp/log/tanh on the FP32 pipe,
+// bit-identical to the CPU oracle.  This is the default and the path every parity test covers.
+// MathFast (opt-in, fbgnn_ctx_set_math): the same formulas with the MUFU approximations
+// ex2.approx / lg2.approx / rcp.approx (2 ulp each).  Not bit-exact; statistically equivalent
+// (tests/test_gpu_fastmath.py) and ~2.5x faster because the path becomes SFU-bound.
+struct MathExact {
+    static __device__ __forceinline__ float softplus(float x) { return fb_softplusf(x); }
+    static __device__ __forceinline__ float logaddexp(float a, float b) { return fb_logaddexpf(a, b); }
+    static __device__ __forceinline__ float phi4(float x) { return fb_phi4f(x); }
+    static __device__ __forceinline__ float phi2(float x) { return fb_phi2f(x); }
+    static __device__ __forceinline__ float tanh(float x) { return fb_tanhf(x); }
+    static __device__ __forceinline__ float atanh(float x) { return fb_atanhf(x); }
+};
+
+struct MathFast {
+    static __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+    static __device__ __forceinline__ float exp(float x) { return ex2(x * 1.4426950408889634f); }
+    static __device__ __forceinline__ float log(float x) { return lg2(x) * 0.6931471805599453f; }
+    static __device__ __forceinline__ float softplus(float x) {
+        const float e = exp(fminf(x, FB_SOFTPLUS_THR));
+        const float r = (x < -FB_SOFTPLUS_THR) ? e : log(1.0f + e);
+        return (x > FB_SOFTPLUS_THR) ? x : r;
+    }
+    static __device__ __forceinline__ float logaddexp(float a, float b) {
+        const float mx = fmaxf(a, b), mn = fminf(a, b);
+        return log(1.0f + exp(mn - mx)) + mx;
+    }
+    static __device__ __forceinline__ float phi4(float x) {
+        x = fminf(fmaxf(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI);
+        const float e = exp(x);
+        const float sp = (x > FB_SOFTPLUS_THR) ? x : log(1.0f + e);
+        return sp - log(fmaxf(e - 1.0f, 1.1920929e-7f));     // exp(clip_lo) must not round to 1
+    }
+    static __device__ __forceinline__ float phi2(float x) {
+        x = fminf(fmaxf(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI);
+        const float e = exp(x);
+        return log(e + 1.0f) - log(fmaxf(e - 1.0f, 1.1920929e-7f));
+    }
+    static __device__ __forceinline__ float tanh(float x) {
+        const float t = ex2(fabsf(x) * -2.8853900817779268f);          // exp(-2|x|)
+        const float r = (1.0f - t) * rcp(1.0f + t);
+        return copysignf(r, x);
+    }
+    static __device__ __forceinline__ float atanh(float x) { return 0.5f * (log(1.0f + x) - log(1.0f - x)); }
+};
+
 // ------------------------------------------------------------------ check nodes -------
 // Update one check node in place: msg[] holds v2c on entry, c2v on exit.  Two passes over
 // the check's edges; pass 1 parks phi(|m|) in the message slot and the signs in a bit mask
 // (check degree <= 64 is enforced when the graph is created).
-template <bool PHI4>
+template <bool PHI4, typename MATH>
 __device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge, int k0, int k1,
                                               float *msg, int synd_bit, int cn_type, float factor) {
     if (cn_type == 0) {
@@ -72,14 +121,14 @@ __device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge,
             const int neg = m < 0.0f;
             mask |= (unsigned long long)neg << (k - k0);
             par ^= neg;
-            const float a = PHI4 ? fb_phi4f(fabsf(m)) : fb_phi2f(fabsf(m));
+            const float a = PHI4 ? MATH::phi4(fabsf(m)) : MATH::phi2(fabsf(m));
             msg[e] = a;
             T = FB_ADD(T, a);
         }
         for (int k = k0; k < k1; k++) {
             const int e = cn_edge[k];
             const float x = FB_SUB(T, msg[e]);
-            float v = PHI4 ? fb_phi4f(x) : fb_phi2f(x);
+            float v = PHI4 ? MATH::phi4(x) : MATH::phi2(x);
             const int s = par ^ (int)((mask >> (k - k0)) & 1ull);
             v = s ? -v : v;
             msg[e] = FB_MUL(v, factor);
@@ -88,7 +137,7 @@ __device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge,
         float P = 1.0f;
         for (int k = k0; k < k1; k++) {
             const int e = cn_edge[k];
-            float t = fb_tanhf(FB_MUL(msg[e], 0.5f));
+            float t = MATH::tanh(FB_MUL(msg[e], 0.5f));
             if (t == 0.0f) t = 1e-12f;
             msg[e] = t;
             P = FB_MUL(P, t);
@@ -99,7 +148,7 @@ __device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge,
             float v = FB_MUL(FB_DIV(1.0f, msg[e]), P);
             if (fabsf(v) < 1e-7f) v = 0.0f;
             v = FB_FMIN(FB_FMAX(v, -FB_ATANH_CLIP), FB_ATANH_CLIP);
-            v = FB_MUL(2.0f, fb_atanhf(v));
+            v = FB_MUL(2.0f, MATH::atanh(v));
             msg[e] = FB_MUL(v, factor);
         }
     } else {
@@ -146,7 +195,7 @@ __device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge,
 // ranges are v*DV.. and c*DC.., all loops unroll, the phi values and signs of a check stay in
 // registers and the DC (or 2*DV) independent phi / logaddexp chains give the scheduler ILP.
 // Operation order is exactly that of the generic path (and of the oracle).
-template <int DC>
+template <int DC, bool PHI4, typename MATH>
 __device__ __forceinline__ void cn_phi_regular(const idx_t *__restrict__ cn_edge, int c, float *msg,
                                                int synd_bit, float factor) {
     int e[DC];
@@ -161,21 +210,21 @@ __device__ __forceinline__ void cn_phi_regular(const idx_t *__restrict__ cn_edge
         const uint32_t sgn = (m < 0.0f) ? 1u : 0u;
         neg |= sgn << k;
         par ^= (int)sgn;
-        a[k] = fb_phi4f(fabsf(m));
+        a[k] = PHI4 ? MATH::phi4(fabsf(m)) : MATH::phi2(fabsf(m));
     }
     float T = 0.0f;
 #pragma unroll
     for (int k = 0; k < DC; k++) T = FB_ADD(T, a[k]);
 #pragma unroll
     for (int k = 0; k < DC; k++) {
-        float v = fb_phi4f(FB_SUB(T, a[k]));
+        float v = PHI4 ? MATH::phi4(FB_SUB(T, a[k])) : MATH::phi2(FB_SUB(T, a[k]));
         const uint32_t s = ((uint32_t)par ^ (neg >> k)) & 1u;
         v = __int_as_float(__float_as_int(v) ^ (int)(s << 31));
         msg[e[k]] = FB_MUL(v, factor);
     }
 }
 
-template <int DV>
+template <int DV, typename MATH>
 __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, float px, float py, float pz) {
     float ax[DV], az[DV];
 #pragma unroll
@@ -188,13 +237,13 @@ __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, f
     const float ly = FB_ADD(FB_ADD(Sz, Sx), py);
     const float lx = FB_ADD(Sz, px);
     const float lz = FB_ADD(Sx, pz);
-    const float num_hx = fb_softplusf(-lx), num_hz = fb_softplusf(-lz);
+    const float num_hx = MATH::softplus(-lx), num_hz = MATH::softplus(-lz);
 #pragma unroll
     for (int k = 0; k < DV; k++)
-        mx[v * DV + k] = FB_SUB(num_hx, fb_logaddexpf(-FB_SUB(lz, ax[k]), -FB_SUB(ly, ax[k])));
+        mx[v * DV + k] = FB_SUB(num_hx, MATH::logaddexp(-FB_SUB(lz, ax[k]), -FB_SUB(ly, ax[k])));
 #pragma unroll
     for (int k = 0; k < DV; k++)
-        mz[v * DV + k] = FB_SUB(num_hz, fb_logaddexpf(-FB_SUB(lx, az[k]), -FB_SUB(ly, az[k])));
+        mz[v * DV + k] = FB_SUB(num_hz, MATH::logaddexp(-FB_SUB(lx, az[k]), -FB_SUB(ly, az[k])));
 }
 
 // ------------------------------------------------------------------ quaternary BP -----
@@ -220,7 +269,7 @@ struct Bp4Args {
 
 // One CTA decodes one frame.  Dynamic shared memory:
 //   float msg_x[E_x], msg_z[E_z], pri[CONST_PRIOR ? 2n : 3n];  u8 sbx[m_x], sbz[m_z], dec[n]
-template <bool CONST_PRIOR, int DV, int DC>
+template <bool CONST_PRIOR, int DV, int DC, typename MATH>
 __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     extern __shared__ float smem[];
     const SideDev &X = a.X, &Z = a.Z;
@@ -244,7 +293,7 @@ __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
             const float py = CONST_PRIOR ? a.prior : pri[n + v];
             const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
             if (DV > 0) {
-                vn_update_regular<(DV > 0 ? DV : 1)>(v, mx, mz, px, py, pz);
+                vn_update_regular<(DV > 0 ? DV : 1), MATH>(v, mx, mz, px, py, pz);
                 continue;
             }
             const int x0 = X.vn_ptr[v], x1 = X.vn_ptr[v + 1], z0 = Z.vn_ptr[v], z1 = Z.vn_ptr[v + 1];
@@ -254,14 +303,14 @@ __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
             const float ly = FB_ADD(FB_ADD(Sz, Sx), py);
             const float lx = FB_ADD(Sz, px);
             const float lz = FB_ADD(Sx, pz);
-            const float num_hx = fb_softplusf(-lx), num_hz = fb_softplusf(-lz);
+            const float num_hx = MATH::softplus(-lx), num_hz = MATH::softplus(-lz);
             for (int e = x0; e < x1; e++) {
                 const float m = mx[e];
-                mx[e] = FB_SUB(num_hx, fb_logaddexpf(-FB_SUB(lz, m), -FB_SUB(ly, m)));
+                mx[e] = FB_SUB(num_hx, MATH::logaddexp(-FB_SUB(lz, m), -FB_SUB(ly, m)));
             }
             for (int e = z0; e < z1; e++) {
                 const float m = mz[e];
-                mz[e] = FB_SUB(num_hz, fb_logaddexpf(-FB_SUB(lx, m), -FB_SUB(ly, m)));
+                mz[e] = FB_SUB(num_hz, MATH::logaddexp(-FB_SUB(lx, m), -FB_SUB(ly, m)));
             }
         }
         __syncthreads();
@@ -272,10 +321,10 @@ __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
             float *msg = isx ? mx : mz;
             const int sb = isx ? sbx[cc] : sbz[cc];
             if (fast) {
-                cn_phi_regular<(DC > 0 ? DC : 1)>(isx ? X.cn_edge : Z.cn_edge, cc, msg, sb, a.factor);
+                cn_phi_regular<(DC > 0 ? DC : 1), true, MATH>(isx ? X.cn_edge : Z.cn_edge, cc, msg, sb, a.factor);
             } else {
                 const SideDev &S = isx ? X : Z;
-                cn_update_one<true>(S.cn_edge, S.cn_ptr[cc], S.cn_ptr[cc + 1], msg, sb, a.cn_type, a.factor);
+                cn_update_one<true, MATH>(S.cn_edge, S.cn_ptr[cc], S.cn_ptr[cc + 1], msg, sb, a.cn_type, a.factor);
             }
         }
         __syncthreads();
@@ -305,12 +354,12 @@ __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         if (lz < best) { best = lz; d = 2; }
         if (ly < best) { best = ly; d = 3; }
         if (want_logits) {
-            const float llr_zp = FB_SUB(fb_softplusf(-lx), fb_logaddexpf(-lz, -ly));
-            const float llr_xp = FB_SUB(fb_softplusf(-lz), fb_logaddexpf(-lx, -ly));
+            const float llr_zp = FB_SUB(MATH::softplus(-lx), MATH::logaddexp(-lz, -ly));
+            const float llr_xp = FB_SUB(MATH::softplus(-lz), MATH::logaddexp(-lx, -ly));
             d |= (llr_xp < 0.0f) << 2;
             d |= (llr_zp < 0.0f) << 3;
-            pri[v] = fb_phi4f(fabsf(llr_xp));
-            pri[n + v] = fb_phi4f(fabsf(llr_zp));
+            pri[v] = MATH::phi4(fabsf(llr_xp));
+            pri[n + v] = MATH::phi4(fabsf(llr_zp));
         }
         dec[v] = (uint8_t)d;
     }
@@ -335,7 +384,7 @@ __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         }
         mismatch |= dpar ^ (isx ? sbx[cc] : sbz[cc]);
         if (want_logits) {
-            float val = fb_phi4f(Tsum);
+            float val = MATH::phi4(Tsum);
             val = par ? -val : val;
             if (isx) { if (a.zl.ptr) a.zl(cc, b) = val; }
             else     { if (a.xl.ptr) a.xl(cc, b) = val; }
@@ -372,8 +421,9 @@ struct Bp2Args {
     uint8_t *vbits;                     // optional [B][n]: the hard decision goes to bit 2 (pipeline mode)
 };
 
-// smem: float msg[E], llr[n]; u8 sb[m]
-__global__ void k_bp2(const Bp2Args a) {
+// smem: float msg[E], llr[n]; u8 sb[m].  (DV, DC) > 0: regular graph, unrolled (boxplus-phi only).
+template <int DV, int DC, typename MATH>
+__global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
     extern __shared__ float smem[];
     const SideDev &S = a.S;
     const int n = S.n, T = blockDim.x, tid = threadIdx.x;
@@ -388,8 +438,22 @@ __global__ void k_bp2(const Bp2Args a) {
     }
     for (int c = tid; c < S.m; c += T) sb[c] = a.synd.ptr ? a.synd(c, b) : 0;
     __syncthreads();
+    const bool fast = DV > 0 && a.cn_type == 0;
     for (int it = 0; it < a.num_iter; it++) {
         for (int v = tid; v < n; v += T) {
+            if (DV > 0) {
+                constexpr int D = DV > 0 ? DV : 1;
+                float m[D];
+#pragma unroll
+                for (int k = 0; k < D; k++) m[k] = msg[v * D + k];
+                float s = 0.0f;
+#pragma unroll
+                for (int k = 0; k < D; k++) s = FB_ADD(s, m[k]);
+                s = FB_ADD(s, llr[v]);
+#pragma unroll
+                for (int k = 0; k < D; k++) msg[v * D + k] = FB_SUB(s, m[k]);
+                continue;
+            }
             const int e0 = S.vn_ptr[v], e1 = S.vn_ptr[v + 1];
             float s = 0.0f;
             for (int e = e0; e < e1; e++) s = FB_ADD(s, msg[e]);
@@ -397,8 +461,10 @@ __global__ void k_bp2(const Bp2Args a) {
             for (int e = e0; e < e1; e++) msg[e] = FB_SUB(s, msg[e]);
         }
         __syncthreads();
-        for (int c = tid; c < S.m; c += T)
-            cn_update_one<false>(S.cn_edge, S.cn_ptr[c], S.cn_ptr[c + 1], msg, sb[c], a.cn_type, a.factor);
+        for (int c = tid; c < S.m; c += T) {
+            if (fast) cn_phi_regular<(DC > 0 ? DC : 1), false, MATH>(S.cn_edge, c, msg, sb[c], a.factor);
+            else cn_update_one<false, MATH>(S.cn_edge, S.cn_ptr[c], S.cn_ptr[c + 1], msg, sb[c], a.cn_type, a.factor);
+        }
         __syncthreads();
     }
     for (int v = tid; v < n; v += T) {
@@ -442,8 +508,9 @@ template <int H, int M> struct GnnLayout {
     static constexpr int total = b0 + pad4(3);
 };
 
+template <typename MATH>
 __device__ __forceinline__ float gnn_act(int act, float x) {
-    if (act == 0) return fb_tanhf(x);
+    if (act == 0) return MATH::tanh(x);
     if (act == 1) return x > 0.0f ? x : 0.0f;
     return x;
 }
@@ -458,7 +525,7 @@ __device__ __forceinline__ float gnn_act(int act, float x) {
 // The two sides share ONE copy of the inner loop (side loop not unrolled) and the loop over hidden
 // units is not unrolled: the hot loop body stays ~2 KB, inside the instruction cache.
 // Requires H % 4 == 0 and M % 4 == 0.
-template <int H, int M, int DV, bool TANH_BIAS>
+template <int H, int M, int DV, bool TANH_BIAS, typename MATH>
 __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
     typedef GnnLayout<H, M> Lay;
     extern __shared__ float w[];
@@ -510,7 +577,7 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
                     for (int k = 0; k < NE; k++) {
                         float t = FB_FMA(hc[k], w0, base);
                         if (use_bias) t = FB_ADD(t, bj);
-                        hv[k] = gnn_act(act, t);
+                        hv[k] = gnn_act<MATH>(act, t);
                     }
                     const float *w2r = W2 + j * M;
 #pragma unroll
@@ -566,7 +633,7 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
                 const float4 bb = *reinterpret_cast<const float4 *>(w + Lay::b3 + j);
                 h0 = FB_ADD(h0, bb.x); h1 = FB_ADD(h1, bb.y); h2 = FB_ADD(h2, bb.z); h3 = FB_ADD(h3, bb.w);
             }
-            const float hh[4] = { gnn_act(act, h0), gnn_act(act, h1), gnn_act(act, h2), gnn_act(act, h3) };
+            const float hh[4] = { gnn_act<MATH>(act, h0), gnn_act<MATH>(act, h1), gnn_act<MATH>(act, h2), gnn_act<MATH>(act, h3) };
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
                 const float *w0 = w + Lay::W0 + (j + jj) * 3;

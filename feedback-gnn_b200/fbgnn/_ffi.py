@@ -54,6 +54,8 @@ _SIGNATURES = {
     "fbgnn_timer_start": [C.c_void_p],
     "fbgnn_timer_stop": [C.c_void_p, C.POINTER(C.c_float)],
     "fbgnn_launch_count": [C.c_void_p, C.POINTER(C.c_int64)],
+    "fbgnn_ctx_set_math": [C.c_void_p, C.c_int32],
+    "fbgnn_ctx_get_math": [C.c_void_p, C.POINTER(C.c_int32)],
     "fbgnn_malloc": [C.c_void_p, C.c_size_t, _vpp],
     "fbgnn_free": [C.c_void_p, C.c_void_p],
     "fbgnn_memset": [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t],
@@ -136,6 +138,15 @@ class Context:
     def sync(self):
         call("fbgnn_ctx_sync", self.handle)
 
+    def set_math(self, mode):
+        """"exact" (default; bit-identical to the CPU oracle) or "fast" (MUFU approximations)."""
+        call("fbgnn_ctx_set_math", self.handle, {"exact": 0, "fast": 1}[mode])
+
+    def get_math(self):
+        m = C.c_int32()
+        call("fbgnn_ctx_get_math", self.handle, C.byref(m))
+        return ["exact", "fast"][m.value]
+
     def timer_start(self):
         call("fbgnn_timer_start", self.handle)
 
@@ -206,6 +217,8 @@ def default_context():
     if _default_ctx is None:
         dev = int(os.environ.get("FBGNN_DEVICE", os.environ.get("LOCAL_RANK", "0")))
         _default_ctx = Context(dev)
+        if os.environ.get("FBGNN_MATH", "exact") != "exact":
+            _default_ctx.set_math(os.environ["FBGNN_MATH"])
     return _default_ctx
 
 

@@ -56,6 +56,10 @@ extern "C" {
 #define FBGNN_CN_TANH    1           /* "boxplus"     */
 #define FBGNN_CN_MINSUM  2           /* "minsum"      */
 
+/* arithmetic of the decoders (fbgnn_ctx_set_math) */
+#define FBGNN_MATH_EXACT 0           /* default: software exp/log/tanh, bit-identical to the CPU oracle */
+#define FBGNN_MATH_FAST  1           /* MUFU ex2/lg2/rcp approximations: ~2 ulp per call, not bit-exact  */
+
 /* Feedback_GNN options */
 #define FBGNN_ACT_TANH   0
 #define FBGNN_ACT_RELU   1
@@ -85,6 +89,9 @@ int fbgnn_ctx_device(fbgnn_ctx *ctx, int *device, int *num_sms, char *name, int 
 /* CUDA-event timer on the context's stream (what bench.py times kernels with) */
 int fbgnn_timer_start(fbgnn_ctx *ctx);
 int fbgnn_timer_stop(fbgnn_ctx *ctx, float *elapsed_ms);          /* synchronises */
+/* Arithmetic mode used by the kernels this context launches from now on (FBGNN_MATH_*). */
+int fbgnn_ctx_set_math(fbgnn_ctx *ctx, int32_t mode);
+int fbgnn_ctx_get_math(fbgnn_ctx *ctx, int32_t *mode);
 /* number of kernel launches this context has enqueued so far */
 int fbgnn_launch_count(fbgnn_ctx *ctx, int64_t *launches);
 
