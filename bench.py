@@ -163,7 +163,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fbgnn", choices=["fbgnn", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=16384, help="frames per step per GPU")
+    ap.add_argument("--frames-per-step", type=int, default=32768, help="frames per step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

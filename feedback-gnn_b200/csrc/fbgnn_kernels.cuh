@@ -62,6 +62,7 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.96
 // ex2.approx / lg2.approx / rcp.approx (2 ulp each).  Not bit-exact; statistically equivalent
 // (tests/test_gpu_fastmath.py) and ~2.5x faster because the path becomes SFU-bound.
 struct MathExact {
+    static constexpr bool kSaturationShortcuts = true;
     static __device__ __forceinline__ float softplus(float x) { return fb_softplusf(x); }
     static __device__ __forceinline__ float logaddexp(float a, float b) { return fb_logaddexpf(a, b); }
     static __device__ __forceinline__ float phi4(float x) { return fb_phi4f(x); }
@@ -71,6 +72,7 @@ struct MathExact {
 };
 
 struct MathFast {
+    static constexpr bool kSaturationShortcuts = false;   // its phi is not exactly constant at the clips
     static __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
     static __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
     static __device__ __forceinline__ float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -104,6 +106,40 @@ struct MathFast {
     static __device__ __forceinline__ float atanh(float x) { return 0.5f * (log(1.0f + x) - log(1.0f - x)); }
 };
 
+// ------------------------------------------------------------------ saturated fast paths
+// Value-dependent shortcuts that return exactly what the full evaluation returns:
+//   phi(x) = phi(clip_hi) = +0          for x >= 16.635532,
+//   phi(x) = phi(clip_lo) = 16.635532   for x <= 8.5e-8      (tests/test_math.py pins both), and
+//   logaddexp(a, b) = 0 + max(a, b)     when min - max < -17.5 (exp < 2^-25, so 1 + exp rounds to 1
+//                                        and log(1) = 0).
+// Once a frame has converged nearly every message sits in these regimes; a warp whose lanes are all
+// saturated skips the polynomial evaluation altogether (the vote only decides whether the full path
+// is executed, never which value a lane takes).
+template <typename MATH, bool PHI4>
+__device__ __forceinline__ float phi_sat(float x) {
+    if (!MATH::kSaturationShortcuts) return PHI4 ? MATH::phi4(x) : MATH::phi2(x);
+    const bool hi = x >= FB_PHI_CLIP_HI, lo = x <= FB_PHI_CLIP_LO;
+    float r = hi ? 0.0f : FB_PHI_CLIP_HI;
+    if (__any_sync(__activemask(), !(hi || lo))) {
+        const float f = PHI4 ? MATH::phi4(x) : MATH::phi2(x);
+        r = (hi || lo) ? r : f;
+    }
+    return r;
+}
+
+template <typename MATH>
+__device__ __forceinline__ float logaddexp_sat(float a, float b) {
+    if (!MATH::kSaturationShortcuts) return MATH::logaddexp(a, b);
+    const float mx = fmaxf(a, b), mn = fminf(a, b);
+    const bool sat = FB_SUB(mn, mx) < -17.5f;
+    float r = FB_ADD(0.0f, mx);
+    if (__any_sync(__activemask(), !sat)) {
+        const float f = MATH::logaddexp(a, b);
+        r = sat ? r : f;
+    }
+    return r;
+}
+
 // ------------------------------------------------------------------ check nodes -------
 // Update one check node in place: msg[] holds v2c on entry, c2v on exit.  Two passes over
 // the check's edges; pass 1 parks phi(|m|) in the message slot and the signs in a bit mask
@@ -121,14 +157,14 @@ __device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge,
             const int neg = m < 0.0f;
             mask |= (unsigned long long)neg << (k - k0);
             par ^= neg;
-            const float a = PHI4 ? MATH::phi4(fabsf(m)) : MATH::phi2(fabsf(m));
+            const float a = phi_sat<MATH, PHI4>(fabsf(m));
             msg[e] = a;
             T = FB_ADD(T, a);
         }
         for (int k = k0; k < k1; k++) {
             const int e = cn_edge[k];
             const float x = FB_SUB(T, msg[e]);
-            float v = PHI4 ? MATH::phi4(x) : MATH::phi2(x);
+            float v = phi_sat<MATH, PHI4>(x);
             const int s = par ^ (int)((mask >> (k - k0)) & 1ull);
             v = s ? -v : v;
             msg[e] = FB_MUL(v, factor);
@@ -210,14 +246,14 @@ __device__ __forceinline__ void cn_phi_regular(const idx_t *__restrict__ cn_edge
         const uint32_t sgn = (m < 0.0f) ? 1u : 0u;
         neg |= sgn << k;
         par ^= (int)sgn;
-        a[k] = PHI4 ? MATH::phi4(fabsf(m)) : MATH::phi2(fabsf(m));
+        a[k] = phi_sat<MATH, PHI4>(fabsf(m));
     }
     float T = 0.0f;
 #pragma unroll
     for (int k = 0; k < DC; k++) T = FB_ADD(T, a[k]);
 #pragma unroll
     for (int k = 0; k < DC; k++) {
-        float v = PHI4 ? MATH::phi4(FB_SUB(T, a[k])) : MATH::phi2(FB_SUB(T, a[k]));
+        float v = phi_sat<MATH, PHI4>(FB_SUB(T, a[k]));
         const uint32_t s = ((uint32_t)par ^ (neg >> k)) & 1u;
         v = __int_as_float(__float_as_int(v) ^ (int)(s << 31));
         msg[e[k]] = FB_MUL(v, factor);
@@ -240,10 +276,10 @@ __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, f
     const float num_hx = MATH::softplus(-lx), num_hz = MATH::softplus(-lz);
 #pragma unroll
     for (int k = 0; k < DV; k++)
-        mx[v * DV + k] = FB_SUB(num_hx, MATH::logaddexp(-FB_SUB(lz, ax[k]), -FB_SUB(ly, ax[k])));
+        mx[v * DV + k] = FB_SUB(num_hx, logaddexp_sat<MATH>(-FB_SUB(lz, ax[k]), -FB_SUB(ly, ax[k])));
 #pragma unroll
     for (int k = 0; k < DV; k++)
-        mz[v * DV + k] = FB_SUB(num_hz, MATH::logaddexp(-FB_SUB(lx, az[k]), -FB_SUB(ly, az[k])));
+        mz[v * DV + k] = FB_SUB(num_hz, logaddexp_sat<MATH>(-FB_SUB(lx, az[k]), -FB_SUB(ly, az[k])));
 }
 
 // ------------------------------------------------------------------ quaternary BP -----
@@ -306,11 +342,11 @@ __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
             const float num_hx = MATH::softplus(-lx), num_hz = MATH::softplus(-lz);
             for (int e = x0; e < x1; e++) {
                 const float m = mx[e];
-                mx[e] = FB_SUB(num_hx, MATH::logaddexp(-FB_SUB(lz, m), -FB_SUB(ly, m)));
+                mx[e] = FB_SUB(num_hx, logaddexp_sat<MATH>(-FB_SUB(lz, m), -FB_SUB(ly, m)));
             }
             for (int e = z0; e < z1; e++) {
                 const float m = mz[e];
-                mz[e] = FB_SUB(num_hz, MATH::logaddexp(-FB_SUB(lx, m), -FB_SUB(ly, m)));
+                mz[e] = FB_SUB(num_hz, logaddexp_sat<MATH>(-FB_SUB(lx, m), -FB_SUB(ly, m)));
             }
         }
         __syncthreads();
@@ -567,7 +603,7 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
                 for (int k = 0; k < NE; k++)
 #pragma unroll
                     for (int i = 0; i < M; i++) acc[k][i] = 0.0f;
-#pragma unroll 1
+#pragma unroll 2
                 for (int j = 0; j < H; j++) {
                     // features [h_cn, Lx, Ly, Lz]: the per-variable terms first, the check term last
                     const float base = FB_FMA(f3, W1[3 * H + j], FB_FMA(f2, W1[2 * H + j], FB_FMA(f1, W1[H + j], 0.0f)));

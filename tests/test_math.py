@@ -68,3 +68,21 @@ def test_phi_against_float32_numpy(oracle, rng):
     scale = np.spacing(np.maximum(x, np.abs(np.log(x))).astype(np.float32))
     assert np.all(np.abs(a - b) <= 4 * scale + 1.5 * 2.0 ** -23 / x)
     assert np.mean(a == b) > 0.5
+
+
+def test_saturation_identities_used_by_the_kernels(oracle, rng):
+    """The CUDA kernels skip the polynomial evaluation when every lane of a warp is saturated
+    (fbgnn_kernels.cuh: phi_sat, logaddexp_sat).  These are the identities that makes exact."""
+    hi = np.concatenate([[16.635532], rng.uniform(16.635532, 200, 100000), [1e30]]).astype(np.float32)
+    lo = np.concatenate([[8.5e-8, 0.0, -0.0], -rng.uniform(0, 200, 100000), rng.uniform(0, 8.5e-8, 1000)]).astype(np.float32)
+    for fn in ("phi4f", "phi2f"):
+        assert np.all(oracle.math_fn(fn, hi).view(np.uint32) == 0)                          # +0.0
+        assert np.all(oracle.math_fn(fn, lo).view(np.uint32) == np.float32(16.635532).view(np.uint32))
+    a = rng.uniform(-120, 120, 1000000).astype(np.float32)
+    b = (a + rng.uniform(-60, 0, 1000000)).astype(np.float32)
+    mx, mn = np.maximum(a, b), np.minimum(a, b)
+    sat = (mn - mx).astype(np.float32) < np.float32(-17.5)
+    r = oracle.math_fn("logaddexpf", a, b)
+    assert sat.sum() > 100000
+    assert np.array_equal(r[sat].view(np.uint32), (np.float32(0) + mx[sat]).view(np.uint32))
+    assert np.array_equal(oracle.math_fn("logaddexpf", b, a)[sat].view(np.uint32), r[sat].view(np.uint32))
