@@ -447,8 +447,9 @@ static int set_smem(K kernel, size_t bytes, fbgnn_ctx *ctx, const char *what) {
     return 0;
 }
 
-static size_t bp4_smem(const SideDev &X, const SideDev &Z, bool const_prior) {
-    return sizeof(float) * ((size_t)X.E + Z.E + (const_prior ? 2 : 3) * (size_t)X.n) + X.m + Z.m + X.n + 16;
+static size_t bp4_smem(const SideDev &X, const SideDev &Z, bool const_prior, bool iter_logits) {
+    return sizeof(float) * ((size_t)X.E + Z.E + ((const_prior ? 2 : 3) + (iter_logits ? 2 : 0)) * (size_t)X.n) +
+           X.m + Z.m + X.n + 16;
 }
 
 template <bool CP, int DV, int DC, typename MATH>
@@ -472,7 +473,7 @@ static int launch_bp4_m(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t s
 static int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {
     if (grid <= 0) return 0;
     const bool cp = a.llr.ptr == nullptr;
-    const size_t smem = bp4_smem(a.X, a.Z, cp);
+    const size_t smem = bp4_smem(a.X, a.Z, cp, a.iter_logits.ptr != nullptr);
     const int threads = pick_threads(a.X.n, a.X.m + a.Z.m);
     // both sides regular with the same degrees -> unrolled instantiation
     int dv = 0, dc = 0;
@@ -534,7 +535,7 @@ extern "C" int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_i
                                 fbgnn_tensor3 llr, float prior, fbgnn_tensor2 synd_x, fbgnn_tensor2 synd_z,
                                 fbgnn_tensor2 Lx, fbgnn_tensor2 Ly, fbgnn_tensor2 Lz, fbgnn_tensor2 x_hat,
                                 fbgnn_tensor2 z_hat, fbgnn_tensor2 x_logit, fbgnn_tensor2 z_logit,
-                                fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z) {
+                                fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z, fbgnn_tensor3 iter_logits) {
     REQUIRE(code, "code is NULL");
     REQUIRE(cn_type >= 0 && cn_type <= 2, "unknown cn_type %d", cn_type);
     REQUIRE(num_iter >= 0 && B >= 0, "num_iter and B must be non-negative");
@@ -550,6 +551,7 @@ extern "C" int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_i
     a.xh = v2<uint8_t>(x_hat); a.zh = v2<uint8_t>(z_hat);
     a.xl = v2<float>(x_logit); a.zl = v2<float>(z_logit);
     a.msg_x = v2<float>(msg_x); a.msg_z = v2<float>(msg_z);
+    a.iter_logits = v3<float>(iter_logits);
     return launch_bp4(ctx, a, B);
 }
 

@@ -295,6 +295,8 @@ struct Bp4Args {
     View2<uint8_t> xh, zh;              // (b, v)   optional (layer mode)
     View2<float> xl, zl;                // (row, b) optional: x_logit over hz rows, z_logit over hx rows
     View2<float> msg_x, msg_z;          // (b, e)   optional dump of the final c2v messages
+    View3<float> iter_logits;           // (slot, row, b) optional: soft syndromes before every iteration and after
+                                        // the last (slot 2*it = x_logit, 2*it+1 = z_logit; decoding_q.py:743-746)
     // pipeline mode (vbits != nullptr): decision + activity bookkeeping of feedback_gnn.py:322-340
     uint8_t *vbits;                     // [B][n], bits 2,3 receive the decision of active frames
     const uint8_t *active_in;           // [B] or nullptr (= all active)
@@ -303,16 +305,60 @@ struct Bp4Args {
     int *next_list, *next_count;        // optional compaction of still-active frames
 };
 
+// Soft syndromes of the current message state (stage_two / trainable output of the reference):
+// marginals from the messages, llr_x' / llr_z', then per check row sign * phi(sum phi(|.|)).
+// scr: 2n floats of scratch, sgn: n bytes.  Generic (CSR) loops; not on the evaluation hot path.
+template <bool CONST_PRIOR, typename MATH>
+__device__ void bp4_iter_logits(const Bp4Args &a, const float *mx, const float *mz, const float *pri,
+                                float *scr, uint8_t *sgn, int64_t b, int slot) {
+    const SideDev &X = a.X, &Z = a.Z;
+    const int n = X.n, T = blockDim.x, tid = threadIdx.x;
+    for (int v = tid; v < n; v += T) {
+        float Sx = 0.0f, Sz = 0.0f;
+        for (int e = X.vn_ptr[v]; e < X.vn_ptr[v + 1]; e++) Sx = FB_ADD(Sx, mx[e]);
+        for (int e = Z.vn_ptr[v]; e < Z.vn_ptr[v + 1]; e++) Sz = FB_ADD(Sz, mz[e]);
+        const float px = CONST_PRIOR ? a.prior : pri[v];
+        const float py = CONST_PRIOR ? a.prior : pri[n + v];
+        const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
+        const float ly = FB_ADD(FB_ADD(Sz, Sx), py);
+        const float lx = FB_ADD(Sz, px);
+        const float lz = FB_ADD(Sx, pz);
+        const float llr_zp = FB_SUB(MATH::softplus(-lx), MATH::logaddexp(-lz, -ly));
+        const float llr_xp = FB_SUB(MATH::softplus(-lz), MATH::logaddexp(-lx, -ly));
+        sgn[v] = (uint8_t)(((llr_xp < 0.0f) ? 1 : 0) | ((llr_zp < 0.0f) ? 2 : 0));
+        scr[v] = MATH::phi4(fabsf(llr_xp));
+        scr[n + v] = MATH::phi4(fabsf(llr_zp));
+    }
+    __syncthreads();
+    for (int c = tid; c < X.m + Z.m; c += T) {
+        const bool isx = c < X.m;                       // hx row -> z_logit (from llr_z'), hz row -> x_logit
+        const SideDev &S = isx ? X : Z;
+        const int cc = isx ? c : c - X.m;
+        const float *sc = isx ? scr + n : scr;
+        int par = 0;
+        float Tsum = 0.0f;
+        for (int k = S.cn_ptr[cc]; k < S.cn_ptr[cc + 1]; k++) {
+            const int v = S.cn_vn[k];
+            par ^= (sgn[v] >> (isx ? 1 : 0)) & 1;
+            Tsum = FB_ADD(Tsum, sc[v]);
+        }
+        float val = MATH::phi4(Tsum);
+        val = par ? -val : val;
+        a.iter_logits(2 * slot + (isx ? 1 : 0), cc, b) = val;
+    }
+    __syncthreads();
+}
+
 // One CTA decodes one frame.  Dynamic shared memory:
-//   float msg_x[E_x], msg_z[E_z], pri[CONST_PRIOR ? 2n : 3n];  u8 sbx[m_x], sbz[m_z], dec[n]
+//   float msg_x[E_x], msg_z[E_z], pri[CONST_PRIOR ? 2n : 3n], (scr[2n] if iter_logits);  u8 sbx[m_x], sbz[m_z], dec[n]
 template <bool CONST_PRIOR, int DV, int DC, typename MATH>
 __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     extern __shared__ float smem[];
     const SideDev &X = a.X, &Z = a.Z;
     const int n = X.n, T = blockDim.x, tid = threadIdx.x;
     const int64_t b = a.frame_list ? a.frame_list[blockIdx.x] : blockIdx.x;
-    float *mx = smem, *mz = mx + X.E, *pri = mz + Z.E;
-    uint8_t *sbx = (uint8_t *)(pri + (CONST_PRIOR ? 2 : 3) * n), *sbz = sbx + X.m, *dec = sbz + Z.m;
+    float *mx = smem, *mz = mx + X.E, *pri = mz + Z.E, *scr2 = pri + (CONST_PRIOR ? 2 : 3) * n;
+    uint8_t *sbx = (uint8_t *)(scr2 + (a.iter_logits.ptr ? 2 * n : 0)), *sbz = sbx + X.m, *dec = sbz + Z.m;
 
     for (int e = tid; e < X.E + Z.E; e += T) mx[e] = 0.0f;
     if (!CONST_PRIOR)
@@ -323,6 +369,7 @@ __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
 
     const bool fast = DV > 0 && a.cn_type == 0;     // regular graph + boxplus-phi: unrolled path
     for (int it = 0; it < a.num_iter; it++) {
+        if (a.iter_logits.ptr) bp4_iter_logits<CONST_PRIOR, MATH>(a, mx, mz, pri, scr2, dec, b, it);
         // variable nodes (decoding_q.py:227-275)
         for (int v = tid; v < n; v += T) {
             const float px = CONST_PRIOR ? a.prior : pri[v];
@@ -366,6 +413,7 @@ __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         __syncthreads();
     }
 
+    if (a.iter_logits.ptr) bp4_iter_logits<CONST_PRIOR, MATH>(a, mx, mz, pri, scr2, dec, b, a.num_iter);
     if (a.msg_x.ptr) for (int e = tid; e < X.E; e += T) a.msg_x(b, e) = mx[e];
     if (a.msg_z.ptr) for (int e = tid; e < Z.E; e += T) a.msg_z(b, e) = mz[e];
 

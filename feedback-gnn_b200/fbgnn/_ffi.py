@@ -76,7 +76,7 @@ _SIGNATURES = {
     "fbgnn_syndrome": [C.c_void_p, C.c_int64, Tensor2, Tensor2],
     "fbgnn_bp4_decode": [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int64, Tensor3, C.c_float,
                          Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2,
-                         Tensor2, Tensor2],
+                         Tensor2, Tensor2, Tensor3],
     "fbgnn_bp2_decode": [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int64, Tensor2, Tensor2, Tensor2,
                          Tensor2],
     "fbgnn_gnn_create": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [_f32p] * 12 + [_vpp],

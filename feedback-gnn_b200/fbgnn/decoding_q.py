@@ -44,9 +44,9 @@ class QLDPCBPDecoder:
                  **kwargs):
         if cn_type not in CN_TYPES:
             raise ValueError('Unknown node type.')
-        if trainable or stage_two:
-            raise NotImplementedError("trainable / stage_two (per-iteration soft syndromes for training) "
-                                      "are outside the inference hot path of this build")
+        if trainable:
+            raise NotImplementedError("trainable=True (gradients through BP) is outside the inference hot path "
+                                      "of this build; stage_two=True gives the same forward outputs")
         self._code = code
         self._cn_type = cn_type
         self._hard_out = hard_out
@@ -104,6 +104,13 @@ class QLDPCBPDecoder:
         sz = ctx.asarray(_to_u8(syndrome_z), np.uint8)
         if sx.shape != (mx, B) or sz.shape != (mz, B):
             raise ValueError(f"syndromes must have shapes [{mx},{B}] and [{mz},{B}]")
+        if self._stage_two and not self._stage_one:
+            # (llr_hat [2*num_iter+2, m, B], x_hat, z_hat): decoding_q.py:794-795
+            out = self.decode_device(llr, sx, sz, want_logits=False, want_iter_logits=True)
+            xh, zh, llr_hat = out[3], out[4], out[-1]
+            if on_device:
+                return llr_hat, xh, zh
+            return llr_hat.numpy(), xh.numpy().astype(np.int64), zh.numpy().astype(np.float64)
         out = self.decode_device(llr, sx, sz, want_logits=self._stage_one)
         Lx, Ly, Lz, xh, zh, xl, zl = out
         if self._stage_one:
@@ -117,7 +124,7 @@ class QLDPCBPDecoder:
 
     call = __call__
 
-    def decode_device(self, llr, sx, sz, want_logits=True, want_msgs=False, prior=None):
+    def decode_device(self, llr, sx, sz, want_logits=True, want_msgs=False, prior=None, want_iter_logits=False):
         """Device-level entry: ``llr`` DeviceArray [B,3,n] (or None with a scalar ``prior``),
         syndromes DeviceArray [m,B].  Returns DeviceArrays (Lx, Ly, Lz [B,n] f32, x_hat, z_hat
         [B,n] u8, x_logit [m_z,B], z_logit [m_x,B] f32 or None) (+ msg_x, msg_z [B,E])."""
@@ -135,13 +142,19 @@ class QLDPCBPDecoder:
         msgs = ()
         if want_msgs:
             msgs = (ctx.empty((B, dev.Ex), np.float32), ctx.empty((B, dev.Ez), np.float32))
+        il = ()
+        if want_iter_logits:
+            if mx != mz:
+                raise ValueError("per-iteration soft syndromes need hx and hz with the same number of rows")
+            il = (ctx.empty((2 * self._num_iter + 2, B, mx), np.float32).transpose((0, 2, 1)),)
         t2 = lambda a: a.t2() if a is not None else _ffi.NULL2
         _ffi.call("fbgnn_bp4_decode", dev.handle, CN_TYPES[self._cn_type], self._num_iter,
                   self._normalization_factor, B,
                   llr.t3() if llr is not None else _ffi.NULL3, float(prior or 0.0),
                   sx.t2(), sz.t2(), Lx.t2(), Ly.t2(), Lz.t2(), xh.t2(), zh.t2(), t2(xl), t2(zl),
-                  msgs[0].t2() if want_msgs else _ffi.NULL2, msgs[1].t2() if want_msgs else _ffi.NULL2)
-        return (Lx, Ly, Lz, xh, zh, xl, zl) + msgs
+                  msgs[0].t2() if want_msgs else _ffi.NULL2, msgs[1].t2() if want_msgs else _ffi.NULL2,
+                  il[0].t3() if want_iter_logits else _ffi.NULL3)
+        return (Lx, Ly, Lz, xh, zh, xl, zl) + msgs + il
 
 
 def _to_u8(s):

@@ -147,13 +147,16 @@ int fbgnn_syndrome(fbgnn_graph *graph, int64_t B, fbgnn_tensor2 noise, fbgnn_ten
  *              soft syndromes; NULL ptr -> not computed
  *   msg_x/msg_z float32 views indexed (b, edge) receiving the final check-to-variable
  *              messages in VN-sorted edge order (teacher-forced parity tests); NULL -> skipped
+ *   iter_logits float32 view indexed (slot, row, b), 2*num_iter+2 slots: the soft syndromes before
+ *              every iteration and after the last -- the llr_hat of the reference's stage_two /
+ *              trainable mode (decoding_q.py:730, 743-746, 779-781); NULL -> skipped
  */
 int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
                      fbgnn_tensor3 llr, float prior, fbgnn_tensor2 synd_x, fbgnn_tensor2 synd_z,
                      fbgnn_tensor2 Lx, fbgnn_tensor2 Ly, fbgnn_tensor2 Lz,
                      fbgnn_tensor2 x_hat, fbgnn_tensor2 z_hat,
                      fbgnn_tensor2 x_logit, fbgnn_tensor2 z_logit,
-                     fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z);
+                     fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z, fbgnn_tensor3 iter_logits);
 
 /* LDPCBPDecoder.call with is_syndrome.  llr: float32 logits (b,v); synd: uint8 (c,b) or
  * NULL ptr (no syndrome); soft: float32 (b,v) output logits; hard: uint8 (b,v) or NULL. */

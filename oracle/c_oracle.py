@@ -172,7 +172,7 @@ def bsc(seed, first_frame, B, n, p):
 
 
 def bp4(g, llr, syndrome_x, syndrome_z, num_iter, factor=1.0, cn_type="boxplus-phi",
-        rows_x=None, rows_z=None, want_msgs=False):
+        rows_x=None, rows_z=None, want_msgs=False, want_iter_logits=False):
     """llr [B,3,n] f32 (or a float: constant prior); syndromes [m,B] 0/1.
     rows_x / rows_z: matrices whose rows define x_logit / z_logit (default: hz / hx, the
     stage_one choice of decoding_q.py:35-37).  Returns a dict."""
@@ -193,11 +193,14 @@ def bp4(g, llr, syndrome_x, syndrome_z, num_iter, factor=1.0, cn_type="boxplus-p
     if want_msgs:
         out["msg_x"] = np.empty((B, g.X.E), np.float32)
         out["msg_z"] = np.empty((B, g.Z.E), np.float32)
+    if want_iter_logits:                # stage_two / trainable output, decoding_q.py:730,743-746,779-781
+        assert rx.m == rz.m
+        out["llr_hat"] = np.empty((2 * num_iter + 2, rx.m, B), np.float32)
     lib().orc_bp4(C.byref(g.X.c), C.byref(g.Z.c), C.byref(rx.c), C.byref(rz.c),
                   C.c_int(CN_TYPES[cn_type]), C.c_int(num_iter), C.c_float(factor), C.c_int64(B),
                   _p(llr_arr), C.c_float(prior), _p(sx), _p(sz), _p(out["Lx"]), _p(out["Ly"]),
                   _p(out["Lz"]), _p(out["x_hat"]), _p(out["z_hat"]), _p(out["x_logit"]),
-                  _p(out["z_logit"]), _p(out.get("msg_x")), _p(out.get("msg_z")))
+                  _p(out["z_logit"]), _p(out.get("msg_x")), _p(out.get("msg_z")), _p(out.get("llr_hat")))
     return out
 
 

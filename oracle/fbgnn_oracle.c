@@ -285,14 +285,35 @@ static void bp4_logits(int n, const orc_rows_t *rows_x, const orc_rows_t *rows_z
 
 /* One frame of QLDPCBPDecoder.call.  mx/mz: work [E_x]/[E_z]; on exit they hold the c2v
  * messages of the last iteration (VN order). */
-static void bp4_frame(const orc_side_t *X, const orc_side_t *Z, int cn_type, int num_iter,
-                      float factor, const float *llrx, const float *llry, const float *llrz,
-                      const uint8_t *sx, const uint8_t *sz, float *mx, float *mz,
-                      float *Lx, float *Ly, float *Lz, uint8_t *xh, uint8_t *zh, float *work) {
+typedef struct {               /* optional per-iteration soft syndromes (stage_two / trainable,      */
+    const orc_rows_t *rows_x;  /* decoding_q.py:743-746, 779-781): slot 2*it = x_logit, 2*it+1 = z_logit */
+    const orc_rows_t *rows_z;
+    float *out;                /* [2*num_iter+2][m][B] */
+    int64_t B, b;
+    int m;
+    float *wa;                 /* work [2n] */
+} orc_iterlog_t;
+
+static void iterlog_write(const orc_iterlog_t *il, int n, int slot, const float *Lx, const float *Ly,
+                          const float *Lz, float *xl, float *zl) {
+    bp4_logits(n, il->rows_x, il->rows_z, Lx, Ly, Lz, xl, zl, il->wa, il->wa + n);
+    for (int r = 0; r < il->rows_x->m; r++) il->out[((int64_t)(2 * slot) * il->m + r) * il->B + il->b] = xl[r];
+    for (int r = 0; r < il->rows_z->m; r++) il->out[((int64_t)(2 * slot + 1) * il->m + r) * il->B + il->b] = zl[r];
+}
+
+static void bp4_frame_il(const orc_side_t *X, const orc_side_t *Z, int cn_type, int num_iter,
+                         float factor, const float *llrx, const float *llry, const float *llrz,
+                         const uint8_t *sx, const uint8_t *sz, float *mx, float *mz,
+                         float *Lx, float *Ly, float *Lz, uint8_t *xh, uint8_t *zh, float *work,
+                         const orc_iterlog_t *il, float *xl, float *zl) {
     const int n = X->n;
     memset(mx, 0, sizeof(float) * (size_t)X->E);
     memset(mz, 0, sizeof(float) * (size_t)Z->E);
     for (int it = 0; it < num_iter; it++) {
+        if (il) {              /* marginals the VN update of this iteration is about to compute */
+            bp4_marginals(X, Z, mx, mz, llrx, llry, llrz, Lx, Ly, Lz);
+            iterlog_write(il, n, it, Lx, Ly, Lz, xl, zl);
+        }
         /* VN update, decoding_q.py:227-275 */
         for (int v = 0; v < n; v++) {
             float Sx = 0.0f, Sz = 0.0f;
@@ -316,6 +337,7 @@ static void bp4_frame(const orc_side_t *X, const orc_side_t *Z, int cn_type, int
         cn_update(Z, cn_type, 1, factor, sz, mz, work);
     }
     bp4_marginals(X, Z, mx, mz, llrx, llry, llrz, Lx, Ly, Lz);
+    if (il) iterlog_write(il, n, num_iter, Lx, Ly, Lz, xl, zl);
     /* argmin over [0, Lx, Lz, Ly], first minimum wins (decoding_q.py:786-790) */
     for (int v = 0; v < n; v++) {
         int d = 0;
@@ -328,6 +350,14 @@ static void bp4_frame(const orc_side_t *X, const orc_side_t *Z, int cn_type, int
     }
 }
 
+static void bp4_frame(const orc_side_t *X, const orc_side_t *Z, int cn_type, int num_iter,
+                      float factor, const float *llrx, const float *llry, const float *llrz,
+                      const uint8_t *sx, const uint8_t *sz, float *mx, float *mz,
+                      float *Lx, float *Ly, float *Lz, uint8_t *xh, uint8_t *zh, float *work) {
+    bp4_frame_il(X, Z, cn_type, num_iter, factor, llrx, llry, llrz, sx, sz, mx, mz, Lx, Ly, Lz, xh, zh,
+                 work, NULL, NULL, NULL);
+}
+
 /* Batched QLDPCBPDecoder.call with the reference's tensor layouts:
  *   llr [B,3,n] (or NULL: the scalar `prior` is used for all three), synd_x [m_x,B],
  *   synd_z [m_z,B] (uint8 0/1), outputs Lx,Ly,Lz [B,n] f32, x_hat,z_hat [B,n] u8,
@@ -337,7 +367,7 @@ void orc_bp4(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *rows_x,
              const orc_rows_t *rows_z, int cn_type, int num_iter, float factor, int64_t B,
              const float *llr, float prior, const uint8_t *synd_x, const uint8_t *synd_z,
              float *Lx, float *Ly, float *Lz, uint8_t *x_hat, uint8_t *z_hat,
-             float *x_logit, float *z_logit, float *msg_x, float *msg_z) {
+             float *x_logit, float *z_logit, float *msg_x, float *msg_z, float *llr_hat) {
     const int n = X->n, mxn = X->m, mzn = Z->m;
     int wd = max_cn_degree(X), wz = max_cn_degree(Z);
     if (wz > wd) wd = wz;
@@ -356,8 +386,10 @@ void orc_bp4(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *rows_x,
             for (int v = 0; v < 3 * n; v++) pri[v] = llr ? llr[b * 3 * n + v] : prior;
             for (int c = 0; c < mxn; c++) sx[c] = synd_x[(int64_t)c * B + b];
             for (int c = 0; c < mzn; c++) sz[c] = synd_z[(int64_t)c * B + b];
-            bp4_frame(X, Z, cn_type, num_iter, factor, pri, pri + n, pri + 2 * n, sx, sz, mx, mz,
-                      Lx + b * n, Ly + b * n, Lz + b * n, x_hat + b * n, z_hat + b * n, work);
+            orc_iterlog_t il = { rows_x, rows_z, llr_hat, B, b, rows_x ? rows_x->m : 0, wa };
+            bp4_frame_il(X, Z, cn_type, num_iter, factor, pri, pri + n, pri + 2 * n, sx, sz, mx, mz,
+                         Lx + b * n, Ly + b * n, Lz + b * n, x_hat + b * n, z_hat + b * n, work,
+                         llr_hat ? &il : NULL, xl, zl);
             if (x_logit || z_logit) {
                 bp4_logits(n, x_logit ? rows_x : NULL, z_logit ? rows_z : NULL, Lx + b * n,
                            Ly + b * n, Lz + b * n, xl, zl, wa, wa + n);

@@ -55,6 +55,25 @@ def test_bp4_layer_bitexact(codes, oracle, name, B, p, cn_type, factor):
         assert_bitexact(d[8].numpy(), ref["msg_z"], f"{name} {cn_type} it={it} msg_z")
 
 
+@pytest.mark.parametrize("name", ["c882", "toric4"])
+def test_bp4_stage_two_per_iteration_soft_syndromes(codes, oracle, name):
+    """stage_two=True returns (llr_hat [2*num_iter+2, m, B], x_hat, z_hat) (decoding_q.py:794-795)."""
+    import fbgnn as F
+    code = codes[name]
+    B, it = 24, 6
+    nx, nz, sx, sz = _noise_and_syndromes(oracle, code, B, 0.08, seed=13)
+    rng = np.random.default_rng(5)
+    llr = (oracle.prior_llr(0.05) + rng.normal(0, 0.2, (B, 3, code.N))).astype(np.float32)
+    dec = F.QLDPCBPDecoder(code, num_iter=it, normalization_factor=1.0, cn_type="boxplus-phi", stage_two=True)
+    llr_hat, x_hat, z_hat = dec((llr, sx, sz))
+    ref = oracle.bp4(oracle.CodeGraph(code), llr, sx, sz, it, 1.0, "boxplus-phi", want_iter_logits=True)
+    assert llr_hat.shape == (2 * it + 2, code.hx.shape[0], B)
+    assert_bitexact(llr_hat, ref["llr_hat"], f"{name} llr_hat")
+    assert_bitexact(x_hat.astype(np.uint8), ref["x_hat"], "x_hat")
+    assert_bitexact(z_hat.astype(np.uint8), ref["z_hat"], "z_hat")
+    assert_bitexact(llr_hat[2 * it], ref["x_logit"], "last slot == x_logit")
+
+
 def test_bp4_output_dtypes_and_plain_mode(codes, oracle):
     import fbgnn as F
     code = codes["c882"]
