@@ -502,6 +502,22 @@ extern "C" int fbgnn_pauli_sample(fbgnn_ctx *ctx, int32_t n, int64_t B, const fl
     return 0;
 }
 
+extern "C" int fbgnn_pauli_sample_wt(fbgnn_ctx *ctx, int32_t n, int64_t B, int32_t wt, uint64_t seed,
+                                     uint64_t first_frame, fbgnn_tensor2 noise_x, fbgnn_tensor2 noise_z) {
+    REQUIRE(ctx && n > 0 && n <= 65535 && B >= 0 && wt >= 0, "bad argument");
+    REQUIRE(noise_x.ptr && noise_z.ptr, "noise outputs are NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    if (B == 0) return 0;
+    SampleArgs a{};
+    a.X.n = n; a.mode = 2; a.wt = wt;
+    a.seed = seed; a.first_frame = first_frame;
+    a.nx_out = v2<uint8_t>(noise_x); a.nz_out = v2<uint8_t>(noise_z);
+    k_sample<<<(unsigned)B, 128, (size_t)3 * n + 8, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 extern "C" int fbgnn_bsc_sample(fbgnn_ctx *ctx, int32_t n, int64_t B, float p, uint64_t seed,
                                 uint64_t first_frame, fbgnn_tensor2 noise) {
     REQUIRE(ctx && n > 0 && B >= 0 && noise.ptr, "bad argument");
@@ -749,12 +765,12 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
 
     // noise + syndromes
     SampleArgs sa{};
-    sa.X = X; sa.Z = Z; sa.mode = 0;
+    sa.X = X; sa.Z = Z; sa.mode = cfg->fixed_weight > 0 ? 2 : 0; sa.wt = cfg->fixed_weight;
     sa.thr0 = cfg->thr[0]; sa.thr1 = cfg->thr[1]; sa.thr2 = cfg->thr[2];
     sa.seed = seed; sa.first_frame = first_frame;
     sa.nx_in = v2<const uint8_t>(noise_x); sa.nz_in = v2<const uint8_t>(noise_z);
     sa.vbits = w.vbits; sa.sbits = w.sbits;
-    k_sample<<<(unsigned)B, 128, (size_t)n, st>>>(sa);
+    k_sample<<<(unsigned)B, 128, (size_t)3 * n + 8, st>>>(sa);
     CK(cudaGetLastError());
     ctx->launches++;
 

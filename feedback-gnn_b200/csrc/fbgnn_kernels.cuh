@@ -736,7 +736,8 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
 // ------------------------------------------------------------------ noise + syndrome --
 struct SampleArgs {
     SideDev X, Z;                       // Z.n == 0 for the binary (single pcm) pipeline
-    int mode;                           // 0 Pauli depolarising, 1 BSC
+    int mode;                           // 0 Pauli depolarising, 1 BSC, 2 Pauli of fixed weight `wt` (pauli.py:80-96)
+    int wt;
     float thr0, thr1, thr2;             // Pauli thresholds, or thr0 = p for BSC
     uint64_t seed, first_frame;
     View2<const uint8_t> nx_in, nz_in;  // optional given noise (b, v)
@@ -745,7 +746,13 @@ struct SampleArgs {
     View2<uint8_t> nx_out, nz_out;      // optional separate outputs (Pauli / BSC layer API)
 };
 
-// smem: u8 nb[n]
+__device__ __forceinline__ float frame_uniform(uint64_t seed, uint64_t frame, uint32_t q, uint32_t stream) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)frame, (uint32_t)(frame >> 32), q >> 2, stream, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    return u01(r[q & 3]);
+}
+
+// smem: u8 nb[n] (+ u16 idx[n] in fixed-weight mode)
 __global__ void k_sample(const SampleArgs a) {
     extern __shared__ uint8_t nb[];
     const int n = a.X.n, T = blockDim.x, tid = threadIdx.x;
@@ -754,6 +761,21 @@ __global__ void k_sample(const SampleArgs a) {
     if (a.nx_in.ptr) {
         for (int v = tid; v < n; v += T)
             nb[v] = (a.nx_in(b, v) ? 1 : 0) | ((a.nz_in.ptr && a.nz_in(b, v)) ? 2 : 0);
+    } else if (a.mode == 2) {
+        // partial Fisher-Yates: the first wt entries of a shuffle, then the Pauli type of each position
+        uint16_t *idx = (uint16_t *)(nb + ((n + 1) & ~1));
+        for (int v = tid; v < n; v += T) { idx[v] = (uint16_t)v; nb[v] = 0; }
+        __syncthreads();
+        if (tid == 0) {
+            const int wt = a.wt < n ? a.wt : n;
+            for (int i = 0; i < wt; i++) {
+                const float u = frame_uniform(a.seed, frame, (uint32_t)i, 2u);
+                const int j = i + (int)FB_MUL(u, (float)(n - i));
+                const uint16_t t = idx[i]; idx[i] = idx[j]; idx[j] = t;
+                const float w = frame_uniform(a.seed, frame, (uint32_t)i, 3u);
+                nb[idx[i]] = (uint8_t)((w < 0.6666667f ? 1 : 0) | (w > 0.33333334f ? 2 : 0));
+            }
+        }
     } else {
         for (int q4 = tid; q4 < (n + 3) / 4; q4 += T) {
             uint32_t r[4];
@@ -765,7 +787,7 @@ __global__ void k_sample(const SampleArgs a) {
                 if (q < n) {
                     const float u = u01(r[j]);
                     int bits;
-                    if (a.mode == 0) bits = (u < a.thr0 ? 1 : 0) | ((u >= a.thr1 && u < a.thr2) ? 2 : 0);
+                    if (a.mode != 1) bits = (u < a.thr0 ? 1 : 0) | ((u >= a.thr1 && u < a.thr2) ? 2 : 0);
                     else bits = (u < a.thr0) ? 1 : 0;
                     nb[q] = (uint8_t)bits;
                 }
@@ -782,7 +804,7 @@ __global__ void k_sample(const SampleArgs a) {
             const bool isx = c < a.X.m;                  // syndrome_x = hx . noise_z (bit1);
             const SideDev &S = isx ? a.X : a.Z;          // syndrome_z = hz . noise_x (bit0)
             const int cc = isx ? c : c - a.X.m;
-            const int bit = (isx && a.mode == 0) ? 1 : 0;
+            const int bit = (isx && a.mode != 1) ? 1 : 0;
             int par = 0;
             for (int k = S.cn_ptr[cc]; k < S.cn_ptr[cc + 1]; k++) par ^= (nb[S.cn_vn[k]] >> bit) & 1;
             sb[c] = (uint8_t)par;

@@ -34,7 +34,7 @@ class PipelineCfg(C.Structure):
     _fields_ = [("num_stages", C.c_int32), ("num_iter", C.POINTER(C.c_int32)),
                 ("factor", C.POINTER(C.c_float)), ("cn_type", C.POINTER(C.c_int32)),
                 ("gnn", C.POINTER(C.c_void_p)), ("prior", C.c_float), ("thr", C.c_float * 3),
-                ("skip_inactive", C.c_int32)]
+                ("fixed_weight", C.c_int32), ("skip_inactive", C.c_int32)]
 
 
 NULL2 = Tensor2(None, 0, 0)
@@ -72,6 +72,7 @@ _SIGNATURES = {
     "fbgnn_code_destroy": [C.c_void_p],
     "fbgnn_code_edges": [C.c_void_p, _i32p, _i32p],
     "fbgnn_pauli_sample": [C.c_void_p, C.c_int32, C.c_int64, _f32p, C.c_uint64, C.c_uint64, Tensor2, Tensor2],
+    "fbgnn_pauli_sample_wt": [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, Tensor2, Tensor2],
     "fbgnn_bsc_sample": [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_uint64, Tensor2],
     "fbgnn_syndrome": [C.c_void_p, C.c_int64, Tensor2, Tensor2],
     "fbgnn_bp4_decode": [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int64, Tensor3, C.c_float,

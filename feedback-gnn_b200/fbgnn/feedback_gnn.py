@@ -202,8 +202,6 @@ class Sandwich_BP_GNN_Evaluation_Model:
 
     def __init__(self, code, decoders, feedbacks, num_layers=4, wt=False, p0=0.05, seed=0, first_frame=0,
                  skip_inactive=False, ctx=None):
-        if wt:
-            raise NotImplementedError("wt=True (fixed-weight training noise) is outside the evaluation hot path")
         self.k, self.n = code.K, code.N
         self.code = code
         self.hx, self.hz, self.lx, self.lz = code.hx, code.hz, code.lx, code.lz
@@ -224,6 +222,8 @@ class Sandwich_BP_GNN_Evaluation_Model:
                 raise TypeError("feedbacks must be fbgnn Feedback_GNN layers")
         self.wt = wt
         self.p0 = p0
+        if wt and p0 is None:
+            raise ValueError("wt=True needs an explicit p0 (the model input is then an error weight, not a rate)")
         self.seed = int(seed)
         self.next_frame = int(first_frame)
         self.skip_inactive = bool(skip_inactive)
@@ -246,9 +246,10 @@ class Sandwich_BP_GNN_Evaluation_Model:
         fa = (C.c_float * S)(*[d.normalization_factor for d in self.decoders[:S]])
         ct = (C.c_int32 * S)(*[CN_TYPES[d.cn_type] for d in self.decoders[:S]])
         gh = (C.c_void_p * max(S - 1, 1))(*[g.device_handle(ctx).value for g in self.feedbacks[:S - 1]])
-        thr = pauli_thresholds(float(p))
+        # wt=True: `p` is the error weight (feedback_gnn.py:300-301) and p0 must be given
+        thr = pauli_thresholds(0.0 if self.wt else float(p))
         cfg = _ffi.PipelineCfg(S, ni, fa, ct, gh, float(self.prior(p)), (C.c_float * 3)(*thr),
-                               1 if self.skip_inactive else 0)
+                               int(round(float(p))) if self.wt else 0, 1 if self.skip_inactive else 0)
         nx = nz = _ffi.NULL2
         keep = None
         if noise is not None:

@@ -130,6 +130,10 @@ int fbgnn_code_edges(fbgnn_code *code, int32_t *e_x, int32_t *e_z);
  * noise_x/noise_z: uint8 [B,n] views. */
 int fbgnn_pauli_sample(fbgnn_ctx *ctx, int32_t n, int64_t B, const float thr[3], uint64_t seed,
                        uint64_t first_frame, fbgnn_tensor2 noise_x, fbgnn_tensor2 noise_z);
+/* Pauli.call, wt branch (pauli.py:80-96): exactly `wt` erroneous qubits per frame (partial
+ * Fisher-Yates from Philox stream 2), each X, Y or Z with probability 1/3 (stream 3). */
+int fbgnn_pauli_sample_wt(fbgnn_ctx *ctx, int32_t n, int64_t B, int32_t wt, uint64_t seed,
+                          uint64_t first_frame, fbgnn_tensor2 noise_x, fbgnn_tensor2 noise_z);
 /* Bernoulli(p) flips (stream 1 of the same generator). noise: uint8 [B,n] */
 int fbgnn_bsc_sample(fbgnn_ctx *ctx, int32_t n, int64_t B, float p, uint64_t seed,
                      uint64_t first_frame, fbgnn_tensor2 noise);
@@ -189,6 +193,7 @@ typedef struct {
     fbgnn_gnn *const *gnn;     /* [num_stages-1] host array of handles                       */
     float prior;               /* log(3(1-p0)/p0) as float32                                 */
     float thr[3];              /* Pauli thresholds, see fbgnn_pauli_sample                   */
+    int32_t fixed_weight;      /* > 0: errors of exactly this weight (Pauli wt=True) instead  */
     int32_t skip_inactive;     /* 0: all frames run all rounds (reference-equivalent work)   */
                                /* 1: frames whose decision matches the syndrome stop early   */
                                /*    (result-identical; the reference masks the scatter)     */

@@ -56,7 +56,7 @@ class _Gnn(C.Structure):
 class _PipeCfg(C.Structure):
     _fields_ = [("num_stages", C.c_int32), ("num_iter", C.c_void_p), ("factor", C.c_void_p),
                 ("cn_type", C.c_void_p), ("gnn", C.c_void_p), ("prior", C.c_float),
-                ("skip_inactive", C.c_int32)]
+                ("fixed_weight", C.c_int32), ("skip_inactive", C.c_int32)]
 
 
 def lib():
@@ -164,6 +164,15 @@ def pauli(seed, first_frame, B, n, p):
     return nx, nz
 
 
+def pauli_wt(seed, first_frame, B, n, wt):
+    """Pauli(wt=True): exactly ``wt`` erroneous qubits per frame (pauli.py:80-96)."""
+    nx = np.empty((B, n), np.uint8)
+    nz = np.empty((B, n), np.uint8)
+    lib().orc_pauli_wt(C.c_uint64(seed), C.c_uint64(first_frame), C.c_int64(B), C.c_int(n), C.c_int(int(wt)),
+                       _p(nx), _p(nz))
+    return nx, nz
+
+
 def bsc(seed, first_frame, B, n, p):
     noise = np.empty((B, n), np.uint8)
     lib().orc_bsc(C.c_uint64(seed), C.c_uint64(first_frame), C.c_int64(B), C.c_int(n),
@@ -229,7 +238,7 @@ def gnn(g, G, h_vn, logit_hx, logit_hz, syndrome_x, syndrome_z):
 
 
 def pipeline(g, num_iters, gnns, p, p0=0.05, factors=None, cn_types=None, seed=0, first_frame=0,
-             B=1, noise=None, skip_inactive=False, want_diff=False):
+             B=1, noise=None, skip_inactive=False, want_diff=False, wt=0):
     """Sandwich model: decoders[i] has num_iters[i] iterations; gnns[i] is feedbacks[i].
     Returns dict(flags [B] u8, counters [4] i64, x_diff, z_diff)."""
     S = len(num_iters)
@@ -239,7 +248,7 @@ def pipeline(g, num_iters, gnns, p, p0=0.05, factors=None, cn_types=None, seed=0
     ct = _i32([CN_TYPES[c] for c in (cn_types or ["boxplus-phi"] * S)])
     garr = (C.c_void_p * max(S - 1, 1))(*[C.addressof(G.c) for G in gnns])
     cfg = _PipeCfg(S, _p(ni), _p(fa), _p(ct), C.cast(garr, C.c_void_p),
-                   C.c_float(prior_llr(p if p0 is None else p0)), int(skip_inactive))
+                   C.c_float(prior_llr(p if p0 is None else p0)), int(wt), int(skip_inactive))
     thr = pauli_thresholds(p)
     flags = np.empty(B, np.uint8)
     counters = np.zeros(4, np.int64)

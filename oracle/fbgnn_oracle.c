@@ -114,6 +114,35 @@ static void pauli_frame(uint64_t seed, uint64_t frame, int n, const float thr[3]
     }
 }
 
+/* Pauli.call, wt branch (pauli.py:80-96): `wt` distinct positions per frame (the reference takes
+ * the first wt entries of a shuffle; here a partial Fisher-Yates driven by Philox stream 2), then one
+ * uniform per position (stream 3): u < 2/3 sets the X bit, u > 1/3 the Z bit. */
+static void pauli_wt_frame(uint64_t seed, uint64_t frame, int n, int wt, uint8_t *nx, uint8_t *nz,
+                           uint16_t *idx) {
+    for (int q = 0; q < n; q++) { idx[q] = (uint16_t)q; nx[q] = 0; nz[q] = 0; }
+    if (wt > n) wt = n;
+    for (int i = 0; i < wt; i++) {
+        float u = frame_uniform(seed, frame, (uint32_t)i, 2u);
+        int j = i + (int)FB_MUL(u, (float)(n - i));
+        uint16_t t = idx[i]; idx[i] = idx[j]; idx[j] = t;
+        float w = frame_uniform(seed, frame, (uint32_t)i, 3u);
+        nx[idx[i]] = (uint8_t)(w < 0.6666667f);
+        nz[idx[i]] = (uint8_t)(w > 0.33333334f);
+    }
+}
+
+void orc_pauli_wt(uint64_t seed, uint64_t first_frame, int64_t B, int n, int wt, uint8_t *noise_x,
+                  uint8_t *noise_z) {
+#pragma omp parallel
+    {
+        uint16_t *idx = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)n);
+#pragma omp for schedule(static)
+        for (int64_t b = 0; b < B; b++)
+            pauli_wt_frame(seed, first_frame + (uint64_t)b, n, wt, noise_x + b * n, noise_z + b * n, idx);
+        free(idx);
+    }
+}
+
 void orc_pauli(uint64_t seed, uint64_t first_frame, int64_t B, int n, const float *thr,
                uint8_t *noise_x, uint8_t *noise_z) {
 #pragma omp parallel for schedule(static)
@@ -567,6 +596,7 @@ typedef struct {
     const int32_t *cn_type;      /* [num_stages]                                              */
     const orc_gnn_t *const *gnn; /* [num_stages-1] feedbacks[i]                               */
     float prior;                 /* log(3 (1 - p0) / p0), feedback_gnn.py:311-312              */
+    int32_t fixed_weight;        /* > 0: Pauli(wt=True) errors of exactly this weight (300-301) */
     int32_t skip_inactive;       /* 0: every frame runs every round (reference behaviour);     */
                                  /* 1: stop a frame once its decision matches the syndrome     */
                                  /*    (result-identical, the scatter is masked: 339-340)      */
@@ -650,16 +680,18 @@ void orc_pipeline(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *lx
         float *fw = (float *)malloc(sizeof(float) * pipe_float_work(X, Z, cfg));
         uint8_t *bw = (uint8_t *)malloc((size_t)(X->m + Z->m) * 2 + 8 * (size_t)n + 64);
         uint8_t *nx = (uint8_t *)malloc((size_t)n), *nz = (uint8_t *)malloc((size_t)n);
+        uint16_t *idx = (uint16_t *)malloc(sizeof(uint16_t) * (size_t)n);
 #pragma omp for schedule(dynamic, 1)
         for (int64_t b = 0; b < B; b++) {
             if (noise_x) { memcpy(nx, noise_x + b * n, (size_t)n); memcpy(nz, noise_z + b * n, (size_t)n); }
+            else if (cfg->fixed_weight > 0) pauli_wt_frame(seed, first_frame + (uint64_t)b, n, cfg->fixed_weight, nx, nz, idx);
             else pauli_frame(seed, first_frame + (uint64_t)b, n, thr, nx, nz);
             uint8_t f = pipeline_frame(X, Z, lx, lz, cfg, nx, nz, fw, bw,
                                        x_diff ? x_diff + b * n : NULL, z_diff ? z_diff + b * n : NULL);
             if (flags) flags[b] = f;
             c_flag += f & 1; c_blk += (f >> 1) & 1; c_s1 += ((f >> 2) > 0);
         }
-        free(fw); free(bw); free(nx); free(nz);
+        free(fw); free(bw); free(nx); free(nz); free(idx);
     }
     if (counters) { counters[0] = B; counters[1] = c_flag; counters[2] = c_blk; counters[3] = c_s1; }
 }

@@ -171,6 +171,28 @@ def test_pauli_and_syndrome_bitexact(codes, oracle):
     assert np.array_equal(synd.numpy(), (code.hx @ rz.T.astype(np.int64)) & 1)
 
 
+def test_fixed_weight_pauli_and_model(codes, oracle, weights):
+    """Pauli(wt=True) (pauli.py:80-96) and Sandwich(..., wt=True): exactly wt errors per frame."""
+    import fbgnn as F
+    code = codes["c882"]
+    B, n, wt = 300, code.N, 37
+    ch = F.Pauli(wt=True, seed=11, first_frame=70)
+    nx, nz = ch([np.zeros((B, n), np.float32), None, wt])
+    rx, rz = oracle.pauli_wt(11, 70, B, n, wt)
+    assert np.array_equal(nx, rx.astype(bool)) and np.array_equal(nz, rz.astype(bool))
+    assert np.all((nx | nz).sum(1) == wt)                           # exactly wt erroneous qubits
+    frac = [(nx & ~nz).sum() / (B * wt), (nx & nz).sum() / (B * wt), (~nx & nz).sum() / (B * wt)]
+    assert all(abs(f - 1 / 3) < 0.03 for f in frac)                 # X, Y, Z equally likely
+    G = F.Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, use_bias=True)
+    G.set_weights(weights["c882"])
+    d1 = F.QLDPCBPDecoder(code, num_iter=16, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+    model = F.Sandwich_BP_GNN_Evaluation_Model(code, [d1, d1], [G], num_layers=2, wt=True, p0=0.05, seed=11)
+    res = model.run(128, 60, want_counters=True)
+    ref = oracle.pipeline(oracle.CodeGraph(code), [16, 16], [oracle.Gnn(weights["c882"])], 0.05, p0=0.05, seed=11,
+                          B=128, wt=60)
+    assert np.array_equal(res["flags"].numpy(), ref["flags"]) and np.array_equal(res["counters"], ref["counters"])
+
+
 @pytest.mark.parametrize("name,nG,p,B", [("c882", 1, 0.12, 192), ("c882", 3, 0.12, 160), ("rsurf3", 0, 0.08, 300),
                                          ("gb48", 2, 0.06, 128)])
 @pytest.mark.parametrize("skip", [False, True])

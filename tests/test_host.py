@@ -94,8 +94,6 @@ def test_constructor_validation(codes):
     with pytest.raises(TypeError):
         F.LDPCBPDecoder([[1, 0]])
     with pytest.raises(NotImplementedError):
-        F.Pauli(wt=True)
-    with pytest.raises(NotImplementedError):
         F.QLDPCBPDecoder(code, trainable=True)
     d = F.QLDPCBPDecoder(code)                              # reference defaults, decoding_q.py:18-22
     assert (d.cn_type, d.num_iter, d.normalization_factor) == ("boxplus", 32, 0.625)
