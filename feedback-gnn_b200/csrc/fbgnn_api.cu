@@ -80,6 +80,10 @@ struct fbgnn_code {
     fbgnn_graph *X, *Z;
     int kx = 0, kz = 0, W = 0;
     uint32_t *lx_bits = nullptr, *lz_bits = nullptr;
+    // host copies of the CSR of hx / hz (to cut row bases out of them) and the OSD-0 bases
+    std::vector<int32_t> hx_ptr, hx_idx, hz_ptr, hz_idx;
+    fbgnn_graph *basis_x = nullptr, *basis_z = nullptr;      // hx[pivot_hx], hz[pivot_hz]
+    idx_t *pivot_x = nullptr, *pivot_z = nullptr;            // device [rank]
 };
 
 struct fbgnn_gnn {
@@ -391,6 +395,8 @@ extern "C" int fbgnn_code_create(fbgnn_ctx *ctx, int32_t n, int32_t m_x, const i
     if (!rc && k_z > 0) rc = validate_csr(n, k_z, lz_indptr, lz_indices, "lz");
     if (rc) { fbgnn_code_destroy(c); return rc; }
     c->kx = std::max(k_x, 0); c->kz = std::max(k_z, 0); c->W = (n + 31) / 32;
+    c->hx_ptr.assign(hx_indptr, hx_indptr + m_x + 1); c->hx_idx.assign(hx_indices, hx_indices + hx_indptr[m_x]);
+    c->hz_ptr.assign(hz_indptr, hz_indptr + m_z + 1); c->hz_idx.assign(hz_indices, hz_indices + hz_indptr[m_z]);
     std::vector<uint32_t> bits;
     if (c->kx) {
         pack_rows(n, c->kx, lx_indptr, lx_indices, bits);
@@ -411,9 +417,44 @@ extern "C" int fbgnn_code_destroy(fbgnn_code *c) {
     cudaSetDevice(c->ctx->device);
     fbgnn_graph_destroy(c->X);
     fbgnn_graph_destroy(c->Z);
+    fbgnn_graph_destroy(c->basis_x);
+    fbgnn_graph_destroy(c->basis_z);
+    cudaFree(c->pivot_x);
+    cudaFree(c->pivot_z);
     cudaFree(c->lx_bits);
     cudaFree(c->lz_bits);
     delete c;
+    return 0;
+}
+
+static int make_basis(fbgnn_ctx *ctx, int n, const std::vector<int32_t> &ptr, const std::vector<int32_t> &idx,
+                      int32_t rank, const int32_t *pivot, fbgnn_graph **graph, idx_t **dpivot) {
+    const int m = (int)ptr.size() - 1;
+    std::vector<int32_t> bp(1, 0), bi;
+    std::vector<idx_t> piv(std::max(rank, 1));
+    for (int r = 0; r < rank; r++) {
+        REQUIRE(pivot[r] >= 0 && pivot[r] < m, "pivot row %d out of range", pivot[r]);
+        bi.insert(bi.end(), idx.begin() + ptr[pivot[r]], idx.begin() + ptr[pivot[r] + 1]);
+        bp.push_back((int32_t)bi.size());
+        piv[r] = (idx_t)pivot[r];
+    }
+    if (int rc = fbgnn_graph_create(ctx, n, rank, bp.data(), bi.data(), graph)) return rc;
+    CK(cudaMalloc(dpivot, piv.size() * sizeof(idx_t)));
+    CK(cudaMemcpy(*dpivot, piv.data(), piv.size() * sizeof(idx_t), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+extern "C" int fbgnn_code_set_basis(fbgnn_code *code, int32_t rank_x, const int32_t *pivot_hx, int32_t rank_z,
+                                    const int32_t *pivot_hz) {
+    REQUIRE(code && pivot_hx && pivot_hz && rank_x > 0 && rank_z > 0, "bad argument");
+    if (set_device(code->ctx)) return FBGNN_E_CUDA;
+    fbgnn_graph_destroy(code->basis_x); code->basis_x = nullptr;
+    fbgnn_graph_destroy(code->basis_z); code->basis_z = nullptr;
+    cudaFree(code->pivot_x); code->pivot_x = nullptr;
+    cudaFree(code->pivot_z); code->pivot_z = nullptr;
+    const int n = code->X->dev.n;
+    if (int rc = make_basis(code->ctx, n, code->hx_ptr, code->hx_idx, rank_x, pivot_hx, &code->basis_x, &code->pivot_x)) return rc;
+    if (int rc = make_basis(code->ctx, n, code->hz_ptr, code->hz_idx, rank_z, pivot_hz, &code->basis_z, &code->pivot_z)) return rc;
     return 0;
 }
 
@@ -571,7 +612,7 @@ extern "C" int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_i
     return launch_bp4(ctx, a, B);
 }
 
-static size_t bp2_smem(const SideDev &S) { return sizeof(float) * ((size_t)S.E + S.n) + S.m + 16; }
+static size_t bp2_smem(const SideDev &S) { return sizeof(float) * ((size_t)S.E + S.n) + S.m + S.n + 16; }
 
 template <int DV, int DC, typename MATH>
 static int launch_bp2_t(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B, size_t smem) {
@@ -714,6 +755,36 @@ extern "C" int fbgnn_gnn_forward(fbgnn_code *code, fbgnn_gnn *gnn, int64_t B, fb
     return launch_gnn(ctx, gnn, a);
 }
 
+// ------------------------------------------------------------------ OSD-0 ---------------
+static int launch_osd0(fbgnn_ctx *ctx, Osd0Args &a, int64_t grid) {
+    if (grid <= 0) return 0;
+    const int n = a.S.n, R = a.S.m, W = (n + 1 + 31) / 32, Rp = R | 1;
+    int npad = 1;
+    while (npad < n) npad <<= 1;
+    a.npad = npad;
+    const size_t main_bytes = std::max<size_t>((size_t)npad * 8, (size_t)W * Rp * 4);
+    const size_t smem = ((main_bytes + 7) & ~(size_t)7) + sizeof(uint16_t) * (2 * (size_t)n + R) + 16;
+    if (int rc = set_smem(k_osd0, smem, ctx, "OSD-0")) return rc;
+    k_osd0<<<(unsigned)grid, 256, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+extern "C" int fbgnn_osd0_decode(fbgnn_graph *basis, int64_t B, fbgnn_tensor2 llr, fbgnn_tensor2 synd,
+                                 fbgnn_tensor2 e_hat) {
+    REQUIRE(basis && llr.ptr && synd.ptr && e_hat.ptr && B >= 0, "bad argument");
+    if (int rc = need_decodable(basis)) return rc;
+    fbgnn_ctx *ctx = basis->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    Osd0Args a{};
+    a.S = basis->dev;
+    a.llr = v2<const float>(llr); a.sign = 1.0f;
+    a.synd = v2<const uint8_t>(synd);
+    a.e_hat = v2<uint8_t>(e_hat);
+    return launch_osd0(ctx, a, B);
+}
+
 // ------------------------------------------------------------------ pipelines -----------
 static int ws_reserve(fbgnn_ctx *ctx, int64_t B, int n, int m) {
     Workspace &w = ctx->ws;
@@ -745,6 +816,7 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
     REQUIRE(cfg->num_stages == 1 || cfg->gnn, "feedback GNNs missing");
     REQUIRE((noise_x.ptr == nullptr) == (noise_z.ptr == nullptr), "give both noise_x and noise_z or neither");
     REQUIRE(B >= 0 && B < ((int64_t)1 << 31), "bad batch size");
+    REQUIRE(!cfg->osd0 || (code->basis_x && code->basis_z), "OSD-0 needs fbgnn_code_set_basis first");
     for (int s = 0; s < cfg->num_stages; s++) {
         REQUIRE(cfg->cn_type[s] >= 0 && cfg->cn_type[s] <= 2, "unknown cn_type in stage %d", s);
         REQUIRE(cfg->num_iter[s] >= 0, "negative num_iter in stage %d", s);
@@ -800,18 +872,20 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
         a.prior = cfg->prior;
         a.sx = View2<const uint8_t>{w.sbits, 1, m};
         a.sz = View2<const uint8_t>{w.sbits + X.m, 1, m};
-        if (!last) {
+        if (!last || cfg->osd0) {
             a.Lx = View2<float>{w.L, 3 * (int64_t)n, 1};
             a.Ly = View2<float>{w.L + n, 3 * (int64_t)n, 1};
             a.Lz = View2<float>{w.L + 2 * n, 3 * (int64_t)n, 1};
-            a.zl = View2<float>{w.logit, 1, m};
-            a.xl = View2<float>{w.logit + X.m, 1, m};
+            if (!last) {
+                a.zl = View2<float>{w.logit, 1, m};
+                a.xl = View2<float>{w.logit + X.m, 1, m};
+            }
         }
         a.vbits = w.vbits;
         a.active_in = (s == 0) ? nullptr : w.active[(s - 1) & 1];
         a.active_out = w.active[s & 1];
         a.rounds = last ? nullptr : w.rounds;
-        const bool compact = cfg->skip_inactive && !last;
+        const bool compact = (cfg->skip_inactive && !last) || (last && cfg->osd0);
         if (compact) {
             CK(cudaMemsetAsync(w.list_count + (s & 1), 0, sizeof(int), st));
             a.next_list = w.list[s & 1];
@@ -826,6 +900,27 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
             cur_list = w.list[s & 1];
             if (cur_count == 0) break;
         }
+    }
+
+    if (cfg->osd0 && cur_count > 0 && cur_list) {
+        // BP4_OSD_Model (bp_osd.py:80-197): frames still mismatching get both parts re-solved by OSD-0
+        OsdLlrArgs la{n, cur_list, cur_count, w.L, w.P};
+        const int64_t blocks = std::min<int64_t>((cur_count * n + 255) / 256, (int64_t)ctx->num_sms * 8);
+        if (ctx->math_mode == FBGNN_MATH_FAST) k_osd_llr<MathFast><<<(unsigned)blocks, 256, 0, st>>>(la);
+        else k_osd_llr<MathExact><<<(unsigned)blocks, 256, 0, st>>>(la);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        Osd0Args oa{};
+        oa.frame_list = cur_list; oa.sign = 1.0f;
+        oa.vbits = w.vbits;
+        oa.S = code->basis_x->dev;                                   // hx basis, osd_llrz, syndrome_x -> z_hat
+        oa.llr = View2<const float>{w.P + n, 3 * (int64_t)n, 1};
+        oa.synd = View2<const uint8_t>{w.sbits, 1, m}; oa.synd_row = code->pivot_x; oa.vbit = 3;
+        if (int rc = launch_osd0(ctx, oa, cur_count)) return rc;
+        oa.S = code->basis_z->dev;                                   // hz basis, osd_llrx, syndrome_z -> x_hat
+        oa.llr = View2<const float>{w.P, 3 * (int64_t)n, 1};
+        oa.synd = View2<const uint8_t>{w.sbits + X.m, 1, m}; oa.synd_row = code->pivot_z; oa.vbit = 2;
+        if (int rc = launch_osd0(ctx, oa, cur_count)) return rc;
     }
 
     FinalArgs fa{};
@@ -850,8 +945,11 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
 
 extern "C" int fbgnn_bsc_pipeline_run(fbgnn_graph *g, fbgnn_graph *logical, int32_t cn_type, int32_t num_iter,
                                       float factor, float llr_const, float p, uint64_t seed, uint64_t first_frame,
-                                      int64_t B, fbgnn_tensor2 noise, uint8_t *flags, int64_t *counters) {
+                                      int64_t B, fbgnn_tensor2 noise, uint8_t *flags, int64_t *counters,
+                                      fbgnn_graph *osd_basis, const int32_t *osd_pivot) {
     REQUIRE(g, "graph is NULL");
+    REQUIRE(!osd_basis || (osd_pivot && osd_basis->dev.n == g->dev.n && osd_basis->dev.m <= g->dev.m),
+            "bad OSD-0 basis");
     REQUIRE(cn_type >= 0 && cn_type <= 2, "unknown cn_type %d", cn_type);
     REQUIRE(num_iter >= 0 && B >= 0 && B < ((int64_t)1 << 31), "bad argument");
     REQUIRE(!logical || logical->dev.n == g->dev.n, "logical_pcm has %d columns, pcm has %d",
@@ -880,7 +978,38 @@ extern "C" int fbgnn_bsc_pipeline_run(fbgnn_graph *g, fbgnn_graph *logical, int3
     a.llr_const = llr_const;
     a.synd = View2<const uint8_t>{w.sbits, 1, m};
     a.vbits = w.vbits;                 // decision -> bit 2
+    if (osd_basis) {
+        CK(cudaMemsetAsync(w.list_count, 0, sizeof(int), st));
+        a.soft = View2<float>{w.L, n, 1};
+        a.next_list = w.list[0]; a.next_count = w.list_count;
+    }
     if (int rc = launch_bp2(ctx, a, B)) return rc;
+    if (osd_basis) {
+        // BP2_OSD_Model (bp_osd.py:199-274): OSD-0 on the frames whose decision misses the syndrome
+        if (int rc = need_decodable(osd_basis)) return rc;
+        int cnt = 0;
+        CK(cudaMemcpyAsync(&cnt, w.list_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (cnt > 0) {
+            const int R = osd_basis->dev.m;
+            std::vector<idx_t> piv(R);
+            for (int r = 0; r < R; r++) {
+                REQUIRE(osd_pivot[r] >= 0 && osd_pivot[r] < m, "pivot row out of range");
+                piv[r] = (idx_t)osd_pivot[r];
+            }
+            idx_t *dp = nullptr;
+            CK(cudaMallocAsync(&dp, R * sizeof(idx_t), st));
+            CK(cudaMemcpyAsync(dp, piv.data(), R * sizeof(idx_t), cudaMemcpyHostToDevice, st));
+            Osd0Args oa{};
+            oa.S = osd_basis->dev; oa.frame_list = w.list[0];
+            oa.llr = View2<const float>{w.L, n, 1}; oa.sign = -1.0f;      // llr_hat = -decoder output
+            oa.synd = View2<const uint8_t>{w.sbits, 1, m}; oa.synd_row = dp;
+            oa.vbits = w.vbits; oa.vbit = 2;
+            if (int rc = launch_osd0(ctx, oa, cnt)) return rc;
+            CK(cudaStreamSynchronize(st));                                  // piv must outlive the copy
+            CK(cudaFreeAsync(dp, st));
+        }
+    }
     FinalArgs fa{};
     fa.X = S;
     fa.lx_bits = logical ? logical->dev.bitrows : nullptr;

@@ -503,9 +503,10 @@ struct Bp2Args {
     View2<float> soft;                  // (b, v) optional
     View2<uint8_t> hard;                // (b, v) optional
     uint8_t *vbits;                     // optional [B][n]: the hard decision goes to bit 2 (pipeline mode)
+    int *next_list, *next_count;        // optional: frames whose decision misses the syndrome (for OSD-0)
 };
 
-// smem: float msg[E], llr[n]; u8 sb[m].  (DV, DC) > 0: regular graph, unrolled (boxplus-phi only).
+// smem: float msg[E], llr[n]; u8 sb[m], dec[n].  (DV, DC) > 0: regular graph, unrolled (boxplus-phi only).
 template <int DV, int DC, typename MATH>
 __global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
     extern __shared__ float smem[];
@@ -513,7 +514,7 @@ __global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
     const int n = S.n, T = blockDim.x, tid = threadIdx.x;
     const int64_t b = blockIdx.x;
     float *msg = smem, *llr = msg + S.E;
-    uint8_t *sb = (uint8_t *)(llr + n);
+    uint8_t *sb = (uint8_t *)(llr + n), *dec = sb + S.m;
     for (int e = tid; e < S.E; e += T) msg[e] = 0.0f;
     for (int v = tid; v < n; v += T) {
         float l = a.llr.ptr ? a.llr(b, v) : a.llr_const;
@@ -558,6 +559,18 @@ __global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
         if (a.soft.ptr) a.soft(b, v) = x;
         if (a.hard.ptr) a.hard(b, v) = (uint8_t)(0.0f < x);
         if (a.vbits) a.vbits[b * n + v] = (uint8_t)((a.vbits[b * n + v] & 3) | ((0.0f < x) ? 4 : 0));
+        dec[v] = (uint8_t)(0.0f < x);
+    }
+    if (a.next_list) {
+        __syncthreads();
+        int mismatch = 0;
+        for (int c = tid; c < S.m; c += T) {
+            int par = sb[c];
+            for (int k = S.cn_ptr[c]; k < S.cn_ptr[c + 1]; k++) par ^= dec[S.cn_vn[k]];
+            mismatch |= par;
+        }
+        mismatch = __syncthreads_or(mismatch);
+        if (tid == 0 && mismatch) a.next_list[atomicAdd(a.next_count, 1)] = (int)b;
     }
 }
 
@@ -829,6 +842,152 @@ __global__ void k_syndrome(const SyndromeArgs a) {
     }
 }
 
+// ------------------------------------------------------------------ OSD-0 -------------
+// OSD0_Decoder (bp_osd.py:8-77) for the frames BP left with a syndrome mismatch: order the columns
+// by increasing reliability (stable), then for every row of the full-rank basis take the first
+// remaining one as pivot and eliminate it from all other rows of [H_perm | s]; the solution sits on
+// the pivot columns.  One CTA per frame; the permuted bit matrix lives in shared memory, stored
+// word-major (M[w * Rp + row]) so that the row-parallel XOR sweeps are conflict-free and the pivot
+// row is a broadcast.
+struct Osd0Args {
+    SideDev S;                          // graph of the basis matrix: rows = the rank basis rows
+    const int *frame_list;              // optional: CTA i handles frame frame_list[i]
+    View2<const float> llr;             // (b, v) reliabilities; the sort key is sign * llr
+    float sign;                         // +1, or -1 to sort by -llr (binary decoder's logits)
+    View2<const uint8_t> synd;          // (row, b): reduced syndrome, or the full one with synd_row
+    const idx_t *synd_row;              // optional [rank]: row of the full syndrome behind basis row r
+    View2<uint8_t> e_hat;               // (b, v) optional output
+    uint8_t *vbits;                     // optional [B][n]: the solution goes to bit `vbit` (pipeline mode)
+    int vbit;
+    int npad;                           // power of two >= n
+};
+
+__device__ __forceinline__ unsigned long long osd_key(float x, int idx) {
+    uint32_t u = (uint32_t)__float_as_int(x);
+    u ^= (u >> 31) ? 0xFFFFFFFFu : 0x80000000u;             // order-preserving map float -> uint
+    return ((unsigned long long)u << 32) | (uint32_t)idx;
+}
+
+// smem: max(npad * 8, W * Rp * 4) bytes shared by the sort keys and the matrix; u16 order[n], inv[n], piv[R]
+__global__ void __launch_bounds__(256) k_osd0(const Osd0Args a) {
+    extern __shared__ unsigned long long osd_smem[];
+    const SideDev &S = a.S;
+    const int n = S.n, R = S.m, T = blockDim.x, tid = threadIdx.x;
+    const int W = (n + 1 + 31) / 32, Rp = R | 1;                 // odd stride: no bank conflicts across words
+    const int64_t b = a.frame_list ? a.frame_list[blockIdx.x] : blockIdx.x;
+    unsigned long long *keys = osd_smem;
+    uint32_t *M = (uint32_t *)osd_smem;
+    const size_t main_bytes = ((size_t)a.npad * 8 > (size_t)W * Rp * 4) ? (size_t)a.npad * 8 : (size_t)W * Rp * 4;
+    uint16_t *order = (uint16_t *)((uint8_t *)osd_smem + ((main_bytes + 7) & ~(size_t)7));
+    uint16_t *inv = order + n, *piv = inv + n;
+    __shared__ int cur_p;
+
+    // 1. stable ascending sort of the reliabilities (bitonic network on (key, index) pairs)
+    for (int i = tid; i < a.npad; i += T)
+        keys[i] = i < n ? osd_key(a.sign * a.llr(b, i), i) : ~0ull;
+    __syncthreads();
+    for (int k = 2; k <= a.npad; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < a.npad; i += T) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned long long x = keys[i], y = keys[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { keys[i] = y; keys[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = tid; j < n; j += T) {
+        const int v = (int)(keys[j] & 0xFFFFFFFFull);
+        order[j] = (uint16_t)v;
+        inv[v] = (uint16_t)j;
+    }
+    __syncthreads();
+
+    // 2. permuted [H | s] as a bit matrix, one thread per row
+    for (int i = tid; i < W * Rp; i += T) M[i] = 0u;
+    __syncthreads();
+    for (int r = tid; r < R; r += T) {
+        for (int k = S.cn_ptr[r]; k < S.cn_ptr[r + 1]; k++) {
+            const int j = inv[S.cn_vn[k]];
+            M[(j >> 5) * Rp + r] ^= 1u << (j & 31);
+        }
+        const int sr = a.synd_row ? a.synd_row[r] : r;
+        if (a.synd(sr, b)) M[(n >> 5) * Rp + r] ^= 1u << (n & 31);
+    }
+    __syncthreads();
+
+    // 3. row-wise elimination
+    const int wn = n >> 5;
+    const uint32_t last_mask = (n & 31) ? ((1u << (n & 31)) - 1u) : 0u;   // columns < n inside word wn
+    for (int r = 0; r < R; r++) {
+        if (tid < 32) {
+            int p = 0, found = 0;
+            for (int w0 = 0; w0 < W && !found; w0 += 32) {
+                const int w = w0 + tid;
+                uint32_t word = w < W ? M[w * Rp + r] : 0u;
+                if (w == wn) word &= last_mask;
+                if (w > wn) word = 0u;
+                const uint32_t vote = __ballot_sync(0xffffffffu, word != 0u);
+                if (vote) {
+                    const int lane = __ffs(vote) - 1;
+                    const uint32_t wsel = __shfl_sync(0xffffffffu, word, lane);
+                    p = (w0 + lane) * 32 + (__ffs(wsel) - 1);
+                    found = 1;
+                }
+            }
+            if (tid == 0) { cur_p = p; piv[r] = (uint16_t)p; }
+        }
+        __syncthreads();
+        const int p = cur_p, pw = p >> 5;
+        const uint32_t pm = 1u << (p & 31);
+        for (int i = tid; i < R; i += T) {
+            if (i != r && (M[pw * Rp + i] & pm)) {
+                for (int w = pw; w < W; w++) M[w * Rp + i] ^= M[w * Rp + r];   // the pivot row is zero before word pw
+            }
+        }
+        __syncthreads();
+    }
+
+    // 4. solution on the pivot columns, mapped back through the permutation
+    if (a.e_hat.ptr) for (int v = tid; v < n; v += T) a.e_hat(b, v) = 0;
+    if (a.vbits) for (int v = tid; v < n; v += T) a.vbits[b * n + v] &= (uint8_t)~(1u << a.vbit);
+    __syncthreads();
+    for (int r = tid; r < R; r += T) {
+        const int sol = (M[wn * Rp + r] >> (n & 31)) & 1u;
+        const int v = order[piv[r]];
+        if (sol) {
+            if (a.e_hat.ptr) a.e_hat(b, v) = 1;
+            if (a.vbits) a.vbits[b * n + v] |= (uint8_t)(1u << a.vbit);
+        }
+    }
+}
+
+// reliabilities handed to OSD-0 by BP4_OSD_Model (bp_osd.py:135-144), for the listed frames:
+// out plane 0 = osd_llrx = softplus(-Lz) - logsumexp(-Lx, -Ly), plane 1 = osd_llrz (x <-> z)
+struct OsdLlrArgs {
+    int n;
+    const int *frame_list;
+    int64_t num_frames;
+    const float *L;                     // [B][3][n]
+    float *out;                         // [B][3][n] (planes 0, 1 written)
+};
+template <typename MATH>
+__global__ void k_osd_llr(const OsdLlrArgs a) {
+    const int64_t items = a.num_frames * a.n;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t fi = it / a.n;
+        const int v = (int)(it - fi * a.n);
+        const int64_t b = a.frame_list ? a.frame_list[fi] : fi;
+        const float *L = a.L + b * 3 * a.n;
+        const float lx = L[v], ly = L[a.n + v], lz = L[2 * a.n + v];
+        a.out[b * 3 * a.n + a.n + v] = FB_SUB(MATH::softplus(-lx), MATH::logaddexp(-lz, -ly));
+        a.out[b * 3 * a.n + v] = FB_SUB(MATH::softplus(-lz), MATH::logaddexp(-lx, -ly));
+    }
+}
+
 // ------------------------------------------------------------------ final checks ------
 struct FinalArgs {
     SideDev X, Z;                       // binary pipeline: X = pcm, Z.n == 0
@@ -889,7 +1048,8 @@ __global__ void k_final(const FinalArgs a) {
     flagged = __syncthreads_or(flagged);
     logical = __syncthreads_or(logical);
     if (tid == 0) {
-        const int blk = flagged | logical | ((a.binary && a.kx == 0) ? flagged : 0);
+        // quaternary: any(hx_perp . d) == flagged or logical.  binary (BP_BSC_Model): ls_hat = logical_pcm . d only
+        const int blk = a.binary ? (a.kx > 0 ? logical : flagged) : (flagged | logical);
         const int rnd = a.rounds ? a.rounds[b] : 0;
         if (a.flags) a.flags[b] = (uint8_t)((flagged ? 1 : 0) | (blk ? 2 : 0) | (rnd << 2));
         if (a.counters) {

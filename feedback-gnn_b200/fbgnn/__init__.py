@@ -15,6 +15,7 @@ from .decoding_q import QLDPCBPDecoder
 from .decoding import LDPCBPDecoder
 from .pauli import Pauli, pauli_thresholds
 from .feedback_gnn import (Feedback_GNN, Sandwich_BP_GNN_Evaluation_Model, BP_BSC_Model, ErrorIndicator)
+from .bp_osd import OSD0_Decoder, BP4_OSD_Model, BP2_OSD_Model
 from .utils import count_block_errors, sim_ber, PlotBER
 from ._ffi import (FbgnnError, Context, DeviceArray, default_context, device_count, from_dlpack)
 

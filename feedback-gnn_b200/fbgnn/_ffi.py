@@ -34,7 +34,7 @@ class PipelineCfg(C.Structure):
     _fields_ = [("num_stages", C.c_int32), ("num_iter", C.POINTER(C.c_int32)),
                 ("factor", C.POINTER(C.c_float)), ("cn_type", C.POINTER(C.c_int32)),
                 ("gnn", C.POINTER(C.c_void_p)), ("prior", C.c_float), ("thr", C.c_float * 3),
-                ("fixed_weight", C.c_int32), ("skip_inactive", C.c_int32)]
+                ("fixed_weight", C.c_int32), ("osd0", C.c_int32), ("skip_inactive", C.c_int32)]
 
 
 NULL2 = Tensor2(None, 0, 0)
@@ -71,6 +71,7 @@ _SIGNATURES = {
                           C.c_int32, _i32p, _i32p, C.c_int32, _i32p, _i32p, _vpp],
     "fbgnn_code_destroy": [C.c_void_p],
     "fbgnn_code_edges": [C.c_void_p, _i32p, _i32p],
+    "fbgnn_code_set_basis": [C.c_void_p, C.c_int32, _i32p, C.c_int32, _i32p],
     "fbgnn_pauli_sample": [C.c_void_p, C.c_int32, C.c_int64, _f32p, C.c_uint64, C.c_uint64, Tensor2, Tensor2],
     "fbgnn_pauli_sample_wt": [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_uint64, C.c_uint64, Tensor2, Tensor2],
     "fbgnn_bsc_sample": [C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint64, C.c_uint64, Tensor2],
@@ -80,6 +81,7 @@ _SIGNATURES = {
                          Tensor2, Tensor2, Tensor3],
     "fbgnn_bp2_decode": [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int64, Tensor2, Tensor2, Tensor2,
                          Tensor2],
+    "fbgnn_osd0_decode": [C.c_void_p, C.c_int64, Tensor2, Tensor2, Tensor2],
     "fbgnn_gnn_create": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [_f32p] * 12 + [_vpp],
     "fbgnn_gnn_destroy": [C.c_void_p],
     "fbgnn_gnn_forward": [C.c_void_p, C.c_void_p, C.c_int64, Tensor3, Tensor2, Tensor2, Tensor2, Tensor2,
@@ -87,7 +89,8 @@ _SIGNATURES = {
     "fbgnn_pipeline_run": [C.c_void_p, C.POINTER(PipelineCfg), C.c_uint64, C.c_uint64, C.c_int64, Tensor2,
                            Tensor2, C.c_void_p, Tensor2, Tensor2, C.POINTER(C.c_int64)],
     "fbgnn_bsc_pipeline_run": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
-                               C.c_uint64, C.c_uint64, C.c_int64, Tensor2, C.c_void_p, C.POINTER(C.c_int64)],
+                               C.c_uint64, C.c_uint64, C.c_int64, Tensor2, C.c_void_p, C.POINTER(C.c_int64),
+                               C.c_void_p, _i32p],
     "fbgnn_sfu_peak": [C.c_void_p, C.POINTER(C.c_double)],
     "fbgnn_fma_peak": [C.c_void_p, C.POINTER(C.c_double)],
     "fbgnn_math_probe": [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64],
@@ -489,6 +492,13 @@ class Code:
         self.handle = C.c_void_p()
         call("fbgnn_code_create", self.ctx.handle, n, mx, _ip(hxp), _ip(hxi), mz, _ip(hzp), _ip(hzi),
              kx, _ip(lxp), _ip(lxi), kz, _ip(lzp), _ip(lzi), C.byref(self.handle))
+        self.has_basis = False
+        if hasattr(code, "pivot_hx") and hasattr(code, "pivot_hz"):
+            px = np.ascontiguousarray(code.pivot_hx, np.int32)
+            pz = np.ascontiguousarray(code.pivot_hz, np.int32)
+            if len(px) and len(pz):
+                call("fbgnn_code_set_basis", self.handle, len(px), _ip(px), len(pz), _ip(pz))
+                self.has_basis = True
 
     def __del__(self):
         try:

@@ -201,7 +201,7 @@ class Sandwich_BP_GNN_Evaluation_Model:
     """
 
     def __init__(self, code, decoders, feedbacks, num_layers=4, wt=False, p0=0.05, seed=0, first_frame=0,
-                 skip_inactive=False, ctx=None):
+                 skip_inactive=False, osd0=False, ctx=None):
         self.k, self.n = code.K, code.N
         self.code = code
         self.hx, self.hz, self.lx, self.lz = code.hx, code.hz, code.lx, code.lz
@@ -227,6 +227,7 @@ class Sandwich_BP_GNN_Evaluation_Model:
         self.seed = int(seed)
         self.next_frame = int(first_frame)
         self.skip_inactive = bool(skip_inactive)
+        self.osd0 = bool(osd0)          # OSD-0 on the frames the last BP stage leaves mismatching (bp_osd.py)
         self._ctx = ctx
         self.last_counters = None
 
@@ -249,7 +250,8 @@ class Sandwich_BP_GNN_Evaluation_Model:
         # wt=True: `p` is the error weight (feedback_gnn.py:300-301) and p0 must be given
         thr = pauli_thresholds(0.0 if self.wt else float(p))
         cfg = _ffi.PipelineCfg(S, ni, fa, ct, gh, float(self.prior(p)), (C.c_float * 3)(*thr),
-                               int(round(float(p))) if self.wt else 0, 1 if self.skip_inactive else 0)
+                               int(round(float(p))) if self.wt else 0, 1 if self.osd0 else 0,
+                               1 if self.skip_inactive else 0)
         nx = nz = _ffi.NULL2
         keep = None
         if noise is not None:
@@ -316,6 +318,8 @@ class BP_BSC_Model:
         self._ctx = ctx
         self._graph = None
         self._logical = None
+        self._osd_basis = None          # set by BP2_OSD_Model
+        self._osd_pivot = None
         self.last_counters = None
 
     def llr_const(self, p):
@@ -345,7 +349,9 @@ class BP_BSC_Model:
         d = self.decoder
         _ffi.call("fbgnn_bsc_pipeline_run", g.handle, lg.handle if lg is not None else None,
                   CN_TYPES[d.cn_type], d.num_iter, d.normalization_factor, float(self.llr_const(p)),
-                  float(np.float32(p)), self.seed, self.next_frame, B, nz, flags.ptr, counters)
+                  float(np.float32(p)), self.seed, self.next_frame, B, nz, flags.ptr, counters,
+                  self._osd_basis.handle if self._osd_basis is not None else None,
+                  self._osd_pivot.ctypes.data_as(C.POINTER(C.c_int32)) if self._osd_pivot is not None else None)
         if noise is None:
             self.next_frame += B
         self.last_counters = np.array(list(counters), np.int64) if want_counters else None

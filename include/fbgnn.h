@@ -15,6 +15,7 @@
  *   fbgnn_pauli_sample       <- Pauli.call (non-wt branch)               channel/pauli.py:98-108
  *   fbgnn_bsc_sample         <- BinarySymmetricChannel.call              channel/discrete_channel.py:385-396
  *   fbgnn_syndrome           <- int_mod_2(tf.matmul(H, noise))           feedback_gnn.py:308-309
+ *   fbgnn_osd0_decode        <- OSD0_Decoder.call                        bp_osd.py:8-77
  *   fbgnn_pipeline_run       <- Sandwich_BP_GNN_Evaluation_Model.call    feedback_gnn.py:293-361
  *   fbgnn_bsc_pipeline_run   <- BP_BSC_Model.call                        feedback_gnn.py:207-229
  *
@@ -121,6 +122,10 @@ int fbgnn_code_create(fbgnn_ctx *ctx, int32_t n,
                       int32_t k_z, const int32_t *lz_indptr, const int32_t *lz_indices,
                       fbgnn_code **code);
 int fbgnn_code_destroy(fbgnn_code *code);
+/* Row bases for OSD-0: pivot_hx[rank_x] / pivot_hz[rank_z] are the rows of hx / hz that form a basis
+ * (css_code.pivot_hx / pivot_hz, codes_q.py:36-39).  Needed before a pipeline with cfg.osd0. */
+int fbgnn_code_set_basis(fbgnn_code *code, int32_t rank_x, const int32_t *pivot_hx, int32_t rank_z,
+                         const int32_t *pivot_hz);
 /* number of edges of hx and hz (message array lengths) */
 int fbgnn_code_edges(fbgnn_code *code, int32_t *e_x, int32_t *e_z);
 
@@ -168,6 +173,13 @@ int fbgnn_bp2_decode(fbgnn_graph *graph, int32_t cn_type, int32_t num_iter, floa
                      int64_t B, fbgnn_tensor2 llr, fbgnn_tensor2 synd, fbgnn_tensor2 soft,
                      fbgnn_tensor2 hard);
 
+/* OSD0_Decoder.call (bp_osd.py:51-77): ordered-statistics post-processing of order 0.  `basis` is the
+ * graph of a FULL-RANK row basis of the parity-check matrix (rank rows); llr float32 (b, v) are the
+ * reliabilities BP produced (small = likely in error; ties are broken by index); synd uint8 (row, b) is
+ * the syndrome reduced to the basis rows; e_hat uint8 (b, v) receives the error that satisfies it. */
+int fbgnn_osd0_decode(fbgnn_graph *basis, int64_t B, fbgnn_tensor2 llr, fbgnn_tensor2 synd,
+                      fbgnn_tensor2 e_hat);
+
 /* ---- feedback GNN --------------------------------------------------------------------- */
 /* Weights in Keras get_weights() order, host float32 pointers (copied); bias pointers may
  * be NULL when use_bias is False.  Shapes: W0[H,3] b0[3] W1x[4,H] b1x[H] W2x[H,M] b2x[M]
@@ -194,6 +206,8 @@ typedef struct {
     float prior;               /* log(3(1-p0)/p0) as float32                                 */
     float thr[3];              /* Pauli thresholds, see fbgnn_pauli_sample                   */
     int32_t fixed_weight;      /* > 0: errors of exactly this weight (Pauli wt=True) instead  */
+    int32_t osd0;              /* 1: OSD-0 on the frames still mismatching after the last stage */
+                               /*    (BP4_OSD_Model, bp_osd.py:80-197)                          */
     int32_t skip_inactive;     /* 0: all frames run all rounds (reference-equivalent work)   */
                                /* 1: frames whose decision matches the syndrome stop early   */
                                /*    (result-identical; the reference masks the scatter)     */
@@ -213,12 +227,15 @@ int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cfg, uint64_t
                        fbgnn_tensor2 z_diff, int64_t *counters);
 
 /* BP_BSC_Model.call: Bernoulli(p) noise, syndrome with `graph`, binary BP from the constant
- * logit llr_const, residual syndrome + logical check against `logical` (may be NULL: block
- * error = flagged).  flags/counters as above. */
+ * logit llr_const, residual syndrome + logical check against `logical` (block error = any row of
+ * `logical` . residual; NULL: block error = flagged).  flags/counters as above.
+ * osd_basis / osd_pivot (optional): BP2_OSD_Model (bp_osd.py:199-274) -- the frames whose decision
+ * misses the syndrome are re-solved by OSD-0 on the given row basis (osd_pivot: HOST int32 rows of
+ * `graph` behind the basis rows). */
 int fbgnn_bsc_pipeline_run(fbgnn_graph *graph, fbgnn_graph *logical, int32_t cn_type,
                            int32_t num_iter, float factor, float llr_const, float p, uint64_t seed,
                            uint64_t first_frame, int64_t B, fbgnn_tensor2 noise, uint8_t *flags,
-                           int64_t *counters);
+                           int64_t *counters, fbgnn_graph *osd_basis, const int32_t *osd_pivot);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* Measured MUFU (ex2.approx) throughput of the device in transcendental evaluations / s:

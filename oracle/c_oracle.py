@@ -56,7 +56,9 @@ class _Gnn(C.Structure):
 class _PipeCfg(C.Structure):
     _fields_ = [("num_stages", C.c_int32), ("num_iter", C.c_void_p), ("factor", C.c_void_p),
                 ("cn_type", C.c_void_p), ("gnn", C.c_void_p), ("prior", C.c_float),
-                ("fixed_weight", C.c_int32), ("skip_inactive", C.c_int32)]
+                ("fixed_weight", C.c_int32), ("osd0", C.c_int32), ("basis_x", C.c_void_p),
+                ("pivot_x", C.c_void_p), ("basis_z", C.c_void_p), ("pivot_z", C.c_void_p),
+                ("skip_inactive", C.c_int32)]
 
 
 def lib():
@@ -238,7 +240,7 @@ def gnn(g, G, h_vn, logit_hx, logit_hz, syndrome_x, syndrome_z):
 
 
 def pipeline(g, num_iters, gnns, p, p0=0.05, factors=None, cn_types=None, seed=0, first_frame=0,
-             B=1, noise=None, skip_inactive=False, want_diff=False, wt=0):
+             B=1, noise=None, skip_inactive=False, want_diff=False, wt=0, osd0=False):
     """Sandwich model: decoders[i] has num_iters[i] iterations; gnns[i] is feedbacks[i].
     Returns dict(flags [B] u8, counters [4] i64, x_diff, z_diff)."""
     S = len(num_iters)
@@ -247,8 +249,13 @@ def pipeline(g, num_iters, gnns, p, p0=0.05, factors=None, cn_types=None, seed=0
     fa = _f32([1.0] * S if factors is None else factors)
     ct = _i32([CN_TYPES[c] for c in (cn_types or ["boxplus-phi"] * S)])
     garr = (C.c_void_p * max(S - 1, 1))(*[C.addressof(G.c) for G in gnns])
+    code = g.code
+    bx, bz = Rows(np.asarray(code.hx)[code.pivot_hx]), Rows(np.asarray(code.hz)[code.pivot_hz])
+    pvx, pvz = _i32(code.pivot_hx), _i32(code.pivot_hz)
     cfg = _PipeCfg(S, _p(ni), _p(fa), _p(ct), C.cast(garr, C.c_void_p),
-                   C.c_float(prior_llr(p if p0 is None else p0)), int(wt), int(skip_inactive))
+                   C.c_float(prior_llr(p if p0 is None else p0)), int(wt), int(osd0),
+                   C.cast(C.pointer(bx.c), C.c_void_p), _p(pvx), C.cast(C.pointer(bz.c), C.c_void_p), _p(pvz),
+                   int(skip_inactive))
     thr = pauli_thresholds(p)
     flags = np.empty(B, np.uint8)
     counters = np.zeros(4, np.int64)
@@ -265,7 +272,7 @@ def pipeline(g, num_iters, gnns, p, p0=0.05, factors=None, cn_types=None, seed=0
 
 
 def bsc_pipeline(pcm, logical_pcm, num_iter, p, p0=None, factor=1.0, cn_type="boxplus-phi",
-                 seed=0, first_frame=0, B=1, noise=None):
+                 seed=0, first_frame=0, B=1, noise=None, osd_basis=None, osd_pivot=None):
     S = Side(pcm)
     L = None if logical_pcm is None else Rows(logical_pcm)
     p0 = np.float32(p if p0 is None else p0)
@@ -273,11 +280,26 @@ def bsc_pipeline(pcm, logical_pcm, num_iter, p, p0=None, factor=1.0, cn_type="bo
     flags = np.empty(B, np.uint8)
     counters = np.zeros(4, np.int64)
     nz = None if noise is None else _u8(noise)
+    basis = None if osd_basis is None else Rows(osd_basis)          # kept alive across the call
+    pivot = None if osd_pivot is None else _i32(osd_pivot)
     lib().orc_bsc_pipeline(C.byref(S.c), None if L is None else C.byref(L.c),
                            C.c_int(CN_TYPES[cn_type]), C.c_int(num_iter), C.c_float(factor),
                            C.c_float(llr_const), C.c_float(np.float32(p)), C.c_uint64(seed),
-                           C.c_uint64(first_frame), C.c_int64(B), _p(nz), _p(flags), _p(counters))
+                           C.c_uint64(first_frame), C.c_int64(B), _p(nz), _p(flags), _p(counters),
+                           None if basis is None else C.byref(basis.c), _p(pivot))
     return dict(flags=flags, counters=counters)
+
+
+def osd0(basis, llr, s):
+    """OSD0_Decoder.call (bp_osd.py:51-77): basis [rank,n] full-rank rows, llr [B,n], s [rank,B] -> e_hat [B,n]."""
+    R = Rows(basis)
+    llr = _f32(llr)
+    B, n = llr.shape
+    s = _u8(s)
+    assert s.shape == (R.m, B)
+    out = np.empty((B, n), np.uint8)
+    lib().orc_osd0(C.byref(R.c), C.c_int(n), C.c_int64(B), _p(llr), _p(s), _p(out))
+    return out
 
 
 def philox(ctr, key):

@@ -588,6 +588,72 @@ void orc_gnn(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t *G, int64
     }
 }
 
+/* ---------------------------------------------------------------- OSD-0 ------------ */
+/* OSD0_Decoder.call + find_mrb (bp_osd.py:8-77).  `rows`: the full-rank basis of the pcm (rank rows),
+ * llr [n] reliabilities (small = likely in error), s [rank] reduced syndrome.  Columns are visited
+ * in order of increasing llr (ties by index: the reference's tf.argsort leaves them unspecified);
+ * for every row, in turn, the pivot is the first remaining one of that row, which is then eliminated
+ * from all other rows (row operations on [pcm | s]).  e_hat is s-solution on the pivot columns. */
+static void osd0_frame(const orc_rows_t *rows, int n, const float *llr, const uint8_t *s, uint8_t *e_hat,
+                       int32_t *order, int32_t *inv, uint32_t *M) {
+    const int R = rows->m, W = (n + 1 + 31) / 32;
+    for (int v = 0; v < n; v++) order[v] = v;
+    /* stable insertion-free sort: simple merge-free O(n log n) via qsort is not stable, so sort keys */
+    for (int i = 1; i < n; i++) {            /* binary-insertion sort keeps ties in index order */
+        int v = order[i];
+        float key = llr[v];
+        int lo = 0, hi = i;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (llr[order[mid]] <= key) lo = mid + 1; else hi = mid; }
+        memmove(order + lo + 1, order + lo, sizeof(int32_t) * (size_t)(i - lo));
+        order[lo] = v;
+    }
+    for (int j = 0; j < n; j++) inv[order[j]] = j;
+    memset(M, 0, sizeof(uint32_t) * (size_t)R * W);
+    for (int r = 0; r < R; r++) {
+        for (int k = rows->ptr[r]; k < rows->ptr[r + 1]; k++) {
+            int j = inv[rows->col[k]];
+            M[(size_t)r * W + (j >> 5)] ^= 1u << (j & 31);
+        }
+        if (s[r]) M[(size_t)r * W + (n >> 5)] ^= 1u << (n & 31);
+    }
+    memset(e_hat, 0, (size_t)n);
+    for (int r = 0; r < R; r++) {
+        uint32_t *row = M + (size_t)r * W;
+        int p = -1;
+        for (int j = 0; j < n; j++) if ((row[j >> 5] >> (j & 31)) & 1u) { p = j; break; }
+        if (p < 0) p = 0;                     /* tf.argmax of an all-zero row (cannot happen for a basis) */
+        for (int i = 0; i < R; i++) {
+            if (i == r) continue;
+            uint32_t *ri = M + (size_t)i * W;
+            if ((ri[p >> 5] >> (p & 31)) & 1u)
+                for (int w = 0; w < W; w++) ri[w] ^= row[w];
+        }
+        order[n + r] = p;                     /* pivot of row r (permuted coordinates) */
+    }
+    for (int r = 0; r < R; r++) {
+        int sol = (M[(size_t)r * W + (n >> 5)] >> (n & 31)) & 1u;
+        e_hat[order[order[n + r]]] = (uint8_t)sol;      /* scatter to pivot, then undo the permutation */
+    }
+}
+
+/* llr [B,n], s [rank,B], e_hat [B,n] */
+void orc_osd0(const orc_rows_t *rows, int n, int64_t B, const float *llr, const uint8_t *s, uint8_t *e_hat) {
+    const int R = rows->m, W = (n + 1 + 31) / 32;
+#pragma omp parallel
+    {
+        int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)(n + R + 1));
+        int32_t *inv = (int32_t *)malloc(sizeof(int32_t) * (size_t)n);
+        uint32_t *M = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)R * W + 4);
+        uint8_t *sr = (uint8_t *)malloc((size_t)R + 1);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t b = 0; b < B; b++) {
+            for (int r = 0; r < R; r++) sr[r] = s[(int64_t)r * B + b];
+            osd0_frame(rows, n, llr + b * n, sr, e_hat + b * n, order, inv, M);
+        }
+        free(order); free(inv); free(M); free(sr);
+    }
+}
+
 /* ---------------------------------------------------------------- pipelines -------- */
 typedef struct {
     int32_t num_stages;          /* num_layers of the reference: 1 + number of GNN rounds     */
@@ -597,6 +663,12 @@ typedef struct {
     const orc_gnn_t *const *gnn; /* [num_stages-1] feedbacks[i]                               */
     float prior;                 /* log(3 (1 - p0) / p0), feedback_gnn.py:311-312              */
     int32_t fixed_weight;        /* > 0: Pauli(wt=True) errors of exactly this weight (300-301) */
+    int32_t osd0;                /* 1: OSD-0 on the frames still mismatching after the last stage  */
+                                 /*    (BP4_OSD_Model, bp_osd.py:80-197)                           */
+    const orc_rows_t *basis_x;   /* hx[pivot_hx] */
+    const int32_t *pivot_x;      /* [rank_x] rows of hx forming the basis */
+    const orc_rows_t *basis_z;
+    const int32_t *pivot_z;
     int32_t skip_inactive;       /* 0: every frame runs every round (reference behaviour);     */
                                  /* 1: stop a frame once its decision matches the syndrome     */
                                  /*    (result-identical, the scatter is masked: 339-340)      */
@@ -637,6 +709,30 @@ static uint8_t pipeline_frame(const orc_side_t *X, const orc_side_t *Z, const or
         bp4_frame(X, Z, cfg->cn_type[i], cfg->num_iter[i], cfg->factor[i], pri, pri + n,
                   pri + 2 * n, sx, sz, mx, mz, L, L + n, L + 2 * n, xh2, zh2, work);
         if (active) { memcpy(xh, xh2, (size_t)n); memcpy(zh, zh2, (size_t)n); }
+    }
+    if (cfg->osd0) {
+        int mismatch = 0;
+        syndrome_frame(Z, xh, t);
+        for (int c = 0; c < Z->m; c++) mismatch |= (t[c] != sz[c]);
+        syndrome_frame(X, zh, t);
+        for (int c = 0; c < X->m; c++) mismatch |= (t[c] != sx[c]);
+        if (mismatch) {
+            /* bp_osd.py:135-144: osd_llrz = softplus(-llrx) - logsumexp(-llrz, -llry), osd_llrx likewise */
+            float *lz_ = wa, *lx_ = wa + n;
+            for (int v = 0; v < n; v++) {
+                lz_[v] = FB_SUB(fb_softplusf(-L[v]), fb_logaddexpf(-L[2 * n + v], -L[n + v]));
+                lx_[v] = FB_SUB(fb_softplusf(-L[2 * n + v]), fb_logaddexpf(-L[v], -L[n + v]));
+            }
+            const int Rx = cfg->basis_x->m, Rz = cfg->basis_z->m, Rm = Rx > Rz ? Rx : Rz;
+            int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)(2 * n + Rm + 1));
+            uint32_t *M = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)Rm * ((n + 32) / 32) + 4);
+            uint8_t *sr = (uint8_t *)malloc((size_t)Rm + 1);
+            for (int r = 0; r < Rx; r++) sr[r] = sx[cfg->pivot_x[r]];
+            osd0_frame(cfg->basis_x, n, lz_, sr, zh, order, order + n + Rm + 1, M);
+            for (int r = 0; r < Rz; r++) sr[r] = sz[cfg->pivot_z[r]];
+            osd0_frame(cfg->basis_z, n, lx_, sr, xh, order, order + n + Rm + 1, M);
+            free(order); free(M); free(sr);
+        }
     }
     for (int v = 0; v < n; v++) { xh[v] ^= nx[v]; zh[v] ^= nz[v]; }   /* x_diff, z_diff: 346-347 */
     if (x_diff) memcpy(x_diff, xh, (size_t)n);
@@ -701,7 +797,8 @@ void orc_pipeline(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *lx
  * logical check with `logical` rows.  flags as in orc_pipeline (bits 0,1). */
 void orc_bsc_pipeline(const orc_side_t *S, const orc_rows_t *logical, int cn_type, int num_iter,
                       float factor, float llr_const, float p, uint64_t seed, uint64_t first_frame,
-                      int64_t B, const uint8_t *noise_in, uint8_t *flags, int64_t *counters) {
+                      int64_t B, const uint8_t *noise_in, uint8_t *flags, int64_t *counters,
+                      const orc_rows_t *osd_basis, const int32_t *osd_pivot) {
     const int n = S->n, m = S->m;
     int wd = max_cn_degree(S);
     int64_t c_flag = 0, c_blk = 0;
@@ -719,6 +816,21 @@ void orc_bsc_pipeline(const orc_side_t *S, const orc_rows_t *logical, int cn_typ
             syndrome_frame(S, noise, s);
             for (int v = 0; v < n; v++) fl[v] = llr_const;
             bp2_frame(S, cn_type, num_iter, factor, fl, s, msg, fl + n, hard, work, fl + 2 * n);
+            if (osd_basis) {                 /* BP2_OSD_Model, bp_osd.py:199-274 */
+                int mismatch = 0;
+                syndrome_frame(S, hard, t);
+                for (int c = 0; c < m; c++) mismatch |= (t[c] != s[c]);
+                if (mismatch) {
+                    const int R = osd_basis->m;
+                    int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)(2 * n + R + 1));
+                    uint32_t *M = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)R * ((n + 32) / 32) + 4);
+                    uint8_t *sr = (uint8_t *)malloc((size_t)R + 1);
+                    for (int v = 0; v < n; v++) fl[2 * n + v] = -fl[n + v];       /* llr_hat = -decoder output */
+                    for (int r = 0; r < R; r++) sr[r] = s[osd_pivot[r]];
+                    osd0_frame(osd_basis, n, fl + 2 * n, sr, hard, order, order + n + R + 1, M);
+                    free(order); free(M); free(sr);
+                }
+            }
             for (int v = 0; v < n; v++) hard[v] ^= noise[v];
             int flagged = 0;
             syndrome_frame(S, hard, t);
