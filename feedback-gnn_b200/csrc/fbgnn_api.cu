@@ -698,6 +698,7 @@ extern "C" int fbgnn_gnn_create(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t ac
 extern "C" int fbgnn_gnn_destroy(fbgnn_gnn *g) {
     if (!g) return 0;
     cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
     cudaFree(g->weights);
     delete g;
     return 0;

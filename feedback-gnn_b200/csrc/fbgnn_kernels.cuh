@@ -612,22 +612,28 @@ __device__ __forceinline__ float gnn_act(int act, float x) {
     return x;
 }
 
-// One thread per (frame, variable node); the 3 923 weights are staged in shared memory and read
-// as broadcast loads.  Messages of one side into the variable node are computed and reduced as in
-// feedback_gnn.py:175-184; the arithmetic and its order are those of oracle/fbgnn_oracle.c.
+// Weights staged per CTA in shared memory and read as broadcast loads.  (Measured alternative:
+// __constant__ memory through LDC is 19 % slower for this kernel -- higher load latency, same FFMA
+// operand traffic -- and packed fma.rn.f32x2 sustains only 0.77x the lanes/s of scalar FFMA on B200.)
+struct WSmem {
+    const float *p;
+    __device__ __forceinline__ float ld(int i) const { return p[i]; }
+    __device__ __forceinline__ float4 ld4(int i) const { return *reinterpret_cast<const float4 *>(p + i); }
+};
+
+// One thread per (frame, variable node).  Messages of one side into the variable node are computed
+// and reduced as in feedback_gnn.py:175-184; the arithmetic and its order are those of
+// oracle/fbgnn_oracle.c.
 //   DV > 0 : both sides are DV-regular -- the DV edges of a side are processed together, so each
 //            weight fetched feeds DV FMAs and the DV tanh chains overlap;  DV == 0 : edge by edge.
 //   TANH_BIAS : compile-time specialisation of the shipped configuration (tanh, use_bias=True);
 //            otherwise activation / bias are run-time switches.
 // The two sides share ONE copy of the inner loop (side loop not unrolled) and the loop over hidden
-// units is not unrolled: the hot loop body stays ~2 KB, inside the instruction cache.
+// units is unrolled by two only: the hot loop body stays a few KB, inside the instruction cache.
 // Requires H % 4 == 0 and M % 4 == 0.
-template <int H, int M, int DV, bool TANH_BIAS, typename MATH>
-__global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
+template <int H, int M, int DV, bool TANH_BIAS, typename MATH, typename WSRC>
+__device__ __forceinline__ void gnn_body(const GnnArgs &a, const WSRC w) {
     typedef GnnLayout<H, M> Lay;
-    extern __shared__ float w[];
-    for (int i = threadIdx.x; i < Lay::total; i += blockDim.x) w[i] = a.weights[i];
-    __syncthreads();
     constexpr int NE = DV > 0 ? DV : 1;
     const int n = a.X.n;
     const int act = TANH_BIAS ? 0 : a.act;
@@ -643,8 +649,8 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
 #pragma unroll 1
         for (int side = 0; side < 2; side++) {
             const SideDev &S = side ? a.Z : a.X;
-            const float *W1 = w + (side ? Lay::W1z : Lay::W1x), *b1 = w + (side ? Lay::b1z : Lay::b1x);
-            const float *W2 = w + (side ? Lay::W2z : Lay::W2x), *b2 = w + (side ? Lay::b2z : Lay::b2x);
+            const int oW1 = side ? Lay::W1z : Lay::W1x, ob1 = side ? Lay::b1z : Lay::b1x;
+            const int oW2 = side ? Lay::W2z : Lay::W2x, ob2 = side ? Lay::b2z : Lay::b2x;
             const View2<const float> &logit = side ? a.logit_hz : a.logit_hx;
             const View2<const uint8_t> &synd = side ? a.sz : a.sx;
             const int e0 = DV > 0 ? v * DV : S.vn_ptr[v], e1 = DV > 0 ? e0 + DV : S.vn_ptr[v + 1];
@@ -667,8 +673,9 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
 #pragma unroll 2
                 for (int j = 0; j < H; j++) {
                     // features [h_cn, Lx, Ly, Lz]: the per-variable terms first, the check term last
-                    const float base = FB_FMA(f3, W1[3 * H + j], FB_FMA(f2, W1[2 * H + j], FB_FMA(f1, W1[H + j], 0.0f)));
-                    const float w0 = W1[j], bj = b1[j];
+                    const float base = FB_FMA(f3, w.ld(oW1 + 3 * H + j),
+                                              FB_FMA(f2, w.ld(oW1 + 2 * H + j), FB_FMA(f1, w.ld(oW1 + H + j), 0.0f)));
+                    const float w0 = w.ld(oW1 + j), bj = w.ld(ob1 + j);
                     float hv[NE];
 #pragma unroll
                     for (int k = 0; k < NE; k++) {
@@ -676,10 +683,9 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
                         if (use_bias) t = FB_ADD(t, bj);
                         hv[k] = gnn_act<MATH>(act, t);
                     }
-                    const float *w2r = W2 + j * M;
 #pragma unroll
                     for (int i = 0; i < M; i += 4) {
-                        const float4 wv = *reinterpret_cast<const float4 *>(w2r + i);
+                        const float4 wv = w.ld4(oW2 + j * M + i);
 #pragma unroll
                         for (int k = 0; k < NE; k++) {
                             acc[k][i + 0] = FB_FMA(hv[k], wv.x, acc[k][i + 0]);
@@ -694,7 +700,7 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
                     const bool first = (eb + k == e0);
 #pragma unroll
                     for (int i = 0; i < M; i++) {
-                        const float mval = use_bias ? FB_ADD(acc[k][i], b2[i]) : acc[k][i];
+                        const float mval = use_bias ? FB_ADD(acc[k][i], w.ld(ob2 + i)) : acc[k][i];
                         if (first) red[i] = (a.reduce <= 1) ? FB_ADD(0.0f, mval) : mval;
                         else if (a.reduce <= 1) red[i] = FB_ADD(red[i], mval);
                         else if (a.reduce == 2) red[i] = (mval > red[i]) ? mval : red[i];
@@ -720,30 +726,37 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
             float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
 #pragma unroll
             for (int k = 0; k < 2 * M + 3; k++) {
-                const float4 wv = *reinterpret_cast<const float4 *>(w + Lay::W3 + k * H + j);
+                const float4 wv = w.ld4(Lay::W3 + k * H + j);
                 h0 = FB_FMA(in[k], wv.x, h0);
                 h1 = FB_FMA(in[k], wv.y, h1);
                 h2 = FB_FMA(in[k], wv.z, h2);
                 h3 = FB_FMA(in[k], wv.w, h3);
             }
             if (use_bias) {
-                const float4 bb = *reinterpret_cast<const float4 *>(w + Lay::b3 + j);
+                const float4 bb = w.ld4(Lay::b3 + j);
                 h0 = FB_ADD(h0, bb.x); h1 = FB_ADD(h1, bb.y); h2 = FB_ADD(h2, bb.z); h3 = FB_ADD(h3, bb.w);
             }
             const float hh[4] = { gnn_act<MATH>(act, h0), gnn_act<MATH>(act, h1), gnn_act<MATH>(act, h2), gnn_act<MATH>(act, h3) };
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) {
-                const float *w0 = w + Lay::W0 + (j + jj) * 3;
-                o0 = FB_FMA(hh[jj], w0[0], o0);
-                o1 = FB_FMA(hh[jj], w0[1], o1);
-                o2 = FB_FMA(hh[jj], w0[2], o2);
+                o0 = FB_FMA(hh[jj], w.ld(Lay::W0 + (j + jj) * 3 + 0), o0);
+                o1 = FB_FMA(hh[jj], w.ld(Lay::W0 + (j + jj) * 3 + 1), o1);
+                o2 = FB_FMA(hh[jj], w.ld(Lay::W0 + (j + jj) * 3 + 2), o2);
             }
         }
         if (use_bias) {
-            o0 = FB_ADD(o0, w[Lay::b0 + 0]); o1 = FB_ADD(o1, w[Lay::b0 + 1]); o2 = FB_ADD(o2, w[Lay::b0 + 2]);
+            o0 = FB_ADD(o0, w.ld(Lay::b0 + 0)); o1 = FB_ADD(o1, w.ld(Lay::b0 + 1)); o2 = FB_ADD(o2, w.ld(Lay::b0 + 2));
         }
         a.out(b, v, 0) = o0; a.out(b, v, 1) = o1; a.out(b, v, 2) = o2;
     }
+}
+
+template <int H, int M, int DV, bool TANH_BIAS, typename MATH>
+__global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
+    extern __shared__ float wsm[];
+    for (int i = threadIdx.x; i < GnnLayout<H, M>::total; i += blockDim.x) wsm[i] = a.weights[i];
+    __syncthreads();
+    gnn_body<H, M, DV, TANH_BIAS, MATH, WSmem>(a, WSmem{wsm});
 }
 
 // ------------------------------------------------------------------ noise + syndrome --
