@@ -82,6 +82,8 @@ struct fbgnn_code {
     uint32_t *lx_bits = nullptr, *lz_bits = nullptr;
     // host copies of the CSR of hx / hz (to cut row bases out of them) and the OSD-0 bases
     std::vector<int32_t> hx_ptr, hx_idx, hz_ptr, hz_idx;
+    int *lx_ptr = nullptr, *lz_ptr = nullptr;                // CSR rows of the logical operators (GNN_BP4 logits)
+    idx_t *lx_col = nullptr, *lz_col = nullptr;
     fbgnn_graph *basis_x = nullptr, *basis_z = nullptr;      // hx[pivot_hx], hz[pivot_hz]
     idx_t *pivot_x = nullptr, *pivot_z = nullptr;            // device [rank]
 };
@@ -398,6 +400,18 @@ extern "C" int fbgnn_code_create(fbgnn_ctx *ctx, int32_t n, int32_t m_x, const i
     c->hx_ptr.assign(hx_indptr, hx_indptr + m_x + 1); c->hx_idx.assign(hx_indices, hx_indices + hx_indptr[m_x]);
     c->hz_ptr.assign(hz_indptr, hz_indptr + m_z + 1); c->hz_idx.assign(hz_indices, hz_indices + hz_indptr[m_z]);
     std::vector<uint32_t> bits;
+    auto up_rows = [&](int k, const int32_t *ptr, const int32_t *idx, int **dptr, idx_t **dcol) -> int {
+        std::vector<int> p(ptr, ptr + k + 1);
+        std::vector<idx_t> col(std::max(ptr[k], 1));
+        for (int i = 0; i < ptr[k]; i++) col[i] = (idx_t)idx[i];
+        CK(cudaMalloc(dptr, p.size() * sizeof(int)));
+        CK(cudaMemcpy(*dptr, p.data(), p.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(dcol, col.size() * sizeof(idx_t)));
+        CK(cudaMemcpy(*dcol, col.data(), col.size() * sizeof(idx_t), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (c->kx) if (int rc2 = up_rows(c->kx, lx_indptr, lx_indices, &c->lx_ptr, &c->lx_col)) return rc2;
+    if (c->kz) if (int rc2 = up_rows(c->kz, lz_indptr, lz_indices, &c->lz_ptr, &c->lz_col)) return rc2;
     if (c->kx) {
         pack_rows(n, c->kx, lx_indptr, lx_indices, bits);
         CK(cudaMalloc(&c->lx_bits, bits.size() * 4));
@@ -421,6 +435,7 @@ extern "C" int fbgnn_code_destroy(fbgnn_code *c) {
     fbgnn_graph_destroy(c->basis_z);
     cudaFree(c->pivot_x);
     cudaFree(c->pivot_z);
+    cudaFree(c->lx_ptr); cudaFree(c->lx_col); cudaFree(c->lz_ptr); cudaFree(c->lz_col);
     cudaFree(c->lx_bits);
     cudaFree(c->lz_bits);
     delete c;
@@ -784,6 +799,141 @@ extern "C" int fbgnn_osd0_decode(fbgnn_graph *basis, int64_t B, fbgnn_tensor2 ll
     a.synd = v2<const uint8_t>(synd);
     a.e_hat = v2<uint8_t>(e_hat);
     return launch_osd0(ctx, a, B);
+}
+
+// ------------------------------------------------------------------ GNN_BP4 -------------
+struct fbgnn_gbp {
+    fbgnn_ctx *ctx;
+    int d, H, M, act, reduce, use_bias;
+    float *w_cn = nullptr, *w_vn = nullptr, *w_inv = nullptr;
+};
+
+typedef GbpLayout<20, 40, 20> GL;
+
+static void pack_edge(std::vector<float> &w, int off, const float *W1, const float *b1, const float *W2, const float *b2) {
+    const int D = 20, H = 40, M = 20;
+    for (int j = 0; j < H; j++) for (int k = 0; k < 2 * D; k++) w[off + j * 2 * D + k] = W1[k * H + j];     // transposed
+    if (b1) std::memcpy(&w[off + GL::e_b1], b1, sizeof(float) * H);
+    std::memcpy(&w[off + GL::e_W2], W2, sizeof(float) * H * M);
+    if (b2) std::memcpy(&w[off + GL::e_b2], b2, sizeof(float) * M);
+}
+static void pack_node(std::vector<float> &w, int off, int K, const float *W1, const float *b1, const float *W2, const float *b2) {
+    const int D = 20, H = 40;
+    std::memcpy(&w[off], W1, sizeof(float) * K * H);
+    if (b1) std::memcpy(&w[off + GL::n_b1(K)], b1, sizeof(float) * H);
+    std::memcpy(&w[off + GL::n_W2(K)], W2, sizeof(float) * H * D);
+    if (b2) std::memcpy(&w[off + GL::n_b2(K)], b2, sizeof(float) * D);
+}
+
+extern "C" int fbgnn_gbp_create(fbgnn_ctx *ctx, int32_t d, int32_t H, int32_t M, int32_t activation, int32_t reduce_op,
+                                const float *const *arrays, fbgnn_gbp **out) {
+    REQUIRE(ctx && arrays && out, "NULL argument");
+    REQUIRE(activation >= 0 && activation <= 2 && reduce_op >= 0 && reduce_op <= 3, "bad activation / reduce_op");
+    if (!(d == 20 && H == 40 && M == 20))
+        return fail(FBGNN_E_UNSUPPORTED, "GNN_BP4 with embed/hidden/msg dims %d/%d/%d is not compiled into this build "
+                    "(available: 20/40/20)", d, H, M);
+    for (int i = 0; i < 30; i += 2) REQUIRE(arrays[i], "kernel %d is NULL", i / 2);
+    bool any_b = false, all_b = true;
+    for (int i = 1; i < 30; i += 2) { any_b |= arrays[i] != nullptr; all_b &= arrays[i] != nullptr; }
+    REQUIRE(any_b == all_b, "either all biases or none must be given");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    // arrays: [Winv, binv, cn.msg_x (W1,b1,W2,b2), cn.msg_z, cn.embed_x, cn.embed_z, vn.msg_x, vn.msg_z, vn.embed]
+    std::vector<float> wc(GL::cn_total, 0.0f), wv(GL::vn_total, 0.0f), wi(20 * 3 + 4, 0.0f);
+    std::memcpy(wi.data(), arrays[0], sizeof(float) * 60);
+    if (arrays[1]) std::memcpy(&wi[60], arrays[1], sizeof(float) * 3);
+    const float *const *p = arrays + 2;
+    pack_edge(wc, 0, p[0], p[1], p[2], p[3]);
+    pack_edge(wc, GL::edge, p[4], p[5], p[6], p[7]);
+    pack_node(wc, 2 * GL::edge, GL::KC, p[8], p[9], p[10], p[11]);
+    pack_node(wc, 2 * GL::edge + GL::node(GL::KC), GL::KC, p[12], p[13], p[14], p[15]);
+    pack_edge(wv, 0, p[16], p[17], p[18], p[19]);
+    pack_edge(wv, GL::edge, p[20], p[21], p[22], p[23]);
+    pack_node(wv, 2 * GL::edge, GL::KV, p[24], p[25], p[26], p[27]);
+    fbgnn_gbp *g = new fbgnn_gbp();
+    g->ctx = ctx; g->d = d; g->H = H; g->M = M; g->act = activation; g->reduce = reduce_op; g->use_bias = all_b ? 1 : 0;
+    auto up = [&](const std::vector<float> &h, float **dptr) -> int {
+        CK(cudaMalloc(dptr, h.size() * sizeof(float)));
+        CK(cudaMemcpy(*dptr, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+        return 0;
+    };
+    if (up(wc, &g->w_cn) || up(wv, &g->w_vn) || up(wi, &g->w_inv)) { delete g; return FBGNN_E_CUDA; }
+    *out = g;
+    return 0;
+}
+
+extern "C" int fbgnn_gbp_destroy(fbgnn_gbp *g) {
+    if (!g) return 0;
+    cudaSetDevice(g->ctx->device);
+    cudaFree(g->w_cn); cudaFree(g->w_vn); cudaFree(g->w_inv);
+    delete g;
+    return 0;
+}
+
+template <typename MATH>
+static int gbp_run(fbgnn_code *code, fbgnn_gbp *g, int32_t num_iter, int64_t B, GbpArgs a, fbgnn_tensor3 x_logit,
+                   fbgnn_tensor3 z_logit, fbgnn_tensor2 x_hat, fbgnn_tensor2 z_hat) {
+    fbgnn_ctx *ctx = code->ctx;
+    cudaStream_t st = ctx->stream;
+    const int n = a.X.n, mt = a.X.m + a.Z.m;
+    const size_t smem_cn = sizeof(float) * (GL::cn_total + 40 * 128), smem_vn = sizeof(float) * (GL::vn_total + 40 * 128);
+    if (int rc = set_smem(k_gbp_cn<20, 40, 20, MATH>, smem_cn, ctx, "GNN_BP4 CN update")) return rc;
+    if (int rc = set_smem(k_gbp_vn<20, 40, 20, MATH>, smem_vn, ctx, "GNN_BP4 VN update")) return rc;
+    const unsigned g_cn = (unsigned)std::min<int64_t>((B * mt + 127) / 128, (int64_t)ctx->num_sms * 8);
+    const unsigned g_vn = (unsigned)std::min<int64_t>((B * n + 127) / 128, (int64_t)ctx->num_sms * 8);
+    const size_t smem_lg = sizeof(float) * 2 * n + n + 16;
+    a.zero_logits = 1;
+    k_gbp_cn<20, 40, 20, MATH><<<g_cn, 128, smem_cn, st>>>(a);
+    ctx->launches++;
+    a.zero_logits = 0;
+    for (int it = 0; it < num_iter; it++) {
+        k_gbp_vn<20, 40, 20, MATH><<<g_vn, 128, smem_vn, st>>>(a);
+        GbpArgs la = a;
+        if (x_logit.ptr) la.x_logit = View2<float>{(float *)x_logit.ptr + it * x_logit.s0, x_logit.s1, x_logit.s2};
+        if (z_logit.ptr) la.z_logit = View2<float>{(float *)z_logit.ptr + it * z_logit.s0, z_logit.s1, z_logit.s2};
+        if (it == num_iter - 1) { la.x_hat = v2<uint8_t>(x_hat); la.z_hat = v2<uint8_t>(z_hat); }
+        k_gbp_logit<20, MATH><<<(unsigned)B, 256, smem_lg, st>>>(la);
+        ctx->launches += 2;
+        if (it == num_iter - 1) break;
+        k_gbp_cn<20, 40, 20, MATH><<<g_cn, 128, smem_cn, st>>>(a);
+        ctx->launches++;
+    }
+    CK(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int fbgnn_gbp_decode(fbgnn_code *code, fbgnn_gbp *g, int32_t num_iter, int64_t B, fbgnn_tensor2 synd_x,
+                                fbgnn_tensor2 synd_z, fbgnn_tensor3 x_logit, fbgnn_tensor3 z_logit,
+                                fbgnn_tensor2 x_hat, fbgnn_tensor2 z_hat) {
+    REQUIRE(code && g && synd_x.ptr && synd_z.ptr && x_hat.ptr && z_hat.ptr, "NULL argument");
+    REQUIRE(num_iter >= 1 && B >= 0, "num_iter must be >= 1");
+    REQUIRE(synd_x.s1 == 1 && synd_z.s1 == 1 && synd_x.s0 == code->X->dev.m && synd_z.s0 == code->Z->dev.m,
+            "syndromes must be contiguous [B, m] (batch first)");
+    fbgnn_ctx *ctx = code->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    if (B == 0) return 0;
+    const SideDev &X = code->X->dev, &Z = code->Z->dev;
+    const int n = X.n, D = 20;
+    float *h_vn = nullptr, *hcx = nullptr, *hcz = nullptr, *lg = nullptr;
+    cudaStream_t st = ctx->stream;
+    CK(cudaMallocAsync(&h_vn, sizeof(float) * B * n * D, st));
+    CK(cudaMallocAsync(&hcx, sizeof(float) * B * std::max(X.m, 1) * D, st));
+    CK(cudaMallocAsync(&hcz, sizeof(float) * B * std::max(Z.m, 1) * D, st));
+    CK(cudaMallocAsync(&lg, sizeof(float) * B * std::max(X.m + Z.m, 1), st));
+    k_fill<<<ctx->num_sms * 4, 256, 0, st>>>((uint32_t *)h_vn, B * n * D, 0x3f800000u);      // h_vn = 1 (gnn.py:394)
+    CK(cudaMemsetAsync(hcx, 0, sizeof(float) * B * X.m * D, st));                              // h_cn = 0 (392-393)
+    CK(cudaMemsetAsync(hcz, 0, sizeof(float) * B * Z.m * D, st));
+    ctx->launches++;
+    GbpArgs a{};
+    a.X = X; a.Z = Z; a.w_cn = g->w_cn; a.w_vn = g->w_vn; a.w_inv = g->w_inv;
+    a.act = g->act; a.reduce = g->reduce; a.use_bias = g->use_bias; a.B = B;
+    a.h_vn = h_vn; a.hcx = hcx; a.hcz = hcz; a.lg = lg;
+    a.sx = (const uint8_t *)synd_x.ptr; a.sz = (const uint8_t *)synd_z.ptr;
+    a.lx_ptr = code->lx_ptr; a.lz_ptr = code->lz_ptr; a.lx_col = code->lx_col; a.lz_col = code->lz_col;
+    a.kx = code->kx; a.kz = code->kz;
+    int rc = ctx->math_mode == FBGNN_MATH_FAST ? gbp_run<MathFast>(code, g, num_iter, B, a, x_logit, z_logit, x_hat, z_hat)
+                                               : gbp_run<MathExact>(code, g, num_iter, B, a, x_logit, z_logit, x_hat, z_hat);
+    CK(cudaFreeAsync(h_vn, st)); CK(cudaFreeAsync(hcx, st)); CK(cudaFreeAsync(hcz, st)); CK(cudaFreeAsync(lg, st));
+    return rc;
 }
 
 // ------------------------------------------------------------------ pipelines -----------

@@ -759,6 +759,342 @@ __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
     gnn_body<H, M, DV, TANH_BIAS, MATH, WSmem>(a, WSmem{wsm});
 }
 
+// ------------------------------------------------------------------ GNN_BP4 -----------
+// The full GNN message-passing decoder of gnn.py:71-751 (BASELINE configs[4]); arithmetic and
+// summation orders are those of oracle/fbgnn_oracle.c (gbp_*).  Embeddings live in HBM
+// ([B][nodes][D] float); one thread owns one receiving node of one frame, walks its edges, runs the
+// edge MLP (2D -> H -> M) per edge with the receiver half of the first layer hoisted out of the edge
+// loop, reduces, and runs the node MLP.  Weights are staged in shared memory.
+template <int D, int H, int M> struct GbpLayout {
+    static constexpr __host__ __device__ int pad4(int x) { return (x + 3) & ~3; }
+    static constexpr int edge = pad4(H * 2 * D) + pad4(H) + pad4(H * M) + pad4(M);        // W1T[H][2D], b1, W2[H][M], b2
+    static constexpr int e_b1 = pad4(H * 2 * D), e_W2 = e_b1 + pad4(H), e_b2 = e_W2 + pad4(H * M);
+    static constexpr __host__ __device__ int node(int K) { return pad4(K * H) + pad4(H) + pad4(H * D) + pad4(D); }   // W1[K][H], b1, W2[H][D], b2
+    static constexpr __host__ __device__ int n_b1(int K) { return pad4(K * H); }
+    static constexpr __host__ __device__ int n_W2(int K) { return pad4(K * H) + pad4(H); }
+    static constexpr __host__ __device__ int n_b2(int K) { return pad4(K * H) + pad4(H) + pad4(H * D); }
+    static constexpr int KC = M + D + 1, KV = 2 * M + D;
+    // CN kernel: [edge x][edge z][node x][node z];  VN kernel: [edge x][edge z][node]
+    static constexpr int cn_total = 2 * edge + 2 * node(KC);
+    static constexpr int vn_total = 2 * edge + node(KV);
+};
+
+struct GbpArgs {
+    SideDev X, Z;
+    const float *w_cn, *w_vn;           // packed weights of update_h_cn / update_h_vn (GbpLayout)
+    const float *w_inv;                 // [D][3] + [3] (bias, zeros if unused)
+    int act, reduce, use_bias;
+    int64_t B;
+    float *h_vn, *hcx, *hcz;            // [B][n][D], [B][m_x][D], [B][m_z][D]
+    float *lg;                          // [B][m_x + m_z]: hx_logit, hz_logit of the last cal_logit
+    const uint8_t *sx, *sz;             // [B][m_x], [B][m_z] (batch first, gnn.py:385-386)
+    int zero_logits;                    // first CN update: logits are zero
+    // cal_logit outputs (optional) and logical rows
+    const int *lx_ptr, *lz_ptr; const idx_t *lx_col, *lz_col; int kx, kz;
+    View2<float> x_logit, z_logit;      // (row, b) slices of this iteration: [m_z + k_z], [m_x + k_x]
+    View2<uint8_t> x_hat, z_hat;        // (v, b) optional (last iteration)
+};
+
+template <typename MATH>
+__device__ __forceinline__ float gbp_act(int act, float x) { return gnn_act<MATH>(act, x); }
+
+// msg = W2^T act(base + W1s^T from + b1) + b2, reduced into red[] (order: oracle gbp_edge_mlp / gbp_reduce)
+template <int D, int H, int M, typename MATH>
+__device__ __forceinline__ void gbp_edge(const float *__restrict__ w, const float *base_s, int bstride,
+                                         const float from[D], int act, bool use_bias, bool negate, bool first,
+                                         int reduce, float red[M]) {
+    typedef GbpLayout<D, H, M> L;
+    float acc[M];
+#pragma unroll
+    for (int i = 0; i < M; i++) acc[i] = 0.0f;
+#pragma unroll 2
+    for (int j = 0; j < H; j++) {
+        float a = base_s[j * bstride];
+        const float *w1 = w + j * 2 * D;
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w1 + k);
+            a = FB_FMA(from[k + 0], wv.x, a); a = FB_FMA(from[k + 1], wv.y, a);
+            a = FB_FMA(from[k + 2], wv.z, a); a = FB_FMA(from[k + 3], wv.w, a);
+        }
+        if (use_bias) a = FB_ADD(a, w[L::e_b1 + j]);
+        const float hv = gbp_act<MATH>(act, a);
+        const float *w2 = w + L::e_W2 + j * M;
+#pragma unroll
+        for (int i = 0; i < M; i += 4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w2 + i);
+            acc[i + 0] = FB_FMA(hv, wv.x, acc[i + 0]); acc[i + 1] = FB_FMA(hv, wv.y, acc[i + 1]);
+            acc[i + 2] = FB_FMA(hv, wv.z, acc[i + 2]); acc[i + 3] = FB_FMA(hv, wv.w, acc[i + 3]);
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        float mval = use_bias ? FB_ADD(acc[i], w[L::e_b2 + i]) : acc[i];
+        if (negate) mval = -mval;
+        if (first) red[i] = (reduce <= 1) ? FB_ADD(0.0f, mval) : mval;
+        else if (reduce <= 1) red[i] = FB_ADD(red[i], mval);
+        else if (reduce == 2) red[i] = (mval > red[i]) ? mval : red[i];
+        else red[i] = (mval < red[i]) ? mval : red[i];
+    }
+}
+
+// receiver half of the first edge layer: base[j] = sum_k to[k] * W1[D + k][j]
+template <int D, int H, int M>
+__device__ __forceinline__ void gbp_base(const float *__restrict__ w, const float to[D], float *base_s, int bstride) {
+#pragma unroll 2
+    for (int j = 0; j < H; j++) {
+        float a = 0.0f;
+        const float *w1 = w + j * 2 * D + D;
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w1 + k);
+            a = FB_FMA(to[k + 0], wv.x, a); a = FB_FMA(to[k + 1], wv.y, a);
+            a = FB_FMA(to[k + 2], wv.z, a); a = FB_FMA(to[k + 3], wv.w, a);
+        }
+        base_s[j * bstride] = a;
+    }
+}
+
+// node MLP: out = W2^T act(W1^T in + b1) + b2 with in[K] in registers (order: oracle gbp_node_mlp)
+template <int D, int H, int M, int K, typename MATH>
+__device__ __forceinline__ void gbp_node(const float *__restrict__ w, const float in[K], int act, bool use_bias,
+                                         float out[D]) {
+    typedef GbpLayout<D, H, M> L;
+#pragma unroll
+    for (int i = 0; i < D; i++) out[i] = 0.0f;
+#pragma unroll 1
+    for (int j = 0; j < H; j += 4) {
+        float h0 = 0.0f, h1 = 0.0f, h2 = 0.0f, h3 = 0.0f;
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+            const float4 wv = *reinterpret_cast<const float4 *>(w + k * H + j);
+            h0 = FB_FMA(in[k], wv.x, h0); h1 = FB_FMA(in[k], wv.y, h1);
+            h2 = FB_FMA(in[k], wv.z, h2); h3 = FB_FMA(in[k], wv.w, h3);
+        }
+        if (use_bias) {
+            const float4 bb = *reinterpret_cast<const float4 *>(w + L::n_b1(K) + j);
+            h0 = FB_ADD(h0, bb.x); h1 = FB_ADD(h1, bb.y); h2 = FB_ADD(h2, bb.z); h3 = FB_ADD(h3, bb.w);
+        }
+        const float hh[4] = { gbp_act<MATH>(act, h0), gbp_act<MATH>(act, h1), gbp_act<MATH>(act, h2), gbp_act<MATH>(act, h3) };
+#pragma unroll
+        for (int jj = 0; jj < 4; jj++) {
+            const float *w2 = w + L::n_W2(K) + (j + jj) * D;
+#pragma unroll
+            for (int i = 0; i < D; i += 4) {
+                const float4 wv = *reinterpret_cast<const float4 *>(w2 + i);
+                out[i + 0] = FB_FMA(hh[jj], wv.x, out[i + 0]); out[i + 1] = FB_FMA(hh[jj], wv.y, out[i + 1]);
+                out[i + 2] = FB_FMA(hh[jj], wv.z, out[i + 2]); out[i + 3] = FB_FMA(hh[jj], wv.w, out[i + 3]);
+            }
+        }
+    }
+    if (use_bias) {
+#pragma unroll
+        for (int i = 0; i < D; i++) out[i] = FB_ADD(out[i], w[L::n_b2(K) + i]);
+    }
+}
+
+// UpdateCNEmbeddings.call (gnn.py:574-610): one thread per (frame, check), X checks then Z checks.
+// smem: weights[cn_total] + base[H][blockDim]
+template <int D, int H, int M, typename MATH>
+__global__ void __launch_bounds__(128) k_gbp_cn(const GbpArgs a) {
+    typedef GbpLayout<D, H, M> L;
+    extern __shared__ float gsm[];
+    float *w = gsm, *base = gsm + L::cn_total + threadIdx.x;
+    for (int i = threadIdx.x; i < L::cn_total; i += blockDim.x) w[i] = a.w_cn[i];
+    __syncthreads();
+    const int mt = a.X.m + a.Z.m;
+    const bool use_bias = a.use_bias != 0;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.B * mt; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = it / mt;
+        const int c = (int)(it - b * mt);
+        const bool isx = c < a.X.m;
+        const SideDev &S = isx ? a.X : a.Z;
+        const int cc = isx ? c : c - a.X.m;
+        const float *we = w + (isx ? 0 : L::edge), *wn = w + 2 * L::edge + (isx ? 0 : L::node(L::KC));
+        float *hc = (isx ? a.hcx + (b * a.X.m + cc) * D : a.hcz + (b * a.Z.m + cc) * D);
+        float in[L::KC], own[D];
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+            const float4 v4 = *reinterpret_cast<const float4 *>(hc + k);
+            own[k] = v4.x; own[k + 1] = v4.y; own[k + 2] = v4.z; own[k + 3] = v4.w;
+        }
+        gbp_base<D, H, M>(we, own, base, blockDim.x);
+        float red[M];
+#pragma unroll
+        for (int i = 0; i < M; i++) red[i] = 0.0f;
+        const int k0 = S.cn_ptr[cc], k1 = S.cn_ptr[cc + 1];
+        for (int k = k0; k < k1; k++) {
+            const float *hv = a.h_vn + (b * S.n + S.cn_vn[k]) * D;
+            float from[D];
+#pragma unroll
+            for (int q = 0; q < D; q += 4) {
+                const float4 v4 = *reinterpret_cast<const float4 *>(hv + q);
+                from[q] = v4.x; from[q + 1] = v4.y; from[q + 2] = v4.z; from[q + 3] = v4.w;
+            }
+            gbp_edge<D, H, M, MATH>(we, base, blockDim.x, from, a.act, use_bias, false, k == k0, a.reduce, red);
+        }
+        if (a.reduce == 0 && k1 > k0) {
+            const float dg = (float)(k1 - k0);
+#pragma unroll
+            for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], dg);
+        }
+#pragma unroll
+        for (int i = 0; i < M; i++) in[i] = red[i];
+#pragma unroll
+        for (int i = 0; i < D; i++) in[M + i] = own[i];
+        float lgv = 0.0f;
+        if (!a.zero_logits) {
+            lgv = a.lg[b * mt + c];
+            if ((isx ? a.sx[b * a.X.m + cc] : a.sz[b * a.Z.m + cc])) lgv = -lgv;      // logit * (1 - 2 s)
+        }
+        in[M + D] = lgv;
+        float out[D];
+        gbp_node<D, H, M, L::KC, MATH>(wn, in, a.act, use_bias, out);
+#pragma unroll
+        for (int k = 0; k < D; k += 4) *reinterpret_cast<float4 *>(hc + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+    }
+}
+
+// UpdateVNEmbeddings.call (gnn.py:716-750): one thread per (frame, variable node)
+template <int D, int H, int M, typename MATH>
+__global__ void __launch_bounds__(128) k_gbp_vn(const GbpArgs a) {
+    typedef GbpLayout<D, H, M> L;
+    extern __shared__ float gsm[];
+    float *w = gsm, *base = gsm + L::vn_total + threadIdx.x;
+    for (int i = threadIdx.x; i < L::vn_total; i += blockDim.x) w[i] = a.w_vn[i];
+    __syncthreads();
+    const int n = a.X.n;
+    const bool use_bias = a.use_bias != 0;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.B * n; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = it / n;
+        const int v = (int)(it - b * n);
+        float *hv = a.h_vn + (b * n + v) * D;
+        float in[L::KV], own[D];
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+            const float4 v4 = *reinterpret_cast<const float4 *>(hv + k);
+            own[k] = v4.x; own[k + 1] = v4.y; own[k + 2] = v4.z; own[k + 3] = v4.w;
+        }
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            const SideDev &S = side ? a.Z : a.X;
+            const float *we = w + (side ? L::edge : 0);
+            const float *hc = side ? a.hcz + b * a.Z.m * D : a.hcx + b * a.X.m * D;
+            const uint8_t *sy = side ? a.sz + b * a.Z.m : a.sx + b * a.X.m;
+            gbp_base<D, H, M>(we, own, base, blockDim.x);
+            float red[M];
+#pragma unroll
+            for (int i = 0; i < M; i++) red[i] = 0.0f;
+            const int e0 = S.vn_ptr[v], e1 = S.vn_ptr[v + 1];
+            for (int e = e0; e < e1; e++) {
+                const int c = S.vn_cn[e];
+                float from[D];
+#pragma unroll
+                for (int q = 0; q < D; q += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4 *>(hc + c * D + q);
+                    from[q] = v4.x; from[q + 1] = v4.y; from[q + 2] = v4.z; from[q + 3] = v4.w;
+                }
+                gbp_edge<D, H, M, MATH>(we, base, blockDim.x, from, a.act, use_bias, sy[c] != 0, e == e0, a.reduce, red);
+            }
+            if (a.reduce == 0 && e1 > e0) {
+                const float dg = (float)(e1 - e0);
+#pragma unroll
+                for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], dg);
+            }
+#pragma unroll
+            for (int i = 0; i < M; i++) {
+                if (side == 0) in[i] = red[i];
+                else in[M + i] = red[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) in[2 * M + i] = own[i];
+        float out[D];
+        gbp_node<D, H, M, L::KV, MATH>(w + 2 * L::edge, in, a.act, use_bias, out);
+#pragma unroll
+        for (int k = 0; k < D; k += 4) *reinterpret_cast<float4 *>(hv + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+    }
+}
+
+// embed_to_llr + cal_logit + make_hard_decision (gnn.py:281-314, 358-366): one CTA per frame.
+// smem: float lxp[n], lzp[n] (phi2 of |llr_x'|, |llr_z'|); u8 sgn[n]
+template <int D, typename MATH>
+__global__ void k_gbp_logit(const GbpArgs a) {
+    extern __shared__ float lsm[];
+    const int n = a.X.n, T = blockDim.x, tid = threadIdx.x;
+    const int64_t b = blockIdx.x;
+    float *px = lsm, *pz = px + n;
+    uint8_t *sgn = (uint8_t *)(pz + n);
+    for (int v = tid; v < n; v += T) {
+        const float *hv = a.h_vn + (b * n + v) * D;
+        float l[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < D; k++) acc = FB_FMA(hv[k], a.w_inv[k * 3 + c], acc);
+            if (a.use_bias) acc = FB_ADD(acc, a.w_inv[D * 3 + c]);
+            l[c] = acc;
+        }
+        const float lx = l[0], ly = l[1], lz = l[2];
+        const float llr_zp = FB_SUB(MATH::softplus(-lx), MATH::logaddexp(-lz, -ly));
+        const float llr_xp = FB_SUB(MATH::softplus(-lz), MATH::logaddexp(-lx, -ly));
+        sgn[v] = (uint8_t)(((llr_xp < 0.0f) ? 1 : 0) | ((llr_zp < 0.0f) ? 2 : 0));
+        px[v] = MATH::phi2(fabsf(llr_xp));
+        pz[v] = MATH::phi2(fabsf(llr_zp));
+        if (a.x_hat.ptr) {
+            int d = 0;
+            float best = 0.0f;
+            if (lx < best) { best = lx; d = 1; }
+            if (lz < best) { best = lz; d = 2; }
+            if (ly < best) { best = ly; d = 3; }
+            a.x_hat(v, b) = (uint8_t)(d & 1);
+            a.z_hat(v, b) = (uint8_t)(d >> 1);
+        }
+    }
+    __syncthreads();
+    const int mx = a.X.m, mz = a.Z.m, total = mx + mz + a.kx + a.kz;
+    for (int r = tid; r < total; r += T) {
+        // rows: [hx (mx)] [hz (mz)] [lx (kx)] [lz (kz)];  hx / lx rows use llr_z', hz / lz rows use llr_x'
+        const bool usez = r < mx || (r >= mx + mz && r < mx + mz + a.kx);
+        const float *sc = usez ? pz : px;
+        const int bit = usez ? 1 : 0;
+        int par = 0;
+        float Tsum = 0.0f;
+        if (r < mx + mz) {
+            const SideDev &S = r < mx ? a.X : a.Z;
+            const int cc = r < mx ? r : r - mx;
+            for (int k = S.cn_ptr[cc]; k < S.cn_ptr[cc + 1]; k++) {
+                const int v = S.cn_vn[k];
+                par ^= (sgn[v] >> bit) & 1;
+                Tsum = FB_ADD(Tsum, sc[v]);
+            }
+        } else {
+            const bool islx = r < mx + mz + a.kx;
+            const int rr = islx ? r - mx - mz : r - mx - mz - a.kx;
+            const int *ptr = islx ? a.lx_ptr : a.lz_ptr;
+            const idx_t *col = islx ? a.lx_col : a.lz_col;
+            for (int k = ptr[rr]; k < ptr[rr + 1]; k++) {
+                const int v = col[k];
+                par ^= (sgn[v] >> bit) & 1;
+                Tsum = FB_ADD(Tsum, sc[v]);
+            }
+        }
+        float val = MATH::phi2(Tsum);
+        val = par ? -val : val;
+        if (r < mx + mz) a.lg[b * (mx + mz) + r] = val;
+        // x_perp_logit = [hz_logit; lz_logit], z_perp_logit = [hx_logit; lx_logit] (gnn.py:311-313)
+        if (a.x_logit.ptr) {
+            if (r >= mx && r < mx + mz) a.x_logit(r - mx, b) = val;
+            else if (r >= mx + mz + a.kx) a.x_logit(mz + (r - mx - mz - a.kx), b) = val;
+        }
+        if (a.z_logit.ptr) {
+            if (r < mx) a.z_logit(r, b) = val;
+            else if (r >= mx + mz && r < mx + mz + a.kx) a.z_logit(mx + (r - mx - mz), b) = val;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ noise + syndrome --
 struct SampleArgs {
     SideDev X, Z;                       // Z.n == 0 for the binary (single pcm) pipeline

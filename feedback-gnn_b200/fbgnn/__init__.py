@@ -10,7 +10,7 @@ from .codes_q import (css_code, create_circulant_matrix, create_generalized_bicy
                       create_QC_GHP_codes, create_cyclic_permuting_matrix,
                       create_bivariate_QC_codes, readAlist, alistToNumpy)
 from .gf2 import row_echelon, rank, kernel, row_basis, compute_code_distance, inverse, int2bin, int_mod_2
-from .gnn import load_weights, save_weights, read_weights, WEIGHTS_DIR
+from .gnn import load_weights, save_weights, read_weights, WEIGHTS_DIR, GNN_BP4
 from .decoding_q import QLDPCBPDecoder
 from .decoding import LDPCBPDecoder
 from .pauli import Pauli, pauli_thresholds

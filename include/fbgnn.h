@@ -16,6 +16,7 @@
  *   fbgnn_bsc_sample         <- BinarySymmetricChannel.call              channel/discrete_channel.py:385-396
  *   fbgnn_syndrome           <- int_mod_2(tf.matmul(H, noise))           feedback_gnn.py:308-309
  *   fbgnn_osd0_decode        <- OSD0_Decoder.call                        bp_osd.py:8-77
+ *   fbgnn_gbp_create/_decode <- GNN_BP4.build / .call                    gnn.py:71-420
  *   fbgnn_pipeline_run       <- Sandwich_BP_GNN_Evaluation_Model.call    feedback_gnn.py:293-361
  *   fbgnn_bsc_pipeline_run   <- BP_BSC_Model.call                        feedback_gnn.py:207-229
  *
@@ -74,6 +75,7 @@ typedef struct fbgnn_ctx   fbgnn_ctx;     /* one GPU: stream, scratch, timers   
 typedef struct fbgnn_graph fbgnn_graph;   /* Tanner graph of one parity-check matrix     */
 typedef struct fbgnn_code  fbgnn_code;    /* CSS code: graphs of hx, hz + logicals lx,lz */
 typedef struct fbgnn_gnn   fbgnn_gnn;     /* one Feedback_GNN weight set                 */
+typedef struct fbgnn_gbp   fbgnn_gbp;     /* one GNN_BP4 weight set                      */
 
 /* strided views (strides in ELEMENTS; ptr == NULL means "absent") */
 typedef struct { void *ptr; int64_t s0, s1; } fbgnn_tensor2;
@@ -195,6 +197,24 @@ int fbgnn_gnn_destroy(fbgnn_gnn *gnn);
 int fbgnn_gnn_forward(fbgnn_code *code, fbgnn_gnn *gnn, int64_t B, fbgnn_tensor3 h_vn,
                       fbgnn_tensor2 logit_hx, fbgnn_tensor2 logit_hz, fbgnn_tensor2 synd_x,
                       fbgnn_tensor2 synd_z, fbgnn_tensor3 out);
+
+/* ---- GNN_BP4: the full GNN message-passing decoder (gnn.py:71-751, BASELINE configs[4]) -------- */
+/* arrays: 30 host float32 pointers in Keras get_weights() order (biases NULL when use_bias is False):
+ *   [0,1]   _llr_inv_embed            kernel [d,3], bias [3]
+ *   [2..9]  update_h_cn._msg_mlp_x/_z  (W1 [2d,H], b1 [H], W2 [H,M], b2 [M]) x 2
+ *   [10..17] update_h_cn._embed_mlp_x/_z (W1 [M+d+1,H], b1, W2 [H,d], b2 [d]) x 2
+ *   [18..25] update_h_vn._msg_mlp_x/_z  (as above)
+ *   [26..29] update_h_vn._embed_mlp     (W1 [2M+d,H], b1, W2 [H,d], b2 [d])
+ * This build provides num_embed_dims/num_hidden_units/num_msg_dims = 20/40/20, 2-layer MLPs, no attributes. */
+int fbgnn_gbp_create(fbgnn_ctx *ctx, int32_t d, int32_t H, int32_t M, int32_t activation, int32_t reduce_op,
+                     const float *const *arrays, fbgnn_gbp **gbp);
+int fbgnn_gbp_destroy(fbgnn_gbp *gbp);
+/* GNN_BP4.call: synd_x uint8 [B,m_x], synd_z uint8 [B,m_z] contiguous, batch first (gnn.py:385-386);
+ * x_logit float32 (iteration, row, b) with m_z + k_z rows = [hz_logit; lz_logit], z_logit with m_x + k_x rows
+ * = [hx_logit; lx_logit] (either may be NULL); x_hat, z_hat uint8 (v, b): the argmin decision. */
+int fbgnn_gbp_decode(fbgnn_code *code, fbgnn_gbp *gbp, int32_t num_iter, int64_t B, fbgnn_tensor2 synd_x,
+                     fbgnn_tensor2 synd_z, fbgnn_tensor3 x_logit, fbgnn_tensor3 z_logit, fbgnn_tensor2 x_hat,
+                     fbgnn_tensor2 z_hat);
 
 /* ---- fused Monte-Carlo pipelines ------------------------------------------------------- */
 typedef struct {

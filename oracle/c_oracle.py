@@ -302,6 +302,65 @@ def osd0(basis, llr, s):
     return out
 
 
+class _Gbp(C.Structure):
+    _fields_ = [(k, C.c_int32) for k in ("d", "H", "M", "act", "reduce", "use_bias", "num_iter")] + \
+               [("Winv", C.c_void_p), ("binv", C.c_void_p)] + \
+               [(k, C.c_void_p * 4) for k in ("cmx", "cmz", "cex", "cez", "vmx", "vmz", "ve")]
+
+
+GBP_KEYS = ("cmx", "cmz", "cex", "cez", "vmx", "vmz", "ve")
+
+
+def gnn_bp4_random_weights(d=20, M=20, H=40, seed=4, use_bias=True):
+    """Glorot-uniform kernels, ones biases, non-zero llr_inv_embed kernel (the
+    reference ships no weights for GNN_BP4)."""
+    rng = np.random.default_rng(seed)
+
+    def glorot(a, b):
+        lim = np.sqrt(6.0 / (a + b))
+        return rng.uniform(-lim, lim, (a, b)).astype(np.float32)
+
+    def mlp(k_in, k_out):
+        return (glorot(k_in, H), np.ones(H, np.float32) if use_bias else None, glorot(H, k_out),
+                np.ones(k_out, np.float32) if use_bias else None)
+
+    W = {"Winv": glorot(d, 3), "binv": np.ones(3, np.float32) if use_bias else None}
+    for k in ("cmx", "cmz", "vmx", "vmz"):
+        W[k] = mlp(2 * d, M)
+    for k in ("cex", "cez"):
+        W[k] = mlp(M + d + 1, d)
+    W["ve"] = mlp(2 * M + d, d)
+    return W
+
+
+def gnn_bp4(g, W, synd_x, synd_z, num_iter, activation="tanh", reduce_op="mean"):
+    """GNN_BP4(...)((syndrome_x [B,m_x], syndrome_z [B,m_z])) -> dict(x_logit [it, m_z+k, B],
+    z_logit [it, m_x+k, B], x_hat [n,B], z_hat [n,B]) (gnn.py:379-420)."""
+    sx, sz = _u8(synd_x), _u8(synd_z)
+    B = sx.shape[0]
+    d, H = W["cmx"][0].shape[0] // 2, W["cmx"][0].shape[1]
+    M = W["cmx"][2].shape[1]
+    G = _Gbp(d, H, M, ACTS[activation], REDUCE[reduce_op], int(W["binv"] is not None), num_iter)
+    keep = []
+
+    def ptr(a):
+        if a is None:
+            return None
+        a = _f32(a)
+        keep.append(a)
+        return a.ctypes.data
+
+    G.Winv, G.binv = ptr(W["Winv"]), ptr(W["binv"])
+    for k in GBP_KEYS:
+        setattr(G, k, (C.c_void_p * 4)(*[ptr(a) for a in W[k]]))
+    rx, rz = g.Z.m + g.lz.m, g.X.m + g.lx.m
+    out = dict(x_logit=np.empty((num_iter, rx, B), np.float32), z_logit=np.empty((num_iter, rz, B), np.float32),
+               x_hat=np.empty((g.n, B), np.uint8), z_hat=np.empty((g.n, B), np.uint8))
+    lib().orc_gnn_bp4(C.byref(G), C.byref(g.X.c), C.byref(g.Z.c), C.byref(g.lx.c), C.byref(g.lz.c), C.c_int64(B),
+                      _p(sx), _p(sz), _p(out["x_logit"]), _p(out["z_logit"]), _p(out["x_hat"]), _p(out["z_hat"]))
+    return out
+
+
 def philox(ctr, key):
     ctr = np.ascontiguousarray(ctr, np.uint32)
     key = np.ascontiguousarray(key, np.uint32)

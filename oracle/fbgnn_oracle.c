@@ -845,6 +845,213 @@ void orc_bsc_pipeline(const orc_side_t *S, const orc_rows_t *logical, int cn_typ
     if (counters) { counters[0] = B; counters[1] = c_flag; counters[2] = c_blk; counters[3] = 0; }
 }
 
+/* ---------------------------------------------------------------- GNN_BP4 ---------- */
+/* GNN_BP4.call and UpdateCNEmbeddings / UpdateVNEmbeddings (gnn.py:71-751), configuration of
+ * BASELINE configs[4]: 2-layer MLPs, no node/edge attributes.  As shipped, `call` unpacks five values
+ * from cal_logit, which returns four (gnn.py:408 vs 314); the restatement drops the
+ * fifth (`sum_llr`), which nothing else uses.  No weights and no recorded outputs of this layer exist
+ * in the reference: parity of this component is UNPINNED (oracle-vs-CUDA only).
+ *
+ * MLP([x]) = W2^T act(W1^T x + b1) + b2.  Summation orders (the reference leaves them to the GEMM):
+ * edge MLPs see x = [h_from (d), h_to (d)] and accumulate the receiver part (rows d..2d-1 of W1)
+ * first, then the sender part (rows 0..d-1); everything else runs over ascending row index.  */
+typedef struct {
+    int32_t d, H, M, act, reduce, use_bias, num_iter;
+    const float *Winv, *binv;                     /* _llr_inv_embed: [d,3], [3]                          */
+    /* update_h_cn: msg_mlp_x, msg_mlp_z ([2d,H],[H],[H,M],[M]); embed_mlp_x, embed_mlp_z ([M+d+1,H],[H],[H,d],[d]) */
+    const float *cmx[4], *cmz[4], *cex[4], *cez[4];
+    /* update_h_vn: msg_mlp_x, msg_mlp_z; embed_mlp ([2M+d,H],[H],[H,d],[d]) */
+    const float *vmx[4], *vmz[4], *ve[4];
+} orc_gbp_t;
+
+static void gbp_edge_mlp(const orc_gbp_t *G, const float *const w[4], const float *from, const float *base,
+                         float *hid, float *msg) {
+    const int d = G->d, H = G->H, M = G->M;
+    for (int j = 0; j < H; j++) {
+        float a = base[j];
+        for (int k = 0; k < d; k++) a = FB_FMA(from[k], w[0][k * H + j], a);
+        if (w[1]) a = FB_ADD(a, w[1][j]);
+        hid[j] = gnn_act(G->act, a);
+    }
+    for (int i = 0; i < M; i++) {
+        float a = 0.0f;
+        for (int j = 0; j < H; j++) a = FB_FMA(hid[j], w[2][j * M + i], a);
+        if (w[3]) a = FB_ADD(a, w[3][i]);
+        msg[i] = a;
+    }
+}
+
+static void gbp_base(const orc_gbp_t *G, const float *const w[4], const float *to, float *base) {
+    const int d = G->d, H = G->H;
+    for (int j = 0; j < H; j++) {
+        float a = 0.0f;
+        for (int k = 0; k < d; k++) a = FB_FMA(to[k], w[0][(d + k) * H + j], a);
+        base[j] = a;
+    }
+}
+
+static void gbp_node_mlp(const orc_gbp_t *G, const float *const w[4], const float *in, int K, float *hid, float *out) {
+    const int d = G->d, H = G->H;
+    for (int j = 0; j < H; j++) {
+        float a = 0.0f;
+        for (int k = 0; k < K; k++) a = FB_FMA(in[k], w[0][k * H + j], a);
+        if (w[1]) a = FB_ADD(a, w[1][j]);
+        hid[j] = gnn_act(G->act, a);
+    }
+    for (int i = 0; i < d; i++) {
+        float a = 0.0f;
+        for (int j = 0; j < H; j++) a = FB_FMA(hid[j], w[2][j * d + i], a);
+        if (w[3]) a = FB_ADD(a, w[3][i]);
+        out[i] = a;
+    }
+}
+
+static void gbp_reduce(const orc_gbp_t *G, float *red, const float *msg, int first, int M) {
+    for (int i = 0; i < M; i++) {
+        if (first) red[i] = (G->reduce <= 1) ? FB_ADD(0.0f, msg[i]) : msg[i];
+        else if (G->reduce <= 1) red[i] = FB_ADD(red[i], msg[i]);
+        else if (G->reduce == 2) red[i] = (msg[i] > red[i]) ? msg[i] : red[i];
+        else red[i] = (msg[i] < red[i]) ? msg[i] : red[i];
+    }
+}
+
+/* UpdateCNEmbeddings.call for one side (gnn.py:574-610) */
+static void gbp_cn_update(const orc_gbp_t *G, const orc_side_t *S, const float *const wm[4], const float *const we[4],
+                          const float *h_vn, float *h_cn, const float *logit, float *work) {
+    const int d = G->d, H = G->H, M = G->M;
+    float *base = work, *hid = base + H, *msg = hid + H, *red = msg + M, *in = red + M, *out = in + M + d + 1;
+    for (int c = 0; c < S->m; c++) {
+        gbp_base(G, wm, h_cn + c * d, base);
+        const int k0 = S->cn_ptr[c], k1 = S->cn_ptr[c + 1];
+        for (int i = 0; i < M; i++) red[i] = 0.0f;
+        for (int k = k0; k < k1; k++) {
+            gbp_edge_mlp(G, wm, h_vn + S->cn_vn[k] * d, base, hid, msg);
+            gbp_reduce(G, red, msg, k == k0, M);
+        }
+        if (G->reduce == 0 && k1 > k0) for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], (float)(k1 - k0));
+        for (int i = 0; i < M; i++) in[i] = red[i];
+        for (int i = 0; i < d; i++) in[M + i] = h_cn[c * d + i];
+        in[M + d] = logit[c];
+        gbp_node_mlp(G, we, in, M + d + 1, hid, out);
+        for (int i = 0; i < d; i++) h_cn[c * d + i] = out[i];
+    }
+}
+
+/* UpdateVNEmbeddings.call (gnn.py:716-750) */
+static void gbp_vn_update(const orc_gbp_t *G, const orc_side_t *X, const orc_side_t *Z, const float *hcx,
+                          const float *hcz, float *h_vn, const uint8_t *sx, const uint8_t *sz, float *work) {
+    const int d = G->d, H = G->H, M = G->M;
+    float *base = work, *hid = base + H, *msg = hid + H, *in = msg + M, *out = in + 2 * M + d;
+    for (int v = 0; v < X->n; v++) {
+        for (int side = 0; side < 2; side++) {
+            const orc_side_t *S = side ? Z : X;
+            const float *const *wm = side ? G->vmz : G->vmx;
+            const float *hc = side ? hcz : hcx;
+            const uint8_t *sy = side ? sz : sx;
+            float *red = in + side * M;
+            gbp_base(G, wm, h_vn + v * d, base);
+            const int e0 = S->vn_ptr[v], e1 = S->vn_ptr[v + 1];
+            for (int i = 0; i < M; i++) red[i] = 0.0f;
+            for (int e = e0; e < e1; e++) {
+                const int c = S->vn_cn[e];
+                gbp_edge_mlp(G, wm, hc + c * d, base, hid, msg);
+                if (sy[c]) for (int i = 0; i < M; i++) msg[i] = -msg[i];          /* x (1 - 2 s), gnn.py:733-737 */
+                gbp_reduce(G, red, msg, e == e0, M);
+            }
+            if (G->reduce == 0 && e1 > e0) for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], (float)(e1 - e0));
+        }
+        for (int i = 0; i < d; i++) in[2 * M + i] = h_vn[v * d + i];
+        gbp_node_mlp(G, G->ve, in, 2 * M + d, hid, out);
+        for (int i = 0; i < d; i++) h_vn[v * d + i] = out[i];
+    }
+}
+
+static float gbp_soft_row(const orc_rows_t *R, int r, const float *l) {
+    float sgn = 1.0f, T = 0.0f;
+    for (int k = R->ptr[r]; k < R->ptr[r + 1]; k++) {
+        float m = l[R->col[k]];
+        if (m < 0.0f) sgn = -sgn;
+        T = FB_ADD(T, fb_phi2f(fabsf(m)));
+    }
+    return FB_MUL(sgn, fb_phi2f(T));
+}
+
+/* One frame of GNN_BP4.call.  sx [m_x], sz [m_z]; x_logit [num_iter][m_z + k_z], z_logit [num_iter][m_x + k_x]
+ * (x_perp_logit = [hz_logit; lz_logit], z_perp_logit = [hx_logit; lx_logit], gnn.py:311-313); xh, zh [n]. */
+static void gbp_frame(const orc_gbp_t *G, const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *lx,
+                      const orc_rows_t *lz, const uint8_t *sx, const uint8_t *sz, float *x_logit, float *z_logit,
+                      uint8_t *xh, uint8_t *zh, float *fw) {
+    const int n = X->n, d = G->d;
+    const orc_rows_t hxr = { X->m, X->cn_ptr, X->cn_vn }, hzr = { Z->m, Z->cn_ptr, Z->cn_vn };
+    float *h_vn = fw, *hcx = h_vn + n * d, *hcz = hcx + X->m * d, *lgx = hcz + Z->m * d, *lgz = lgx + X->m,
+          *llr = lgz + Z->m, *lxp = llr + 3 * n, *lzp = lxp + n, *work = lzp + n;
+    for (int i = 0; i < n * d; i++) h_vn[i] = 1.0f;
+    for (int i = 0; i < (X->m + Z->m) * d; i++) hcx[i] = 0.0f;
+    for (int c = 0; c < X->m + Z->m; c++) lgx[c] = 0.0f;
+    gbp_cn_update(G, X, G->cmx, G->cex, h_vn, hcx, lgx, work);
+    gbp_cn_update(G, Z, G->cmz, G->cez, h_vn, hcz, lgz, work);
+    for (int it = 0; it < G->num_iter; it++) {
+        gbp_vn_update(G, X, Z, hcx, hcz, h_vn, sx, sz, work);
+        for (int v = 0; v < n; v++) {                       /* embed_to_llr + cal_logit, gnn.py:281-314 */
+            for (int c = 0; c < 3; c++) {
+                float a = 0.0f;
+                for (int k = 0; k < d; k++) a = FB_FMA(h_vn[v * d + k], G->Winv[k * 3 + c], a);
+                if (G->binv) a = FB_ADD(a, G->binv[c]);
+                llr[c * n + v] = a;
+            }
+            const float Lx = llr[v], Ly = llr[n + v], Lz = llr[2 * n + v];
+            lzp[v] = FB_SUB(fb_softplusf(-Lx), fb_logaddexpf(-Lz, -Ly));
+            lxp[v] = FB_SUB(fb_softplusf(-Lz), fb_logaddexpf(-Lx, -Ly));
+        }
+        float *xo = x_logit + (size_t)it * (Z->m + lz->m), *zo = z_logit + (size_t)it * (X->m + lx->m);
+        for (int r = 0; r < Z->m; r++) xo[r] = lgz[r] = gbp_soft_row(&hzr, r, lxp);
+        for (int r = 0; r < lz->m; r++) xo[Z->m + r] = gbp_soft_row(lz, r, lxp);
+        for (int r = 0; r < X->m; r++) zo[r] = lgx[r] = gbp_soft_row(&hxr, r, lzp);
+        for (int r = 0; r < lx->m; r++) zo[X->m + r] = gbp_soft_row(lx, r, lzp);
+        if (it == G->num_iter - 1) break;
+        for (int c = 0; c < X->m; c++) if (sx[c]) lgx[c] = -lgx[c];            /* hx_logit * (1 - 2 s) */
+        for (int c = 0; c < Z->m; c++) if (sz[c]) lgz[c] = -lgz[c];
+        gbp_cn_update(G, X, G->cmx, G->cex, h_vn, hcx, lgx, work);
+        gbp_cn_update(G, Z, G->cmz, G->cez, h_vn, hcz, lgz, work);
+    }
+    for (int v = 0; v < n; v++) {                           /* make_hard_decision, gnn.py:358-366 */
+        int dd = 0;
+        float best = 0.0f;
+        if (llr[v] < best) { best = llr[v]; dd = 1; }
+        if (llr[2 * n + v] < best) { best = llr[2 * n + v]; dd = 2; }
+        if (llr[n + v] < best) { best = llr[n + v]; dd = 3; }
+        xh[v] = (uint8_t)(dd & 1);
+        zh[v] = (uint8_t)(dd >> 1);
+    }
+}
+
+/* synd_x [B,m_x], synd_z [B,m_z] (batch first, gnn.py:385-386); x_logit [num_iter][m_z+k_z][B],
+ * z_logit [num_iter][m_x+k_x][B]; x_hat, z_hat [n][B] */
+void orc_gnn_bp4(const orc_gbp_t *G, const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *lx,
+                 const orc_rows_t *lz, int64_t B, const uint8_t *synd_x, const uint8_t *synd_z, float *x_logit,
+                 float *z_logit, uint8_t *x_hat, uint8_t *z_hat) {
+    const int n = X->n, d = G->d, rx = Z->m + lz->m, rz = X->m + lx->m;
+#pragma omp parallel
+    {
+        const size_t fwn = (size_t)(n + X->m + Z->m) * d + X->m + Z->m + 5 * (size_t)n + 4 * (size_t)G->H +
+                           6 * (size_t)G->M + 4 * (size_t)d + 64;
+        float *fw = (float *)malloc(sizeof(float) * fwn);
+        float *xl = (float *)malloc(sizeof(float) * (size_t)G->num_iter * rx + 4);
+        float *zl = (float *)malloc(sizeof(float) * (size_t)G->num_iter * rz + 4);
+        uint8_t *xh = (uint8_t *)malloc(2 * (size_t)n);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t b = 0; b < B; b++) {
+            gbp_frame(G, X, Z, lx, lz, synd_x + b * X->m, synd_z + b * Z->m, xl, zl, xh, xh + n, fw);
+            for (int it = 0; it < G->num_iter; it++) {
+                for (int r = 0; r < rx; r++) x_logit[((int64_t)it * rx + r) * B + b] = xl[(size_t)it * rx + r];
+                for (int r = 0; r < rz; r++) z_logit[((int64_t)it * rz + r) * B + b] = zl[(size_t)it * rz + r];
+            }
+            for (int v = 0; v < n; v++) { x_hat[(int64_t)v * B + b] = xh[v]; z_hat[(int64_t)v * B + b] = xh[n + v]; }
+        }
+        free(fw); free(xl); free(zl); free(xh);
+    }
+}
+
 /* ---------------------------------------------------------------- math probes ------ */
 #define ORC_VEC(name, fn) \
     void name(const float *x, float *y, int64_t n) { for (int64_t i = 0; i < n; i++) y[i] = fn(x[i]); }

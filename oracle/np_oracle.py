@@ -253,3 +253,76 @@ def pipeline(code, X, Z, num_iters, weights_list, noise_x, noise_z, prior, facto
     s_hat = np.concatenate([(code.hz @ xd) & 1, (code.hx @ zd) & 1], 0).T
     ls_hat = np.concatenate([(code.hx_perp @ xd) & 1, (code.hz_perp @ zd) & 1], 0).T
     return s_hat, ls_hat
+
+
+# ------------------------------------------------------------------ GNN_BP4 (gnn.py:71-751) ----
+def _mlp2(x, w, act):
+    """MLP with one hidden layer: w = (W1, b1, W2, b2) (gnn.py:31-69)."""
+    h = act((x @ w[0] + (w[1] if w[1] is not None else 0)).astype(F)).astype(F)
+    return (h @ w[2] + (w[3] if w[3] is not None else 0)).astype(F)
+
+
+def _reduce(msg, starts, deg, reduce_op):
+    if reduce_op in ("mean", "sum"):
+        red = np.add.reduceat(msg, starts, axis=1)
+        if reduce_op == "mean":
+            red = red / deg[None, :, None].astype(F)
+    elif reduce_op == "max":
+        red = np.maximum.reduceat(msg, starts, axis=1)
+    else:
+        red = np.minimum.reduceat(msg, starts, axis=1)
+    return red.astype(F)
+
+
+def _soft_rows(rows_side, l):
+    S = rows_side
+    vals = l[S.vn_of_edge[S.ind_cn]]
+    sign = np.where(vals < 0, F(-1), F(1))
+    node = S.cn_reduce(np.multiply, sign)
+    T = S.cn_reduce(np.add, phi2(np.abs(vals))).astype(F)
+    return (node * phi2(T)).astype(F)
+
+
+def gnn_bp4(X, Z, LX, LZ, W, synd_x, synd_z, num_iter, activation="tanh", reduce_op="mean"):
+    """GNN_BP4.call.  X, Z, LX, LZ: Side objects of hx, hz, lx, lz; W: dict with keys Winv, binv and the
+    4-tuples cmx, cmz, cex, cez, vmx, vmz, ve; synd_* [B, m] 0/1.  Returns (list of (x_logit, z_logit)
+    with shapes [m_z+k, B], [m_x+k, B]), x_hat [n,B], z_hat [n,B]."""
+    act = _act(activation)
+    sx, sz = np.asarray(synd_x), np.asarray(synd_z)
+    B, n, d = sx.shape[0], X.n, W["Winv"].shape[0]
+    ssx, ssz = (1 - 2 * sx.astype(np.int32)).astype(F), (1 - 2 * sz.astype(np.int32)).astype(F)
+    h_vn = np.ones((B, n, d), F)
+    h_cn = {0: np.zeros((B, X.m, d), F), 1: np.zeros((B, Z.m, d), F)}
+    sides = {0: X, 1: Z}
+
+    def cn_update(logits):
+        for s, S in sides.items():
+            vn_c, cn_c = S.vn_of_edge[S.ind_cn], S.cn_of_edge_c             # edges in CN order
+            feat = np.concatenate([h_vn[:, vn_c, :], h_cn[s][:, cn_c, :]], -1)
+            msg = _mlp2(feat, W["cmx" if s == 0 else "cmz"], act)
+            m = _reduce(msg, S.cn_starts, S.cn_deg, reduce_op)
+            inp = np.concatenate([m, h_cn[s], logits[s][:, :, None]], -1)
+            h_cn[s] = _mlp2(inp, W["cex" if s == 0 else "cez"], act)
+
+    cn_update({0: np.zeros((B, X.m), F), 1: np.zeros((B, Z.m), F)})
+    out = []
+    for it in range(num_iter):
+        ms = []
+        for s, S in sides.items():
+            feat = np.concatenate([h_cn[s][:, S.cn_of_edge, :], h_vn[:, S.vn_of_edge, :]], -1)   # VN order
+            msg = _mlp2(feat, W["vmx" if s == 0 else "vmz"], act)
+            msg = msg * (ssx if s == 0 else ssz)[:, S.cn_of_edge, None]
+            ms.append(_reduce(msg.astype(F), S.vn_starts, S.vn_deg, reduce_op))
+        h_vn = _mlp2(np.concatenate(ms + [h_vn], -1), W["ve"], act)
+        llr = (h_vn @ W["Winv"] + (W["binv"] if W["binv"] is not None else 0)).astype(F)       # [B,n,3]
+        Lx, Ly, Lz = llr[..., 0].T, llr[..., 1].T, llr[..., 2].T                              # [n,B]
+        llr_z = (softplus(-Lx) - logsumexp2(-Lz, -Ly)).astype(F)
+        llr_x = (softplus(-Lz) - logsumexp2(-Lx, -Ly)).astype(F)
+        hz_logit, lz_logit = _soft_rows(Z, llr_x), _soft_rows(LZ, llr_x)
+        hx_logit, lx_logit = _soft_rows(X, llr_z), _soft_rows(LX, llr_z)
+        out.append((np.concatenate([hz_logit, lz_logit], 0), np.concatenate([hx_logit, lx_logit], 0)))
+        if it == num_iter - 1:
+            break
+        cn_update({0: (hx_logit.T * ssx).astype(F), 1: (hz_logit.T * ssz).astype(F)})
+    xh, zh = decide(Lx, Ly, Lz)
+    return out, xh, zh
