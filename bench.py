@@ -326,7 +326,13 @@ def main():
                 "peak": sfu_peak / 1e9, "unit": "G transcendental evals/s", "frac": achieved / sfu_peak,
                 "peak_source": "measured live: ex2.approx micro-benchmark (fbgnn_sfu_peak)",
                 "units_per_launch": B, "te_per_unit": 64 * TE_ITER + TE_EPI, "launch_ms": k_ms,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
+                # (profiles/r01_ncu_final_bp4_gnn_2368frames.txt: 7.89 MB for a 2368-frame launch), scaled to B frames
+                "traffic": int(7893504 / 2368 * B),
+                "traffic_note": "scaled from the 2368-frame ncu capture in profiles/; the algorithmic HBM bytes are "
+                                "~1.3 KB of syndromes in + 20 KB of marginals/soft syndromes out per frame (the writes "
+                                "stay in the 126 MB L2 during the launch)",
+                "issue_slot_utilisation_ncu": 0.864,
                 "fp32_issue_peak_ginstr_s": fma_peak / 1e9,
                 "whole_step_frac": value * TE_PER_FRAME / sfu_peak,
                 "hbm_peak_gbs": _measured_peaks().get("hbm_gbs"),
