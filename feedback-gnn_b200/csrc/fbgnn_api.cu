@@ -505,13 +505,13 @@ static int set_smem(K kernel, size_t bytes, fbgnn_ctx *ctx, const char *what) {
 
 static size_t bp4_smem(const SideDev &X, const SideDev &Z, bool const_prior, bool iter_logits) {
     return sizeof(float) * ((size_t)X.E + Z.E + ((const_prior ? 2 : 3) + (iter_logits ? 2 : 0)) * (size_t)X.n) +
-           X.m + Z.m + X.n + 16;
+           2 * (((size_t)X.n + 1) & ~(size_t)1) + X.m + Z.m + X.n + 16;
 }
 
-template <bool CP, int DV, int DC, typename MATH>
+template <bool CP, int DV, int DC, typename MATH, bool FPX>
 static int launch_bp4_t(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t smem, int threads) {
-    if (int rc = set_smem(k_bp4<CP, DV, DC, MATH>, smem, ctx, "quaternary BP")) return rc;
-    k_bp4<CP, DV, DC, MATH><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+    if (int rc = set_smem(k_bp4<CP, DV, DC, MATH, FPX>, smem, ctx, "quaternary BP")) return rc;
+    k_bp4<CP, DV, DC, MATH, FPX><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->launches++;
     return 0;
@@ -520,10 +520,16 @@ static int launch_bp4_t(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t s
 template <int DV, int DC>
 static int launch_bp4_m(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t smem, int threads, bool cp) {
     if (ctx->math_mode == FBGNN_MATH_FAST)
-        return cp ? launch_bp4_t<true, DV, DC, MathFast>(ctx, a, grid, smem, threads)
-                  : launch_bp4_t<false, DV, DC, MathFast>(ctx, a, grid, smem, threads);
-    return cp ? launch_bp4_t<true, DV, DC, MathExact>(ctx, a, grid, smem, threads)
-              : launch_bp4_t<false, DV, DC, MathExact>(ctx, a, grid, smem, threads);
+        return cp ? launch_bp4_t<true, DV, DC, MathFast, false>(ctx, a, grid, smem, threads)
+                  : launch_bp4_t<false, DV, DC, MathFast, false>(ctx, a, grid, smem, threads);
+    // fixed-point exit: exact arithmetic, regular graph, boxplus-phi, long runs (the bookkeeping costs ~5 %
+    // per unsaturated iteration and a 16-iteration stage does not converge-and-saturate in time)
+    const bool fpx = DV > 0 && a.cn_type == 0 && a.num_iter >= 32 && !a.iter_logits.ptr;
+    if (fpx)
+        return cp ? launch_bp4_t<true, DV, DC, MathExact, true>(ctx, a, grid, smem, threads)
+                  : launch_bp4_t<false, DV, DC, MathExact, true>(ctx, a, grid, smem, threads);
+    return cp ? launch_bp4_t<true, DV, DC, MathExact, false>(ctx, a, grid, smem, threads)
+              : launch_bp4_t<false, DV, DC, MathExact, false>(ctx, a, grid, smem, threads);
 }
 
 static int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {

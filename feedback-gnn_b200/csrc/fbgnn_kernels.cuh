@@ -231,9 +231,15 @@ __device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge,
 // ranges are v*DV.. and c*DC.., all loops unroll, the phi values and signs of a check stay in
 // registers and the DC (or 2*DV) independent phi / logaddexp chains give the scheduler ILP.
 // Operation order is exactly that of the generic path (and of the oracle).
-template <int DC, bool PHI4, typename MATH>
-__device__ __forceinline__ void cn_phi_regular(const idx_t *__restrict__ cn_edge, int c, float *msg,
-                                               int synd_bit, float factor) {
+// `rec` (optional): per-variable record written by the preceding VN phase -- bit s set if the incoming
+// c2v message in slot s (x edges 0..DV-1, z edges DV..2DV-1) was negative, bit 15 set unless all of them
+// had the saturated magnitude phi_max * factor.  The function returns true iff every message it writes
+// is bit-identical to the one it replaces (saturated magnitude, same sign): when that holds for all
+// checks of a frame the decoder state is a fixed point of the (deterministic) iteration and the
+// remaining iterations cannot change it.
+template <int DC, int DV, bool PHI4, typename MATH, bool FPX>
+__device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge, int c, float *msg,
+                                               int synd_bit, float factor, const uint16_t *rec, int slot0) {
     int e[DC];
     float a[DC];
     uint32_t neg = 0;
@@ -251,20 +257,44 @@ __device__ __forceinline__ void cn_phi_regular(const idx_t *__restrict__ cn_edge
     float T = 0.0f;
 #pragma unroll
     for (int k = 0; k < DC; k++) T = FB_ADD(T, a[k]);
+    bool stable = FPX && rec != nullptr;
 #pragma unroll
     for (int k = 0; k < DC; k++) {
-        float v = phi_sat<MATH, PHI4>(FB_SUB(T, a[k]));
+        const float x = FB_SUB(T, a[k]);
+        float v = phi_sat<MATH, PHI4>(x);
         const uint32_t s = ((uint32_t)par ^ (neg >> k)) & 1u;
         v = __int_as_float(__float_as_int(v) ^ (int)(s << 31));
         msg[e[k]] = FB_MUL(v, factor);
+        if (FPX && rec) {
+            if (__all_sync(__activemask(), x <= FB_PHI_CLIP_LO)) {
+                const int vv = e[k] / DV;
+                const int r = rec[vv];
+                stable = stable && !(r & 0x8000) && ((uint32_t)((r >> (e[k] - vv * DV + slot0)) & 1) == s);
+            } else {
+                stable = false;
+            }
+        }
     }
+    return stable;
 }
 
-template <int DV, typename MATH>
-__device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, float px, float py, float pz) {
+template <int DV, typename MATH, bool FPX>
+__device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, float px, float py, float pz,
+                                                  uint16_t *rec, int sat_bits) {
     float ax[DV], az[DV];
 #pragma unroll
     for (int k = 0; k < DV; k++) { ax[k] = mx[v * DV + k]; az[k] = mz[v * DV + k]; }
+    if (FPX && rec) {      // signs of the incoming messages and whether all of them are saturated (see cn_phi_regular)
+        int r = 0, bad = 0;
+#pragma unroll
+        for (int k = 0; k < DV; k++) {
+            const int bx = __float_as_int(ax[k]), bz = __float_as_int(az[k]);
+            r |= ((bx >> 31) & 1) << k;
+            r |= ((bz >> 31) & 1) << (DV + k);
+            bad |= ((bx & 0x7fffffff) ^ sat_bits) | ((bz & 0x7fffffff) ^ sat_bits);
+        }
+        rec[v] = (uint16_t)(bad ? 0x8000 : r);
+    }
     float Sx = 0.0f, Sz = 0.0f;
 #pragma unroll
     for (int k = 0; k < DV; k++) Sx = FB_ADD(Sx, ax[k]);
@@ -350,15 +380,17 @@ __device__ void bp4_iter_logits(const Bp4Args &a, const float *mx, const float *
 }
 
 // One CTA decodes one frame.  Dynamic shared memory:
-//   float msg_x[E_x], msg_z[E_z], pri[CONST_PRIOR ? 2n : 3n], (scr[2n] if iter_logits);  u8 sbx[m_x], sbz[m_z], dec[n]
-template <bool CONST_PRIOR, int DV, int DC, typename MATH>
+//   float msg_x[E_x], msg_z[E_z], pri[CONST_PRIOR ? 2n : 3n], (scr[2n] if iter_logits);  u16 rec[n];
+//   u8 sbx[m_x], sbz[m_z], dec[n]
+template <bool CONST_PRIOR, int DV, int DC, typename MATH, bool FPX>
 __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     extern __shared__ float smem[];
     const SideDev &X = a.X, &Z = a.Z;
     const int n = X.n, T = blockDim.x, tid = threadIdx.x;
     const int64_t b = a.frame_list ? a.frame_list[blockIdx.x] : blockIdx.x;
     float *mx = smem, *mz = mx + X.E, *pri = mz + Z.E, *scr2 = pri + (CONST_PRIOR ? 2 : 3) * n;
-    uint8_t *sbx = (uint8_t *)(scr2 + (a.iter_logits.ptr ? 2 * n : 0)), *sbz = sbx + X.m, *dec = sbz + Z.m;
+    uint16_t *rec = (uint16_t *)(scr2 + (a.iter_logits.ptr ? 2 * n : 0));
+    uint8_t *sbx = (uint8_t *)(rec + ((n + 1) & ~1)), *sbz = sbx + X.m, *dec = sbz + Z.m;
 
     for (int e = tid; e < X.E + Z.E; e += T) mx[e] = 0.0f;
     if (!CONST_PRIOR)
@@ -368,15 +400,21 @@ __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     __syncthreads();
 
     const bool fast = DV > 0 && a.cn_type == 0;     // regular graph + boxplus-phi: unrolled path
+    // Fixed-point exit (exact arithmetic only): once an iteration reproduces every message bit for bit
+    // the remaining iterations are no-ops, so they are skipped -- the outputs are unchanged by construction.
+    // Only worth its bookkeeping for long runs (the 64-iteration first stage), and never before iteration 6.
+    const bool fp_exit = FPX && fast && MATH::kSaturationShortcuts && !a.iter_logits.ptr;
+    const int sat_bits = __float_as_int(FB_MUL(FB_PHI_CLIP_HI, a.factor)) & 0x7fffffff;   // |phi(clip_lo) * factor|
     for (int it = 0; it < a.num_iter; it++) {
         if (a.iter_logits.ptr) bp4_iter_logits<CONST_PRIOR, MATH>(a, mx, mz, pri, scr2, dec, b, it);
+        uint16_t *recp = (fp_exit && it >= 6) ? rec : nullptr;
         // variable nodes (decoding_q.py:227-275)
         for (int v = tid; v < n; v += T) {
             const float px = CONST_PRIOR ? a.prior : pri[v];
             const float py = CONST_PRIOR ? a.prior : pri[n + v];
             const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
             if (DV > 0) {
-                vn_update_regular<(DV > 0 ? DV : 1), MATH>(v, mx, mz, px, py, pz);
+                vn_update_regular<(DV > 0 ? DV : 1), MATH, FPX>(v, mx, mz, px, py, pz, recp, sat_bits);
                 continue;
             }
             const int x0 = X.vn_ptr[v], x1 = X.vn_ptr[v + 1], z0 = Z.vn_ptr[v], z1 = Z.vn_ptr[v + 1];
@@ -398,19 +436,25 @@ __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         }
         __syncthreads();
         // check nodes of both sides as one index space
+        bool stable = true;
         for (int c = tid; c < X.m + Z.m; c += T) {
             const bool isx = c < X.m;
             const int cc = isx ? c : c - X.m;
             float *msg = isx ? mx : mz;
             const int sb = isx ? sbx[cc] : sbz[cc];
             if (fast) {
-                cn_phi_regular<(DC > 0 ? DC : 1), true, MATH>(isx ? X.cn_edge : Z.cn_edge, cc, msg, sb, a.factor);
+                stable &= cn_phi_regular<(DC > 0 ? DC : 1), (DV > 0 ? DV : 1), true, MATH, FPX>(
+                    isx ? X.cn_edge : Z.cn_edge, cc, msg, sb, a.factor, recp, isx ? 0 : DV);
             } else {
                 const SideDev &S = isx ? X : Z;
                 cn_update_one<true, MATH>(S.cn_edge, S.cn_ptr[cc], S.cn_ptr[cc + 1], msg, sb, a.cn_type, a.factor);
             }
         }
-        __syncthreads();
+        if (FPX && recp) {
+            if (__syncthreads_and(stable)) break;
+        } else {
+            __syncthreads();
+        }
     }
 
     if (a.iter_logits.ptr) bp4_iter_logits<CONST_PRIOR, MATH>(a, mx, mz, pri, scr2, dec, b, a.num_iter);
@@ -547,7 +591,7 @@ __global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
         }
         __syncthreads();
         for (int c = tid; c < S.m; c += T) {
-            if (fast) cn_phi_regular<(DC > 0 ? DC : 1), false, MATH>(S.cn_edge, c, msg, sb[c], a.factor);
+            if (fast) cn_phi_regular<(DC > 0 ? DC : 1), (DV > 0 ? DV : 1), false, MATH, false>(S.cn_edge, c, msg, sb[c], a.factor, nullptr, 0);
             else cn_update_one<false, MATH>(S.cn_edge, S.cn_ptr[c], S.cn_ptr[c + 1], msg, sb[c], a.cn_type, a.factor);
         }
         __syncthreads();
