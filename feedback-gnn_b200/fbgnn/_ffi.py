@@ -350,11 +350,15 @@ class DeviceArray:
 
     def t2(self):
         assert self.ndim == 2
-        return Tensor2(self.ptr, self.strides[0], self.strides[1])
+        t = Tensor2(self.ptr, self.strides[0], self.strides[1])
+        t._keep = self          # the view keeps its allocation alive (frees are stream-ordered)
+        return t
 
     def t3(self):
         assert self.ndim == 3
-        return Tensor3(self.ptr, self.strides[0], self.strides[1], self.strides[2])
+        t = Tensor3(self.ptr, self.strides[0], self.strides[1], self.strides[2])
+        t._keep = self
+        return t
 
     # -- host transfer -------------------------------------------------------------------
     def numpy(self):
