@@ -334,7 +334,7 @@ def main():
                                 "stay in the 126 MB L2 during the launch)",
                 "issue_slot_utilisation_ncu": 0.864,
                 "fp32_issue_peak_ginstr_s": fma_peak / 1e9,
-                "whole_step_frac": value * TE_PER_FRAME / sfu_peak,
+                "whole_step_frac": value * TE_PER_FRAME / (sfu_peak * world),
                 "hbm_peak_gbs": _measured_peaks().get("hbm_gbs"),
                 "note": "algorithmic TE count of SURVEY.md 8(d) / measured MUFU peak; the shipped path evaluates "
                         "exp/log in bit-exact software (FP32 pipe) so its own bound is the FP32 issue rate "
@@ -371,7 +371,7 @@ def main():
                                       "is reported beside the headline, not as the headline"},
             "fast_math": {"value": fast_value, "unit": "frames/s", "steps": fast_steps,
                           "block_errors": int(fast_counters[2]), "frames": int(fast_counters[0]),
-                          "sfu_frac": fast_value * TE_PER_FRAME / sfu_peak,
+                          "sfu_frac": fast_value * TE_PER_FRAME / (sfu_peak * world),
                           "note": "opt-in Context.set_math('fast'): MUFU ex2/lg2/rcp instead of the bit-exact software "
                                   "libm. NOT a parity path: not bit-exact and its logical error rate is lower than "
                                   "the reference's (tests/test_gpu_fastmath.py); informational only"},

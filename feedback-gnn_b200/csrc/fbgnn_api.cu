@@ -725,23 +725,23 @@ extern "C" int fbgnn_gnn_destroy(fbgnn_gnn *g) {
     return 0;
 }
 
-template <int H, int M, int DV, bool TB, typename MATH>
+template <int H, int M, int DV, bool TB, bool FACT, typename MATH>
 static int launch_gnn_t(fbgnn_ctx *ctx, const GnnArgs &a) {
     const size_t smem = sizeof(float) * GnnLayout<H, M>::total;
-    if (int rc = set_smem(k_gnn<H, M, DV, TB, MATH>, smem, ctx, "feedback GNN")) return rc;
+    if (int rc = set_smem(k_gnn<H, M, DV, TB, FACT, MATH>, smem, ctx, "feedback GNN")) return rc;
     const int64_t items = a.num_frames * a.X.n;
     int64_t blocks = (items + 127) / 128;
     blocks = std::min<int64_t>(blocks, (int64_t)ctx->num_sms * 8);
-    k_gnn<H, M, DV, TB, MATH><<<(unsigned)blocks, 128, smem, ctx->stream>>>(a);
+    k_gnn<H, M, DV, TB, FACT, MATH><<<(unsigned)blocks, 128, smem, ctx->stream>>>(a);
     CK(cudaGetLastError());
     ctx->launches++;
     return 0;
 }
 
-template <int H, int M, int DV, bool TB>
+template <int H, int M, int DV, bool TB, bool FACT = true>
 static int launch_gnn_m(fbgnn_ctx *ctx, const GnnArgs &a) {
-    return ctx->math_mode == FBGNN_MATH_FAST ? launch_gnn_t<H, M, DV, TB, MathFast>(ctx, a)
-                                             : launch_gnn_t<H, M, DV, TB, MathExact>(ctx, a);
+    return ctx->math_mode == FBGNN_MATH_FAST ? launch_gnn_t<H, M, DV, TB, FACT, MathFast>(ctx, a)
+                                             : launch_gnn_t<H, M, DV, TB, FACT, MathExact>(ctx, a);
 }
 
 static int launch_gnn(fbgnn_ctx *ctx, const fbgnn_gnn *g, GnnArgs &a) {
@@ -749,13 +749,15 @@ static int launch_gnn(fbgnn_ctx *ctx, const fbgnn_gnn *g, GnnArgs &a) {
     a.weights = g->weights; a.act = g->act; a.reduce = g->reduce; a.use_bias = g->use_bias;
     const bool reg3 = a.X.reg_dv == 3 && a.Z.reg_dv == 3;      // the (3,6)-regular GHP / bivariate codes
     const bool tb = g->act == FBGNN_ACT_TANH && g->use_bias;   // the shipped configuration
+    const bool fact = g->reduce <= 1;                          // mean / sum: output layer after the reduction
     if (g->H == 40 && g->M == 20) {
+        if (!fact) return launch_gnn_m<40, 20, 0, false, false>(ctx, a);
         if (reg3 && tb) return launch_gnn_m<40, 20, 3, true>(ctx, a);
         if (reg3) return launch_gnn_m<40, 20, 3, false>(ctx, a);
         return tb ? launch_gnn_m<40, 20, 0, true>(ctx, a) : launch_gnn_m<40, 20, 0, false>(ctx, a);
     }
-    if (g->H == 20 && g->M == 20) return launch_gnn_m<20, 20, 0, false>(ctx, a);
-    if (g->H == 64 && g->M == 32) return launch_gnn_m<64, 32, 0, false>(ctx, a);
+    if (g->H == 20 && g->M == 20) return fact ? launch_gnn_m<20, 20, 0, false>(ctx, a) : launch_gnn_m<20, 20, 0, false, false>(ctx, a);
+    if (g->H == 64 && g->M == 32) return fact ? launch_gnn_m<64, 32, 0, false>(ctx, a) : launch_gnn_m<64, 32, 0, false, false>(ctx, a);
     return fail(FBGNN_E_UNSUPPORTED, "unsupported GNN dimensions");
 }
 

@@ -667,17 +667,21 @@ struct WSmem {
 
 // One thread per (frame, variable node).  Messages of one side into the variable node are computed
 // and reduced as in feedback_gnn.py:175-184; the arithmetic and its order are those of
-// oracle/fbgnn_oracle.c.
-//   DV > 0 : both sides are DV-regular -- the DV edges of a side are processed together, so each
-//            weight fetched feeds DV FMAs and the DV tanh chains overlap;  DV == 0 : edge by edge.
+// oracle/fbgnn_oracle.c (gnn_side).
+//   FACT   : reduce_op "mean" / "sum" -- the linear output layer of the edge MLP is applied once to
+//            the sum of the hidden activations over the node's edges (W2^T sum_e t_e + deg b2), which
+//            removes deg-1 of every deg H x M products;  !FACT ("max" / "min"): per-edge messages.
+//   DV > 0 : both sides are DV-regular -- the DV edges of a side are processed together, so the DV
+//            tanh chains overlap;  DV == 0 : any degrees.
 //   TANH_BIAS : compile-time specialisation of the shipped configuration (tanh, use_bias=True);
 //            otherwise activation / bias are run-time switches.
 // The two sides share ONE copy of the inner loop (side loop not unrolled) and the loop over hidden
 // units is unrolled by two only: the hot loop body stays a few KB, inside the instruction cache.
 // Requires H % 4 == 0 and M % 4 == 0.
-template <int H, int M, int DV, bool TANH_BIAS, typename MATH, typename WSRC>
+template <int H, int M, int DV, bool TANH_BIAS, bool FACT, typename MATH, typename WSRC>
 __device__ __forceinline__ void gnn_body(const GnnArgs &a, const WSRC w) {
     typedef GnnLayout<H, M> Lay;
+    static_assert(FACT || DV == 0, "the per-edge form is only built for the generic degree path");
     constexpr int NE = DV > 0 ? DV : 1;
     const int n = a.X.n;
     const int act = TANH_BIAS ? 0 : a.act;
@@ -701,61 +705,97 @@ __device__ __forceinline__ void gnn_body(const GnnArgs &a, const WSRC w) {
             float red[M];
 #pragma unroll
             for (int i = 0; i < M; i++) red[i] = 0.0f;
-            for (int eb = e0; eb < e1; eb += NE) {
+            if (FACT) {
                 float hc[NE];
+                if (DV > 0) {
 #pragma unroll
-                for (int k = 0; k < NE; k++) {
-                    const int c = S.vn_cn[eb + k];
-                    const float lg = logit(c, b);
-                    hc[k] = synd(c, b) ? -lg : lg;
+                    for (int k = 0; k < NE; k++) {
+                        const int c = S.vn_cn[e0 + k];
+                        const float lg = logit(c, b);
+                        hc[k] = synd(c, b) ? -lg : lg;
+                    }
                 }
-                float acc[NE][M];
-#pragma unroll
-                for (int k = 0; k < NE; k++)
-#pragma unroll
-                    for (int i = 0; i < M; i++) acc[k][i] = 0.0f;
 #pragma unroll 2
                 for (int j = 0; j < H; j++) {
                     // features [h_cn, Lx, Ly, Lz]: the per-variable terms first, the check term last
                     const float base = FB_FMA(f3, w.ld(oW1 + 3 * H + j),
                                               FB_FMA(f2, w.ld(oW1 + 2 * H + j), FB_FMA(f1, w.ld(oW1 + H + j), 0.0f)));
                     const float w0 = w.ld(oW1 + j), bj = w.ld(ob1 + j);
-                    float hv[NE];
+                    float hs = 0.0f;
+                    if (DV > 0) {
+                        float hv[NE];
 #pragma unroll
-                    for (int k = 0; k < NE; k++) {
-                        float t = FB_FMA(hc[k], w0, base);
-                        if (use_bias) t = FB_ADD(t, bj);
-                        hv[k] = gnn_act<MATH>(act, t);
+                        for (int k = 0; k < NE; k++) {
+                            float t = FB_FMA(hc[k], w0, base);
+                            if (use_bias) t = FB_ADD(t, bj);
+                            hv[k] = gnn_act<MATH>(act, t);
+                        }
+                        hs = hv[0];
+#pragma unroll
+                        for (int k = 1; k < NE; k++) hs = FB_ADD(hs, hv[k]);
+                    } else {
+                        for (int e = e0; e < e1; e++) {
+                            const int c = S.vn_cn[e];
+                            const float lg = logit(c, b);
+                            float t = FB_FMA(synd(c, b) ? -lg : lg, w0, base);
+                            if (use_bias) t = FB_ADD(t, bj);
+                            const float hv = gnn_act<MATH>(act, t);
+                            hs = (e == e0) ? hv : FB_ADD(hs, hv);
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < M; i += 4) {
                         const float4 wv = w.ld4(oW2 + j * M + i);
-#pragma unroll
-                        for (int k = 0; k < NE; k++) {
-                            acc[k][i + 0] = FB_FMA(hv[k], wv.x, acc[k][i + 0]);
-                            acc[k][i + 1] = FB_FMA(hv[k], wv.y, acc[k][i + 1]);
-                            acc[k][i + 2] = FB_FMA(hv[k], wv.z, acc[k][i + 2]);
-                            acc[k][i + 3] = FB_FMA(hv[k], wv.w, acc[k][i + 3]);
-                        }
+                        red[i + 0] = FB_FMA(hs, wv.x, red[i + 0]);
+                        red[i + 1] = FB_FMA(hs, wv.y, red[i + 1]);
+                        red[i + 2] = FB_FMA(hs, wv.z, red[i + 2]);
+                        red[i + 3] = FB_FMA(hs, wv.w, red[i + 3]);
                     }
                 }
+                const float dg = (float)(e1 - e0);
 #pragma unroll
-                for (int k = 0; k < NE; k++) {
-                    const bool first = (eb + k == e0);
+                for (int i = 0; i < M; i++) {
+                    float r = red[i];
+                    if (a.reduce == 0) {
+                        r = FB_DIV(r, dg);
+                        if (use_bias) r = FB_ADD(r, w.ld(ob2 + i));
+                    } else if (use_bias) {
+                        r = FB_FMA(dg, w.ld(ob2 + i), r);
+                    }
+                    red[i] = (e1 > e0) ? r : 0.0f;
+                }
+            } else {
+                for (int e = e0; e < e1; e++) {
+                    const int c = S.vn_cn[e];
+                    const float lg = logit(c, b);
+                    const float hc = synd(c, b) ? -lg : lg;
+                    float acc[M];
+#pragma unroll
+                    for (int i = 0; i < M; i++) acc[i] = 0.0f;
+#pragma unroll 2
+                    for (int j = 0; j < H; j++) {
+                        const float base = FB_FMA(f3, w.ld(oW1 + 3 * H + j),
+                                                  FB_FMA(f2, w.ld(oW1 + 2 * H + j), FB_FMA(f1, w.ld(oW1 + H + j), 0.0f)));
+                        float t = FB_FMA(hc, w.ld(oW1 + j), base);
+                        if (use_bias) t = FB_ADD(t, w.ld(ob1 + j));
+                        const float hv = gnn_act<MATH>(act, t);
+#pragma unroll
+                        for (int i = 0; i < M; i += 4) {
+                            const float4 wv = w.ld4(oW2 + j * M + i);
+                            acc[i + 0] = FB_FMA(hv, wv.x, acc[i + 0]);
+                            acc[i + 1] = FB_FMA(hv, wv.y, acc[i + 1]);
+                            acc[i + 2] = FB_FMA(hv, wv.z, acc[i + 2]);
+                            acc[i + 3] = FB_FMA(hv, wv.w, acc[i + 3]);
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < M; i++) {
-                        const float mval = use_bias ? FB_ADD(acc[k][i], w.ld(ob2 + i)) : acc[k][i];
-                        if (first) red[i] = (a.reduce <= 1) ? FB_ADD(0.0f, mval) : mval;
-                        else if (a.reduce <= 1) red[i] = FB_ADD(red[i], mval);
+                        const float mval = use_bias ? FB_ADD(acc[i], w.ld(ob2 + i)) : acc[i];
+                        if (e == e0) red[i] = mval;
                         else if (a.reduce == 2) red[i] = (mval > red[i]) ? mval : red[i];
                         else red[i] = (mval < red[i]) ? mval : red[i];
                     }
                 }
-            }
-            if (a.reduce == 0 && e1 > e0) {
-                const float dg = (float)(e1 - e0);
-#pragma unroll
-                for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], dg);
             }
 #pragma unroll
             for (int i = 0; i < M; i++) {
@@ -795,12 +835,12 @@ __device__ __forceinline__ void gnn_body(const GnnArgs &a, const WSRC w) {
     }
 }
 
-template <int H, int M, int DV, bool TANH_BIAS, typename MATH>
+template <int H, int M, int DV, bool TANH_BIAS, bool FACT, typename MATH>
 __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
     extern __shared__ float wsm[];
     for (int i = threadIdx.x; i < GnnLayout<H, M>::total; i += blockDim.x) wsm[i] = a.weights[i];
     __syncthreads();
-    gnn_body<H, M, DV, TANH_BIAS, MATH, WSmem>(a, WSmem{wsm});
+    gnn_body<H, M, DV, TANH_BIAS, FACT, MATH, WSmem>(a, WSmem{wsm});
 }
 
 // ------------------------------------------------------------------ GNN_BP4 -----------

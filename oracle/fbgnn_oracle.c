@@ -491,23 +491,53 @@ static float gnn_act(int act, float x) {
     return x;
 }
 
-/* messages of one side into one variable node, reduced (feedback_gnn.py:175-184) */
+/* hidden layer of the edge MLP for edge e of variable v: features [h_cn[c], Lx, Ly, Lz]
+ * (feedback_gnn.py:175-178); the three per-variable terms are accumulated first, the check-node
+ * term last */
+static float gnn_hidden(const orc_gnn_t *G, const float *W1, const float *b1, float hc, const float f3[3], int j) {
+    const int H = G->H;
+    float a = 0.0f;
+    for (int k = 0; k < 3; k++) a = FB_FMA(f3[k], W1[(k + 1) * H + j], a);
+    a = FB_FMA(hc, W1[j], a);
+    if (b1) a = FB_ADD(a, b1[j]);
+    return gnn_act(G->act, a);
+}
+
+/* messages of one side into one variable node, reduced (feedback_gnn.py:175-184).
+ * reduce_op "mean" / "sum": the output layer of the edge MLP is linear, so it is applied ONCE to the
+ * sum of the hidden activations over the node's edges --
+ *     sum_e (W2^T t_e + b2) = W2^T (sum_e t_e) + deg * b2        (mean: divided by deg) --
+ * which is the reference's value up to float32 re-association (np_oracle.py keeps the literal
+ * per-edge form; tests/test_oracle.py bounds the difference).  "max" / "min" keep the per-edge form. */
 static void gnn_side(const orc_side_t *S, const orc_gnn_t *G, const float *W1, const float *b1,
                      const float *W2, const float *b2, const float *h_cn, int v,
                      const float f3[3], float *red, float *hid, float *msg) {
     const int H = G->H, M = G->M;
     const int e0 = S->vn_ptr[v], e1 = S->vn_ptr[v + 1];
-    for (int e = e0; e < e1; e++) {
-        /* features [h_cn[c], Lx, Ly, Lz] (feedback_gnn.py:175-178); the three per-variable terms
-         * are accumulated first, the check-node term last */
-        const float hc = h_cn[S->vn_cn[e]];
+    if (e1 == e0) { for (int i = 0; i < M; i++) red[i] = 0.0f; return; }
+    if (G->reduce <= 1) {
+        const float deg = (float)(e1 - e0);
         for (int j = 0; j < H; j++) {
-            float a = 0.0f;
-            for (int k = 0; k < 3; k++) a = FB_FMA(f3[k], W1[(k + 1) * H + j], a);
-            a = FB_FMA(hc, W1[j], a);
-            if (b1) a = FB_ADD(a, b1[j]);
-            hid[j] = gnn_act(G->act, a);
+            float hs = gnn_hidden(G, W1, b1, h_cn[S->vn_cn[e0]], f3, j);
+            for (int e = e0 + 1; e < e1; e++) hs = FB_ADD(hs, gnn_hidden(G, W1, b1, h_cn[S->vn_cn[e]], f3, j));
+            hid[j] = hs;
         }
+        for (int i = 0; i < M; i++) {
+            float a = 0.0f;
+            for (int j = 0; j < H; j++) a = FB_FMA(hid[j], W2[j * M + i], a);
+            if (G->reduce == 0) {
+                a = FB_DIV(a, deg);
+                if (b2) a = FB_ADD(a, b2[i]);
+            } else if (b2) {
+                a = FB_FMA(deg, b2[i], a);
+            }
+            red[i] = a;
+        }
+        return;
+    }
+    for (int e = e0; e < e1; e++) {
+        const float hc = h_cn[S->vn_cn[e]];
+        for (int j = 0; j < H; j++) hid[j] = gnn_hidden(G, W1, b1, hc, f3, j);
         for (int i = 0; i < M; i++) {
             float a = 0.0f;
             for (int j = 0; j < H; j++) a = FB_FMA(hid[j], W2[j * M + i], a);
@@ -515,15 +545,11 @@ static void gnn_side(const orc_side_t *S, const orc_gnn_t *G, const float *W1, c
             msg[i] = a;
         }
         for (int i = 0; i < M; i++) {
-            if (e == e0) red[i] = (G->reduce <= 1) ? FB_ADD(0.0f, msg[i]) : msg[i];
-            else if (G->reduce <= 1) red[i] = FB_ADD(red[i], msg[i]);
+            if (e == e0) red[i] = msg[i];
             else if (G->reduce == 2) red[i] = (msg[i] > red[i]) ? msg[i] : red[i];
             else red[i] = (msg[i] < red[i]) ? msg[i] : red[i];
         }
     }
-    if (e1 == e0) for (int i = 0; i < M; i++) red[i] = 0.0f;
-    if (G->reduce == 0 && e1 > e0)
-        for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], (float)(e1 - e0));
 }
 
 /* One frame of Feedback_GNN.call.  logit_hx [m_x] pairs with hx rows, logit_hz [m_z] with hz
