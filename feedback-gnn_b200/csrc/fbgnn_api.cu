@@ -883,18 +883,40 @@ static int gbp_run(fbgnn_code *code, fbgnn_gbp *g, int32_t num_iter, int64_t B, 
     fbgnn_ctx *ctx = code->ctx;
     cudaStream_t st = ctx->stream;
     const int n = a.X.n, mt = a.X.m + a.Z.m;
-    const size_t smem_cn = sizeof(float) * (GL::cn_total + 40 * 128), smem_vn = sizeof(float) * (GL::vn_total + 40 * 128);
-    if (int rc = set_smem(k_gbp_cn<20, 40, 20, MATH>, smem_cn, ctx, "GNN_BP4 CN update")) return rc;
-    if (int rc = set_smem(k_gbp_vn<20, 40, 20, MATH>, smem_vn, ctx, "GNN_BP4 VN update")) return rc;
+    const bool fact = g->reduce <= 1;        // mean / sum: factored edge MLPs (sender halves in a.pfc / a.pfv)
+    const size_t smem_pre = sizeof(float) * 2 * 40 * 20;
+    const size_t smem_cn = fact ? sizeof(float) * GL::cn_total + smem_pre : sizeof(float) * (GL::cn_total + 40 * 128);
+    const size_t smem_vn = fact ? sizeof(float) * GL::vn_total + smem_pre : sizeof(float) * (GL::vn_total + 40 * 128);
+    const bool tb = g->act == FBGNN_ACT_TANH && g->use_bias;
+    if (fact) {
+        if (int rc = set_smem(k_gbp_cn_f<20, 40, 20, true, MATH>, smem_cn, ctx, "GNN_BP4 CN update")) return rc;
+        if (int rc = set_smem(k_gbp_vn_f<20, 40, 20, true, MATH>, smem_vn, ctx, "GNN_BP4 VN update")) return rc;
+        if (int rc = set_smem(k_gbp_cn_f<20, 40, 20, false, MATH>, smem_cn, ctx, "GNN_BP4 CN update")) return rc;
+        if (int rc = set_smem(k_gbp_vn_f<20, 40, 20, false, MATH>, smem_vn, ctx, "GNN_BP4 VN update")) return rc;
+    } else {
+        if (int rc = set_smem(k_gbp_cn<20, 40, 20, MATH>, smem_cn, ctx, "GNN_BP4 CN update")) return rc;
+        if (int rc = set_smem(k_gbp_vn<20, 40, 20, MATH>, smem_vn, ctx, "GNN_BP4 VN update")) return rc;
+    }
     const unsigned g_cn = (unsigned)std::min<int64_t>((B * mt + 127) / 128, (int64_t)ctx->num_sms * 8);
     const unsigned g_vn = (unsigned)std::min<int64_t>((B * n + 127) / 128, (int64_t)ctx->num_sms * 8);
     const size_t smem_lg = sizeof(float) * 2 * n + n + 16;
+    auto cn_update = [&]() {
+        if (fact && tb) k_gbp_cn_f<20, 40, 20, true, MATH><<<g_cn, 128, smem_cn, st>>>(a);
+        else if (fact) k_gbp_cn_f<20, 40, 20, false, MATH><<<g_cn, 128, smem_cn, st>>>(a);
+        else k_gbp_cn<20, 40, 20, MATH><<<g_cn, 128, smem_cn, st>>>(a);
+        ctx->launches++;
+    };
+    if (fact) {
+        k_gbp_pre_vn<20, 40, 20><<<g_vn, 128, smem_pre, st>>>(a);
+        ctx->launches++;
+    }
     a.zero_logits = 1;
-    k_gbp_cn<20, 40, 20, MATH><<<g_cn, 128, smem_cn, st>>>(a);
-    ctx->launches++;
+    cn_update();
     a.zero_logits = 0;
     for (int it = 0; it < num_iter; it++) {
-        k_gbp_vn<20, 40, 20, MATH><<<g_vn, 128, smem_vn, st>>>(a);
+        if (fact && tb) k_gbp_vn_f<20, 40, 20, true, MATH><<<g_vn, 128, smem_vn, st>>>(a);
+        else if (fact) k_gbp_vn_f<20, 40, 20, false, MATH><<<g_vn, 128, smem_vn, st>>>(a);
+        else k_gbp_vn<20, 40, 20, MATH><<<g_vn, 128, smem_vn, st>>>(a);
         GbpArgs la = a;
         if (x_logit.ptr) la.x_logit = View2<float>{(float *)x_logit.ptr + it * x_logit.s0, x_logit.s1, x_logit.s2};
         if (z_logit.ptr) la.z_logit = View2<float>{(float *)z_logit.ptr + it * z_logit.s0, z_logit.s1, z_logit.s2};
@@ -902,8 +924,7 @@ static int gbp_run(fbgnn_code *code, fbgnn_gbp *g, int32_t num_iter, int64_t B, 
         k_gbp_logit<20, MATH><<<(unsigned)B, 256, smem_lg, st>>>(la);
         ctx->launches += 2;
         if (it == num_iter - 1) break;
-        k_gbp_cn<20, 40, 20, MATH><<<g_cn, 128, smem_cn, st>>>(a);
-        ctx->launches++;
+        cn_update();
     }
     CK(cudaGetLastError());
     return 0;
@@ -920,27 +941,47 @@ extern "C" int fbgnn_gbp_decode(fbgnn_code *code, fbgnn_gbp *g, int32_t num_iter
     if (set_device(ctx)) return FBGNN_E_CUDA;
     if (B == 0) return 0;
     const SideDev &X = code->X->dev, &Z = code->Z->dev;
-    const int n = X.n, D = 20;
-    float *h_vn = nullptr, *hcx = nullptr, *hcz = nullptr, *lg = nullptr;
+    const int n = X.n, D = 20, H = 40, mt = std::max(X.m + Z.m, 1);
+    const bool fact = g->reduce <= 1;
+    // The embeddings (and, factored, the sender halves) of a frame take (n + m) (D + H) floats + n H floats of
+    // HBM: the batch is walked in chunks that keep this state to a few GB.
+    const int64_t per_frame = sizeof(float) * ((int64_t)(n + mt) * D + (fact ? (int64_t)(mt + 2 * n) * H : 0) + mt);
+    const int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(B, ((int64_t)6 << 30) / per_frame));
+    float *h_vn = nullptr, *hcx = nullptr, *hcz = nullptr, *lg = nullptr, *pfc = nullptr, *pfv = nullptr;
     cudaStream_t st = ctx->stream;
-    CK(cudaMallocAsync(&h_vn, sizeof(float) * B * n * D, st));
-    CK(cudaMallocAsync(&hcx, sizeof(float) * B * std::max(X.m, 1) * D, st));
-    CK(cudaMallocAsync(&hcz, sizeof(float) * B * std::max(Z.m, 1) * D, st));
-    CK(cudaMallocAsync(&lg, sizeof(float) * B * std::max(X.m + Z.m, 1), st));
-    k_fill<<<ctx->num_sms * 4, 256, 0, st>>>((uint32_t *)h_vn, B * n * D, 0x3f800000u);      // h_vn = 1 (gnn.py:394)
-    CK(cudaMemsetAsync(hcx, 0, sizeof(float) * B * X.m * D, st));                              // h_cn = 0 (392-393)
-    CK(cudaMemsetAsync(hcz, 0, sizeof(float) * B * Z.m * D, st));
-    ctx->launches++;
-    GbpArgs a{};
-    a.X = X; a.Z = Z; a.w_cn = g->w_cn; a.w_vn = g->w_vn; a.w_inv = g->w_inv;
-    a.act = g->act; a.reduce = g->reduce; a.use_bias = g->use_bias; a.B = B;
-    a.h_vn = h_vn; a.hcx = hcx; a.hcz = hcz; a.lg = lg;
-    a.sx = (const uint8_t *)synd_x.ptr; a.sz = (const uint8_t *)synd_z.ptr;
-    a.lx_ptr = code->lx_ptr; a.lz_ptr = code->lz_ptr; a.lx_col = code->lx_col; a.lz_col = code->lz_col;
-    a.kx = code->kx; a.kz = code->kz;
-    int rc = ctx->math_mode == FBGNN_MATH_FAST ? gbp_run<MathFast>(code, g, num_iter, B, a, x_logit, z_logit, x_hat, z_hat)
-                                               : gbp_run<MathExact>(code, g, num_iter, B, a, x_logit, z_logit, x_hat, z_hat);
+    CK(cudaMallocAsync(&h_vn, sizeof(float) * chunk * n * D, st));
+    CK(cudaMallocAsync(&hcx, sizeof(float) * chunk * std::max(X.m, 1) * D, st));
+    CK(cudaMallocAsync(&hcz, sizeof(float) * chunk * std::max(Z.m, 1) * D, st));
+    CK(cudaMallocAsync(&lg, sizeof(float) * chunk * mt, st));
+    if (fact) {
+        CK(cudaMallocAsync(&pfc, sizeof(float) * chunk * mt * H, st));
+        CK(cudaMallocAsync(&pfv, sizeof(float) * chunk * n * 2 * H, st));
+    }
+    int rc = 0;
+    for (int64_t b0 = 0; b0 < B && rc == 0; b0 += chunk) {
+        const int64_t nb = std::min(chunk, B - b0);
+        k_fill<<<ctx->num_sms * 4, 256, 0, st>>>((uint32_t *)h_vn, nb * n * D, 0x3f800000u);   // h_vn = 1 (gnn.py:394)
+        CK(cudaMemsetAsync(hcx, 0, sizeof(float) * nb * X.m * D, st));                          // h_cn = 0 (392-393)
+        CK(cudaMemsetAsync(hcz, 0, sizeof(float) * nb * Z.m * D, st));
+        ctx->launches++;
+        GbpArgs a{};
+        a.X = X; a.Z = Z; a.w_cn = g->w_cn; a.w_vn = g->w_vn; a.w_inv = g->w_inv;
+        a.act = g->act; a.reduce = g->reduce; a.use_bias = g->use_bias; a.B = nb;
+        a.h_vn = h_vn; a.hcx = hcx; a.hcz = hcz; a.lg = lg; a.pfc = pfc; a.pfv = pfv;
+        a.sx = (const uint8_t *)synd_x.ptr + b0 * synd_x.s0; a.sz = (const uint8_t *)synd_z.ptr + b0 * synd_z.s0;
+        a.lx_ptr = code->lx_ptr; a.lz_ptr = code->lz_ptr; a.lx_col = code->lx_col; a.lz_col = code->lz_col;
+        a.kx = code->kx; a.kz = code->kz;
+        fbgnn_tensor3 xl = x_logit, zl = z_logit;               // (iteration, row, frame)
+        fbgnn_tensor2 xh = x_hat, zh = z_hat;                   // (qubit, frame)
+        if (xl.ptr) xl.ptr = (float *)xl.ptr + b0 * xl.s2;
+        if (zl.ptr) zl.ptr = (float *)zl.ptr + b0 * zl.s2;
+        xh.ptr = (uint8_t *)xh.ptr + b0 * xh.s1;
+        zh.ptr = (uint8_t *)zh.ptr + b0 * zh.s1;
+        rc = ctx->math_mode == FBGNN_MATH_FAST ? gbp_run<MathFast>(code, g, num_iter, nb, a, xl, zl, xh, zh)
+                                               : gbp_run<MathExact>(code, g, num_iter, nb, a, xl, zl, xh, zh);
+    }
     CK(cudaFreeAsync(h_vn, st)); CK(cudaFreeAsync(hcx, st)); CK(cudaFreeAsync(hcz, st)); CK(cudaFreeAsync(lg, st));
+    if (fact) { CK(cudaFreeAsync(pfc, st)); CK(cudaFreeAsync(pfv, st)); }
     return rc;
 }
 

@@ -871,6 +871,10 @@ struct GbpArgs {
     int64_t B;
     float *h_vn, *hcx, *hcz;            // [B][n][D], [B][m_x][D], [B][m_z][D]
     float *lg;                          // [B][m_x + m_z]: hx_logit, hz_logit of the last cal_logit
+    // factored form (reduce mean / sum): sender halves of the first edge layer, written by the kernel that
+    // produces the sender's embedding and read once per edge by the receiving side
+    float *pfc;                         // [B][m_x + m_z][H]: W1[:D]^T h_cn with update_h_vn's msg_mlp_{x,z}
+    float *pfv;                         // [B][n][2][H]:      W1[:D]^T h_vn with update_h_cn's msg_mlp_{x,z}
     const uint8_t *sx, *sz;             // [B][m_x], [B][m_z] (batch first, gnn.py:385-386)
     int zero_logits;                    // first CN update: logits are zero
     // cal_logit outputs (optional) and logical rows
@@ -1097,6 +1101,252 @@ __global__ void __launch_bounds__(128) k_gbp_vn(const GbpArgs a) {
         gbp_node<D, H, M, L::KV, MATH>(w + 2 * L::edge, in, a.act, use_bias, out);
 #pragma unroll
         for (int k = 0; k < D; k += 4) *reinterpret_cast<float4 *>(hv + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+    }
+}
+
+// ---- factored form for reduce_op "mean" / "sum" (arithmetic: oracle gbp_from / gbp_hidden_acc / gbp_out_layer)
+// The first edge layer is linear in [h_from, h_to]: its sender half Pf = W1[:D]^T h_from is formed ONCE per
+// sender node (by the kernel that writes that node's embedding), its receiver half once per receiver, and an
+// edge only adds the two.  The output layer is linear too and is applied once per receiver to the signed sum
+// of hidden activations.  Per edge that leaves H additions and H activations instead of 2 H (D + M) FMAs.
+
+// Pf[j] = sum_k h[k] W1T[j][k]  (k < D), written as H floats
+template <int D, int H>
+__device__ __forceinline__ void gbp_sender_half(const float *__restrict__ w1t, const float h[D], float *__restrict__ dst) {
+#pragma unroll 1
+    for (int j = 0; j < H; j += 4) {
+        float p[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            float acc = 0.0f;
+            const float *w1 = w1t + (j + q) * D;
+#pragma unroll
+            for (int k = 0; k < D; k += 4) {
+                const float4 wv = *reinterpret_cast<const float4 *>(w1 + k);
+                acc = FB_FMA(h[k + 0], wv.x, acc); acc = FB_FMA(h[k + 1], wv.y, acc);
+                acc = FB_FMA(h[k + 2], wv.z, acc); acc = FB_FMA(h[k + 3], wv.w, acc);
+            }
+            p[q] = acc;
+        }
+        *reinterpret_cast<float4 *>(dst + j) = make_float4(p[0], p[1], p[2], p[3]);
+    }
+}
+
+// Messages into one receiver over edges [e0, e1): SENDER(e, neg) gives the sender's row number in `rows`
+// (row_stride floats apart) and whether the message is negated.  red[M] receives the reduced message.
+// Hidden units are walked eight at a time (one 32-byte sector of every sender row per step).  Loads run ahead
+// of their use without unrolling the edge loop (its body stays inside the instruction cache): the row of edge
+// e+1 and the sender number of edge e+2 are requested before edge e is evaluated, and the first row of the
+// next step before the output-layer products of this one.
+template <int D, int H, int M, typename MATH, typename SENDER>
+__device__ __forceinline__ void gbp_recv_factored(const float *__restrict__ w, const float own[D], int e0, int e1, int act,
+                                                  bool use_bias, int reduce, const float *__restrict__ rows, int row_stride,
+                                                  SENDER sender, float red[M]) {
+    typedef GbpLayout<D, H, M> L;
+    constexpr int JB = 8;
+    static_assert(H % JB == 0, "H must be a multiple of 8");
+#pragma unroll
+    for (int i = 0; i < M; i++) red[i] = 0.0f;
+    int ssum = 0, i0 = 0, i1 = 0;
+    bool g0 = false, g1 = false;
+    float4 nx0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), nx1 = nx0;
+    if (e0 < e1) {
+        i0 = sender(e0, g0);
+        const float *pf = rows + (int64_t)i0 * row_stride;
+        nx0 = *reinterpret_cast<const float4 *>(pf); nx1 = *reinterpret_cast<const float4 *>(pf + 4);
+    }
+    if (e0 + 1 < e1) i1 = sender(e0 + 1, g1);
+#pragma unroll 1
+    for (int j = 0; j < H; j += JB) {
+        float bs[JB], hs[JB], b1[JB];
+#pragma unroll
+        for (int q = 0; q < JB; q++) {          // receiver half of the first layer (oracle gbp_base)
+            float acc = 0.0f;
+            const float *w1 = w + (j + q) * 2 * D + D;
+#pragma unroll
+            for (int k = 0; k < D; k += 4) {
+                const float4 wv = *reinterpret_cast<const float4 *>(w1 + k);
+                acc = FB_FMA(own[k + 0], wv.x, acc); acc = FB_FMA(own[k + 1], wv.y, acc);
+                acc = FB_FMA(own[k + 2], wv.z, acc); acc = FB_FMA(own[k + 3], wv.w, acc);
+            }
+            bs[q] = acc;
+            hs[q] = 0.0f;
+            b1[q] = use_bias ? w[L::e_b1 + j + q] : 0.0f;
+        }
+        int ni = i1;
+        bool ng = g1, cg = g0;
+#pragma unroll 1
+        for (int e = e0; e < e1; e++) {
+            const float pq[JB] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
+            const bool neg = cg;
+            if (e + 1 < e1) {
+                const float *pf = rows + (int64_t)ni * row_stride + j;
+                nx0 = *reinterpret_cast<const float4 *>(pf); nx1 = *reinterpret_cast<const float4 *>(pf + 4);
+                cg = ng;
+                if (e + 2 < e1) ni = sender(e + 2, ng);
+            }
+            if (j == 0) ssum += neg ? -1 : 1;
+#pragma unroll
+            for (int q = 0; q < JB; q++) {
+                float t = FB_ADD(pq[q], bs[q]);
+                if (use_bias) t = FB_ADD(t, b1[q]);
+                t = gbp_act<MATH>(act, t);
+                if (neg) t = -t;
+                hs[q] = (e == e0) ? t : FB_ADD(hs[q], t);
+            }
+        }
+        if (j + JB < H && e0 < e1) {
+            const float *pf = rows + (int64_t)i0 * row_stride + j + JB;
+            nx0 = *reinterpret_cast<const float4 *>(pf); nx1 = *reinterpret_cast<const float4 *>(pf + 4);
+        }
+#pragma unroll
+        for (int q = 0; q < JB; q++) {
+            const float *w2 = w + L::e_W2 + (j + q) * M;
+#pragma unroll
+            for (int i = 0; i < M; i += 4) {
+                const float4 wv = *reinterpret_cast<const float4 *>(w2 + i);
+                red[i + 0] = FB_FMA(hs[q], wv.x, red[i + 0]); red[i + 1] = FB_FMA(hs[q], wv.y, red[i + 1]);
+                red[i + 2] = FB_FMA(hs[q], wv.z, red[i + 2]); red[i + 3] = FB_FMA(hs[q], wv.w, red[i + 3]);
+            }
+        }
+    }
+    const float fs = (float)ssum, dg = (float)(e1 - e0);
+#pragma unroll
+    for (int i = 0; i < M; i++) {
+        float r = red[i];
+        if (use_bias) r = FB_FMA(fs, w[L::e_b2 + i], r);
+        if (reduce == 0 && e1 > e0) r = FB_DIV(r, dg);
+        red[i] = r;
+    }
+}
+
+// initial sender halves of the variable nodes (h_vn as stored), before the first CN update
+template <int D, int H, int M>
+__global__ void __launch_bounds__(128) k_gbp_pre_vn(const GbpArgs a) {
+    typedef GbpLayout<D, H, M> L;
+    extern __shared__ float gsm[];
+    float *wp = gsm;                                                   // [2][H][D]
+    for (int i = threadIdx.x; i < 2 * H * D; i += blockDim.x) {
+        const int side = i / (H * D), r = i - side * H * D, j = r / D, k = r - j * D;
+        wp[i] = a.w_cn[side * L::edge + j * 2 * D + k];
+    }
+    __syncthreads();
+    const int n = a.X.n;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.B * n; it += (int64_t)gridDim.x * blockDim.x) {
+        float own[D];
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+            const float4 v4 = *reinterpret_cast<const float4 *>(a.h_vn + it * D + k);
+            own[k] = v4.x; own[k + 1] = v4.y; own[k + 2] = v4.z; own[k + 3] = v4.w;
+        }
+        gbp_sender_half<D, H>(wp, own, a.pfv + it * 2 * H);
+        gbp_sender_half<D, H>(wp + H * D, own, a.pfv + it * 2 * H + H);
+    }
+}
+
+// UpdateCNEmbeddings.call, factored; also writes the new check embedding's sender half for the VN update.
+// smem: weights[cn_total] + sender-half weights of update_h_vn's msg_mlp_{x,z} [2][H][D]
+template <int D, int H, int M, bool TB, typename MATH>
+__global__ void __launch_bounds__(128, 4) k_gbp_cn_f(const GbpArgs a) {
+    typedef GbpLayout<D, H, M> L;
+    extern __shared__ float gsm[];
+    float *w = gsm, *wp = gsm + L::cn_total;
+    for (int i = threadIdx.x; i < L::cn_total; i += blockDim.x) w[i] = a.w_cn[i];
+    for (int i = threadIdx.x; i < 2 * H * D; i += blockDim.x) {
+        const int side = i / (H * D), r = i - side * H * D, j = r / D, k = r - j * D;
+        wp[i] = a.w_vn[side * L::edge + j * 2 * D + k];
+    }
+    __syncthreads();
+    const int mt = a.X.m + a.Z.m, n = a.X.n;
+    // TB: compile-time specialisation of tanh + use_bias=True (BASELINE configs[4]); keeps one copy of the loops
+    const bool use_bias = TB ? true : (a.use_bias != 0);
+    const int act = TB ? 0 : a.act;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.B * mt; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = it / mt;
+        const int c = (int)(it - b * mt);
+        const bool isx = c < a.X.m;
+        const SideDev &S = isx ? a.X : a.Z;
+        const int cc = isx ? c : c - a.X.m;
+        const float *we = w + (isx ? 0 : L::edge), *wn = w + 2 * L::edge + (isx ? 0 : L::node(L::KC));
+        float *hc = (isx ? a.hcx + (b * a.X.m + cc) * D : a.hcz + (b * a.Z.m + cc) * D);
+        float in[L::KC], own[D];
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+            const float4 v4 = *reinterpret_cast<const float4 *>(hc + k);
+            own[k] = v4.x; own[k + 1] = v4.y; own[k + 2] = v4.z; own[k + 3] = v4.w;
+        }
+        const float *pf_b = a.pfv + b * n * 2 * H + (isx ? 0 : H);
+        const idx_t *cn_vn = S.cn_vn;
+        float red[M];
+        gbp_recv_factored<D, H, M, MATH>(we, own, S.cn_ptr[cc], S.cn_ptr[cc + 1], act, use_bias, a.reduce, pf_b, 2 * H,
+            [&](int e, bool &neg) { neg = false; return (int)cn_vn[e]; }, red);
+#pragma unroll
+        for (int i = 0; i < M; i++) in[i] = red[i];
+#pragma unroll
+        for (int i = 0; i < D; i++) in[M + i] = own[i];
+        float lgv = 0.0f;
+        if (!a.zero_logits) {
+            lgv = a.lg[b * mt + c];
+            if ((isx ? a.sx[b * a.X.m + cc] : a.sz[b * a.Z.m + cc])) lgv = -lgv;      // logit * (1 - 2 s)
+        }
+        in[M + D] = lgv;
+        float out[D];
+        gbp_node<D, H, M, L::KC, MATH>(wn, in, act, use_bias, out);
+#pragma unroll
+        for (int k = 0; k < D; k += 4) *reinterpret_cast<float4 *>(hc + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+        gbp_sender_half<D, H>(wp + (isx ? 0 : H * D), out, a.pfc + it * H);
+    }
+}
+
+// UpdateVNEmbeddings.call, factored; also writes the new variable embedding's sender halves for the CN update.
+template <int D, int H, int M, bool TB, typename MATH>
+__global__ void __launch_bounds__(128) k_gbp_vn_f(const GbpArgs a) {
+    typedef GbpLayout<D, H, M> L;
+    extern __shared__ float gsm[];
+    float *w = gsm, *wp = gsm + L::vn_total;
+    for (int i = threadIdx.x; i < L::vn_total; i += blockDim.x) w[i] = a.w_vn[i];
+    for (int i = threadIdx.x; i < 2 * H * D; i += blockDim.x) {
+        const int side = i / (H * D), r = i - side * H * D, j = r / D, k = r - j * D;
+        wp[i] = a.w_cn[side * L::edge + j * 2 * D + k];
+    }
+    __syncthreads();
+    const int n = a.X.n, mt = a.X.m + a.Z.m;
+    // TB: compile-time specialisation of tanh + use_bias=True (BASELINE configs[4]); keeps one copy of the loops
+    const bool use_bias = TB ? true : (a.use_bias != 0);
+    const int act = TB ? 0 : a.act;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < a.B * n; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = it / n;
+        const int v = (int)(it - b * n);
+        float *hv = a.h_vn + it * D;
+        float in[L::KV], own[D];
+#pragma unroll
+        for (int k = 0; k < D; k += 4) {
+            const float4 v4 = *reinterpret_cast<const float4 *>(hv + k);
+            own[k] = v4.x; own[k + 1] = v4.y; own[k + 2] = v4.z; own[k + 3] = v4.w;
+        }
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            const SideDev &S = side ? a.Z : a.X;
+            const float *pf_b = a.pfc + (b * mt + (side ? a.X.m : 0)) * H;
+            const uint8_t *sy = side ? a.sz + b * a.Z.m : a.sx + b * a.X.m;
+            const idx_t *vn_cn = S.vn_cn;
+            float red[M];
+            gbp_recv_factored<D, H, M, MATH>(w + (side ? L::edge : 0), own, S.vn_ptr[v], S.vn_ptr[v + 1], act, use_bias,
+                a.reduce, pf_b, H, [&](int e, bool &neg) { const int c = vn_cn[e]; neg = sy[c] != 0; return c; }, red);
+#pragma unroll
+            for (int i = 0; i < M; i++) {
+                if (side == 0) in[i] = red[i];
+                else in[M + i] = red[i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < D; i++) in[2 * M + i] = own[i];
+        float out[D];
+        gbp_node<D, H, M, L::KV, MATH>(w + 2 * L::edge, in, act, use_bias, out);
+#pragma unroll
+        for (int k = 0; k < D; k += 4) *reinterpret_cast<float4 *>(hv + k) = make_float4(out[k], out[k + 1], out[k + 2], out[k + 3]);
+        gbp_sender_half<D, H>(wp, out, a.pfv + it * 2 * H);
+        gbp_sender_half<D, H>(wp + H * D, out, a.pfv + it * 2 * H + H);
     }
 }
 

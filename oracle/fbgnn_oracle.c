@@ -934,10 +934,49 @@ static void gbp_node_mlp(const orc_gbp_t *G, const float *const w[4], const floa
 
 static void gbp_reduce(const orc_gbp_t *G, float *red, const float *msg, int first, int M) {
     for (int i = 0; i < M; i++) {
-        if (first) red[i] = (G->reduce <= 1) ? FB_ADD(0.0f, msg[i]) : msg[i];
-        else if (G->reduce <= 1) red[i] = FB_ADD(red[i], msg[i]);
+        if (first) red[i] = msg[i];
         else if (G->reduce == 2) red[i] = (msg[i] > red[i]) ? msg[i] : red[i];
         else red[i] = (msg[i] < red[i]) ? msg[i] : red[i];
+    }
+}
+
+/* reduce_op "mean" / "sum": both layers of the edge MLP are applied in factored form.  The first layer is
+ * linear in [h_from, h_to], so its two halves are formed per NODE (sender half Pf = W1[:d]^T h_from,
+ * receiver half base = W1[d:]^T h_to) and only added per edge; the output layer is linear, so it is applied
+ * once to the signed sum of the hidden activations over the receiver's edges:
+ *     sum_e s_e (W2^T t_e + b2) = W2^T (sum_e s_e t_e) + (sum_e s_e) b2        (mean: divided by deg).
+ * Same value as the reference's per-edge Dense layers up to float32 re-association (np_oracle.py keeps the
+ * literal form; tests/test_gnn_bp4.py bounds the difference).  "max" / "min" use the per-edge form above. */
+static void gbp_from(const orc_gbp_t *G, const float *const w[4], const float *from, float *pf) {
+    const int d = G->d, H = G->H;
+    for (int j = 0; j < H; j++) {
+        float a = 0.0f;
+        for (int k = 0; k < d; k++) a = FB_FMA(from[k], w[0][k * H + j], a);
+        pf[j] = a;
+    }
+}
+
+/* hs[j] (+)= s * act(pf[j] + base[j] + b1[j]) */
+static void gbp_hidden_acc(const orc_gbp_t *G, const float *const w[4], const float *pf, const float *base, int negate,
+                           int first, float *hs) {
+    for (int j = 0; j < G->H; j++) {
+        float a = FB_ADD(pf[j], base[j]);
+        if (w[1]) a = FB_ADD(a, w[1][j]);
+        float t = gnn_act(G->act, a);
+        if (negate) t = -t;
+        hs[j] = first ? t : FB_ADD(hs[j], t);
+    }
+}
+
+/* red[i] = (sum_j hs[j] W2[j][i] + ssum b2[i]) (/ deg for "mean") */
+static void gbp_out_layer(const orc_gbp_t *G, const float *const w[4], const float *hs, float ssum, int deg, float *red) {
+    const int H = G->H, M = G->M;
+    for (int i = 0; i < M; i++) {
+        float a = 0.0f;
+        for (int j = 0; j < H; j++) a = FB_FMA(hs[j], w[2][j * M + i], a);
+        if (w[3]) a = FB_FMA(ssum, w[3][i], a);
+        if (G->reduce == 0 && deg > 0) a = FB_DIV(a, (float)deg);
+        red[i] = a;
     }
 }
 
@@ -945,16 +984,25 @@ static void gbp_reduce(const orc_gbp_t *G, float *red, const float *msg, int fir
 static void gbp_cn_update(const orc_gbp_t *G, const orc_side_t *S, const float *const wm[4], const float *const we[4],
                           const float *h_vn, float *h_cn, const float *logit, float *work) {
     const int d = G->d, H = G->H, M = G->M;
-    float *base = work, *hid = base + H, *msg = hid + H, *red = msg + M, *in = red + M, *out = in + M + d + 1;
+    float *base = work, *hid = base + H, *msg = hid + H, *red = msg + M, *in = red + M, *out = in + M + d + 1,
+          *pf = out + d, *hs = pf + H;
     for (int c = 0; c < S->m; c++) {
         gbp_base(G, wm, h_cn + c * d, base);
         const int k0 = S->cn_ptr[c], k1 = S->cn_ptr[c + 1];
         for (int i = 0; i < M; i++) red[i] = 0.0f;
-        for (int k = k0; k < k1; k++) {
-            gbp_edge_mlp(G, wm, h_vn + S->cn_vn[k] * d, base, hid, msg);
-            gbp_reduce(G, red, msg, k == k0, M);
+        if (G->reduce <= 1) {
+            for (int j = 0; j < H; j++) hs[j] = 0.0f;
+            for (int k = k0; k < k1; k++) {
+                gbp_from(G, wm, h_vn + S->cn_vn[k] * d, pf);
+                gbp_hidden_acc(G, wm, pf, base, 0, k == k0, hs);
+            }
+            gbp_out_layer(G, wm, hs, (float)(k1 - k0), k1 - k0, red);
+        } else {
+            for (int k = k0; k < k1; k++) {
+                gbp_edge_mlp(G, wm, h_vn + S->cn_vn[k] * d, base, hid, msg);
+                gbp_reduce(G, red, msg, k == k0, M);
+            }
         }
-        if (G->reduce == 0 && k1 > k0) for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], (float)(k1 - k0));
         for (int i = 0; i < M; i++) in[i] = red[i];
         for (int i = 0; i < d; i++) in[M + i] = h_cn[c * d + i];
         in[M + d] = logit[c];
@@ -967,7 +1015,7 @@ static void gbp_cn_update(const orc_gbp_t *G, const orc_side_t *S, const float *
 static void gbp_vn_update(const orc_gbp_t *G, const orc_side_t *X, const orc_side_t *Z, const float *hcx,
                           const float *hcz, float *h_vn, const uint8_t *sx, const uint8_t *sz, float *work) {
     const int d = G->d, H = G->H, M = G->M;
-    float *base = work, *hid = base + H, *msg = hid + H, *in = msg + M, *out = in + 2 * M + d;
+    float *base = work, *hid = base + H, *msg = hid + H, *in = msg + M, *out = in + 2 * M + d, *pf = out + d, *hs = pf + H;
     for (int v = 0; v < X->n; v++) {
         for (int side = 0; side < 2; side++) {
             const orc_side_t *S = side ? Z : X;
@@ -978,13 +1026,24 @@ static void gbp_vn_update(const orc_gbp_t *G, const orc_side_t *X, const orc_sid
             gbp_base(G, wm, h_vn + v * d, base);
             const int e0 = S->vn_ptr[v], e1 = S->vn_ptr[v + 1];
             for (int i = 0; i < M; i++) red[i] = 0.0f;
+            if (G->reduce <= 1) {
+                int ssum = 0;
+                for (int j = 0; j < H; j++) hs[j] = 0.0f;
+                for (int e = e0; e < e1; e++) {
+                    const int c = S->vn_cn[e];
+                    gbp_from(G, wm, hc + c * d, pf);
+                    gbp_hidden_acc(G, wm, pf, base, sy[c] != 0, e == e0, hs);    /* x (1 - 2 s), gnn.py:733-737 */
+                    ssum += sy[c] ? -1 : 1;
+                }
+                gbp_out_layer(G, wm, hs, (float)ssum, e1 - e0, red);
+                continue;
+            }
             for (int e = e0; e < e1; e++) {
                 const int c = S->vn_cn[e];
                 gbp_edge_mlp(G, wm, hc + c * d, base, hid, msg);
                 if (sy[c]) for (int i = 0; i < M; i++) msg[i] = -msg[i];          /* x (1 - 2 s), gnn.py:733-737 */
                 gbp_reduce(G, red, msg, e == e0, M);
             }
-            if (G->reduce == 0 && e1 > e0) for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], (float)(e1 - e0));
         }
         for (int i = 0; i < d; i++) in[2 * M + i] = h_vn[v * d + i];
         gbp_node_mlp(G, G->ve, in, 2 * M + d, hid, out);
@@ -1059,7 +1118,7 @@ void orc_gnn_bp4(const orc_gbp_t *G, const orc_side_t *X, const orc_side_t *Z, c
     const int n = X->n, d = G->d, rx = Z->m + lz->m, rz = X->m + lx->m;
 #pragma omp parallel
     {
-        const size_t fwn = (size_t)(n + X->m + Z->m) * d + X->m + Z->m + 5 * (size_t)n + 4 * (size_t)G->H +
+        const size_t fwn = (size_t)(n + X->m + Z->m) * d + X->m + Z->m + 5 * (size_t)n + 6 * (size_t)G->H +
                            6 * (size_t)G->M + 4 * (size_t)d + 64;
         float *fw = (float *)malloc(sizeof(float) * fwn);
         float *xl = (float *)malloc(sizeof(float) * (size_t)G->num_iter * rx + 4);
