@@ -12,6 +12,7 @@
 
 #include "../../include/fbgnn.h"
 #include "fbgnn_kernels.cuh"
+#include "fbgnn_gbp_tc.cuh"
 
 using namespace fbgnn;
 
@@ -813,7 +814,9 @@ extern "C" int fbgnn_osd0_decode(fbgnn_graph *basis, int64_t B, fbgnn_tensor2 ll
 struct fbgnn_gbp {
     fbgnn_ctx *ctx;
     int d, H, M, act, reduce, use_bias;
+    int gemm = FBGNN_GEMM_FMA;
     float *w_cn = nullptr, *w_vn = nullptr, *w_inv = nullptr;
+    float *w_vn_tc = nullptr, *w_cn_tc[2] = {nullptr, nullptr};     // tensor-core operand tiles (fbgnn_gbp_tc.cuh)
 };
 
 typedef GbpLayout<20, 40, 20> GL;
@@ -832,6 +835,8 @@ static void pack_node(std::vector<float> &w, int off, int K, const float *W1, co
     std::memcpy(&w[off + GL::n_W2(K)], W2, sizeof(float) * H * D);
     if (b2) std::memcpy(&w[off + GL::n_b2(K)], b2, sizeof(float) * D);
 }
+
+extern "C" int fbgnn_gbp_destroy(fbgnn_gbp *g);
 
 extern "C" int fbgnn_gbp_create(fbgnn_ctx *ctx, int32_t d, int32_t H, int32_t M, int32_t activation, int32_t reduce_op,
                                 const float *const *arrays, fbgnn_gbp **out) {
@@ -865,6 +870,50 @@ extern "C" int fbgnn_gbp_create(fbgnn_ctx *ctx, int32_t d, int32_t H, int32_t M,
         return 0;
     };
     if (up(wc, &g->w_cn) || up(wv, &g->w_vn) || up(wi, &g->w_inv)) { delete g; return FBGNN_E_CUDA; }
+    {   // tensor-core operand tiles: TF32 hi / lo parts in the canonical K-major UMMA layout
+        auto tile = [](std::vector<float> &buf, int off, int kpad, int npad, auto wf) {
+            for (int nn = 0; nn < npad; nn++)
+                for (int k = 0; k < kpad; k++) {
+                    const float w = wf(k, nn), hi = tc::tf32_hi(w);
+                    buf[off + tc::b_tile_offset(nn, k, kpad)] = hi;
+                    buf[off + kpad * npad + tc::b_tile_offset(nn, k, kpad)] = w - hi;
+                }
+        };
+        auto bias = [](std::vector<float> &buf, int off, const float *b, int cnt) {
+            for (int i = 0; i < cnt; i++) buf[off + i] = b ? b[i] : 0.0f;
+        };
+        using tc::VnW; using tc::CnW;
+        std::vector<float> tv(VnW::total, 0.0f);
+        for (int sd = 0; sd < 2; sd++) {
+            const float *W1 = p[16 + 4 * sd], *W2 = p[18 + 4 * sd];
+            tile(tv, sd ? VnW::B1Z : VnW::B1X, 24, 48, [&](int k, int nn) { return (k < 20 && nn < 40) ? W1[(20 + k) * 40 + nn] : 0.0f; });
+            tile(tv, sd ? VnW::W2Z : VnW::W2X, 40, 32, [&](int k, int nn) { return nn < 20 ? W2[k * 20 + nn] : 0.0f; });
+            bias(tv, VnW::BIAS + sd * 40, p[17 + 4 * sd], 40);
+            bias(tv, VnW::BIAS + 80 + sd * 20, p[19 + 4 * sd], 20);
+        }
+        tile(tv, VnW::W3AB, 40, 48, [&](int k, int nn) { return nn < 40 ? p[24][k * 40 + nn] : 0.0f; });
+        tile(tv, VnW::W3C, 24, 48, [&](int k, int nn) { return (k < 20 && nn < 40) ? p[24][(40 + k) * 40 + nn] : 0.0f; });
+        tile(tv, VnW::W4, 40, 32, [&](int k, int nn) { return nn < 20 ? p[26][k * 20 + nn] : 0.0f; });
+        tile(tv, VnW::W5, 24, 80, [&](int k, int nn) { return k < 20 ? (nn < 40 ? p[0][k * 40 + nn] : p[4][k * 40 + nn - 40]) : 0.0f; });
+        bias(tv, VnW::BIAS + 120, p[25], 40);
+        bias(tv, VnW::BIAS + 160, p[27], 20);
+        if (up(tv, &g->w_vn_tc)) { fbgnn_gbp_destroy(g); return FBGNN_E_CUDA; }
+        for (int sd = 0; sd < 2; sd++) {
+            std::vector<float> tcn(CnW::total, 0.0f);
+            const float *mW1 = p[4 * sd], *mW2 = p[2 + 4 * sd], *eW1 = p[8 + 4 * sd], *eW2 = p[10 + 4 * sd], *vW1 = p[16 + 4 * sd];
+            tile(tcn, CnW::B1, 24, 48, [&](int k, int nn) { return (k < 20 && nn < 40) ? mW1[(20 + k) * 40 + nn] : 0.0f; });
+            tile(tcn, CnW::W2, 40, 32, [&](int k, int nn) { return nn < 20 ? mW2[k * 20 + nn] : 0.0f; });
+            tile(tcn, CnW::W3A, 24, 48, [&](int k, int nn) { return nn >= 40 ? 0.0f : k < 20 ? eW1[k * 40 + nn] : k == 20 ? eW1[40 * 40 + nn] : 0.0f; });
+            tile(tcn, CnW::W3B, 24, 48, [&](int k, int nn) { return (k < 20 && nn < 40) ? eW1[(20 + k) * 40 + nn] : 0.0f; });
+            tile(tcn, CnW::W4, 40, 32, [&](int k, int nn) { return nn < 20 ? eW2[k * 20 + nn] : 0.0f; });
+            tile(tcn, CnW::W5, 24, 48, [&](int k, int nn) { return (k < 20 && nn < 40) ? vW1[k * 40 + nn] : 0.0f; });
+            bias(tcn, CnW::BIAS, p[1 + 4 * sd], 40);
+            bias(tcn, CnW::BIAS + 40, p[3 + 4 * sd], 20);
+            bias(tcn, CnW::BIAS + 60, p[9 + 4 * sd], 40);
+            bias(tcn, CnW::BIAS + 100, p[11 + 4 * sd], 20);
+            if (up(tcn, &g->w_cn_tc[sd])) { fbgnn_gbp_destroy(g); return FBGNN_E_CUDA; }
+        }
+    }
     *out = g;
     return 0;
 }
@@ -873,7 +922,17 @@ extern "C" int fbgnn_gbp_destroy(fbgnn_gbp *g) {
     if (!g) return 0;
     cudaSetDevice(g->ctx->device);
     cudaFree(g->w_cn); cudaFree(g->w_vn); cudaFree(g->w_inv);
+    cudaFree(g->w_vn_tc); cudaFree(g->w_cn_tc[0]); cudaFree(g->w_cn_tc[1]);
     delete g;
+    return 0;
+}
+
+extern "C" int fbgnn_gbp_set_gemm(fbgnn_gbp *g, int32_t mode) {
+    REQUIRE(g, "NULL handle");
+    REQUIRE(mode == FBGNN_GEMM_FMA || mode == FBGNN_GEMM_TF32X3, "unknown gemm mode %d", mode);
+    if (mode == FBGNN_GEMM_TF32X3 && !(g->reduce <= 1 && g->act == FBGNN_ACT_TANH))
+        return fail(FBGNN_E_UNSUPPORTED, "the tensor-core path needs reduce_op mean / sum and tanh activation");
+    g->gemm = mode;
     return 0;
 }
 
@@ -900,7 +959,23 @@ static int gbp_run(fbgnn_code *code, fbgnn_gbp *g, int32_t num_iter, int64_t B, 
     const unsigned g_cn = (unsigned)std::min<int64_t>((B * mt + 127) / 128, (int64_t)ctx->num_sms * 8);
     const unsigned g_vn = (unsigned)std::min<int64_t>((B * n + 127) / 128, (int64_t)ctx->num_sms * 8);
     const size_t smem_lg = sizeof(float) * 2 * n + n + 16;
+    const bool use_tc = fact && g->gemm == FBGNN_GEMM_TF32X3 && g->act == FBGNN_ACT_TANH;
+    const size_t smem_vn_tc = sizeof(float) * tc::VnW::total, smem_cn_tc = sizeof(float) * tc::CnW::total;
+    if (use_tc) {
+        if (int rc = set_smem(tc::k_gbp_vn_tc<MATH>, smem_vn_tc, ctx, "GNN_BP4 VN update (tensor cores)")) return rc;
+        if (int rc = set_smem(tc::k_gbp_cn_tc<MATH>, smem_cn_tc, ctx, "GNN_BP4 CN update (tensor cores)")) return rc;
+    }
+    auto tc_grid = [&](int64_t rows) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((rows + 255) / 256, (int64_t)ctx->num_sms * 2)); };
     auto cn_update = [&]() {
+        if (use_tc) {
+            for (int sd = 0; sd < 2; sd++) {
+                const int ms = sd ? a.Z.m : a.X.m;
+                if (ms == 0) continue;
+                tc::k_gbp_cn_tc<MATH><<<tc_grid(B * ms), 256, smem_cn_tc, st>>>(a, g->w_cn_tc[sd], sd);
+                ctx->launches++;
+            }
+            return;
+        }
         if (fact && tb) k_gbp_cn_f<20, 40, 20, true, MATH><<<g_cn, 128, smem_cn, st>>>(a);
         else if (fact) k_gbp_cn_f<20, 40, 20, false, MATH><<<g_cn, 128, smem_cn, st>>>(a);
         else k_gbp_cn<20, 40, 20, MATH><<<g_cn, 128, smem_cn, st>>>(a);
@@ -914,7 +989,8 @@ static int gbp_run(fbgnn_code *code, fbgnn_gbp *g, int32_t num_iter, int64_t B, 
     cn_update();
     a.zero_logits = 0;
     for (int it = 0; it < num_iter; it++) {
-        if (fact && tb) k_gbp_vn_f<20, 40, 20, true, MATH><<<g_vn, 128, smem_vn, st>>>(a);
+        if (use_tc) tc::k_gbp_vn_tc<MATH><<<tc_grid(B * n), 256, smem_vn_tc, st>>>(a, g->w_vn_tc);
+        else if (fact && tb) k_gbp_vn_f<20, 40, 20, true, MATH><<<g_vn, 128, smem_vn, st>>>(a);
         else if (fact) k_gbp_vn_f<20, 40, 20, false, MATH><<<g_vn, 128, smem_vn, st>>>(a);
         else k_gbp_vn<20, 40, 20, MATH><<<g_vn, 128, smem_vn, st>>>(a);
         GbpArgs la = a;

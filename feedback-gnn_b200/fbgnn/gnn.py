@@ -53,6 +53,11 @@ def load_weights(system, model_path):
     system.set_weights(read_weights(model_path))
 
 
+# how the per-node matrix products run: FP32 FMAs (bit-exact with the oracle) or tcgen05 tensor cores with the
+# 3-product TF32 split (float32 accuracy; needs reduce_op mean / sum and tanh)
+GEMM_MODES = {"fma": 0, "tf32x3": 1}
+
+
 class GNN_BP4:
     """The full GNN message-passing decoder -- ``GNN_BP4`` of the reference (``gnn.py:71-420`` with
     ``UpdateCNEmbeddings`` ``:423-610`` and ``UpdateVNEmbeddings`` ``:613-751``).
@@ -68,18 +73,23 @@ class GNN_BP4:
     ``[_llr_inv_embed (W,b), update_h_cn: msg_mlp_x, msg_mlp_z, embed_mlp_x, embed_mlp_z, update_h_vn:
     msg_mlp_x, msg_mlp_z, embed_mlp]`` with ``(W1, b1, W2, b2)`` per MLP.  This build provides
     20 / 40 / 20 embedding / hidden / message dims with 2-layer MLPs and no node/edge attributes.
+
+    ``gemm="tf32x3"`` (extension) evaluates the per-node matrix products on the tensor cores.
     """
 
     def __init__(self, code, num_embed_dims, num_msg_dims, num_hidden_units, num_mlp_layers, num_iter,
                  reduce_op="mean", activation="tanh", clip_llr_to=None, use_attributes=False,
                  node_attribute_dims=0, msg_attribute_dims=0, use_bias=False, input_embed=False,
-                 loss_type="boxplus-phi", ctx=None):
+                 loss_type="boxplus-phi", ctx=None, gemm="fma"):
         if int(num_mlp_layers) != 2 or use_attributes:
             raise NotImplementedError("this build provides 2-layer MLPs without node/edge attributes")
         if loss_type != "boxplus-phi":
             raise NotImplementedError("only loss_type='boxplus-phi' (soft syndromes) is provided")
         if reduce_op not in ("mean", "sum", "max", "min"):
             raise ValueError("unknown reduce operation")
+        if gemm not in GEMM_MODES:
+            raise ValueError("gemm must be 'fma' or 'tf32x3'")
+        self._gemm = gemm
         self._code = code
         self._d, self._M, self._H = int(num_embed_dims), int(num_msg_dims), int(num_hidden_units)
         self._num_iter = int(num_iter)
@@ -163,6 +173,7 @@ class GNN_BP4:
             _ffi.call("fbgnn_gbp_create", ctx.handle, self._d, self._H, self._M, ACTS[self._activation],
                       REDUCE[self._reduce_op], arr, C.byref(h))
             self._handle = h
+            _ffi.call("fbgnn_gbp_set_gemm", h, GEMM_MODES[self._gemm])
         return self._handle
 
     def __call__(self, inputs):

@@ -66,6 +66,8 @@ extern "C" {
 #define FBGNN_ACT_TANH   0
 #define FBGNN_ACT_RELU   1
 #define FBGNN_ACT_LINEAR 2
+#define FBGNN_GEMM_FMA    0           /* GNN_BP4 matrix products in FP32 FMAs, bit-exact with the oracle (default) */
+#define FBGNN_GEMM_TF32X3 1           /* on tcgen05 tensor cores, 3-product TF32 split: float32 accuracy, not bit-exact */
 #define FBGNN_REDUCE_MEAN 0
 #define FBGNN_REDUCE_SUM  1
 #define FBGNN_REDUCE_MAX  2
@@ -209,6 +211,9 @@ int fbgnn_gnn_forward(fbgnn_code *code, fbgnn_gnn *gnn, int64_t B, fbgnn_tensor3
 int fbgnn_gbp_create(fbgnn_ctx *ctx, int32_t d, int32_t H, int32_t M, int32_t activation, int32_t reduce_op,
                      const float *const *arrays, fbgnn_gbp **gbp);
 int fbgnn_gbp_destroy(fbgnn_gbp *gbp);
+/* Select how GNN_BP4's per-node matrix products are evaluated (FBGNN_GEMM_*).  The tensor-core form
+ * (fbgnn_gbp_tc.cuh) needs reduce_op mean / sum and tanh; otherwise FBGNN_E_UNSUPPORTED. */
+int fbgnn_gbp_set_gemm(fbgnn_gbp *gbp, int32_t mode);
 /* GNN_BP4.call: synd_x uint8 [B,m_x], synd_z uint8 [B,m_z] contiguous, batch first (gnn.py:385-386);
  * x_logit float32 (iteration, row, b) with m_z + k_z rows = [hz_logit; lz_logit], z_logit with m_x + k_x rows
  * = [hx_logit; lx_logit] (either may be NULL); x_hat, z_hat uint8 (v, b): the argmin decision. */

@@ -75,3 +75,39 @@ def test_cuda_gnn_bp4_bitexact(oracle, codes, name, reduce_op, bias):
             assert got.shape == want.shape
             assert np.array_equal(np.ascontiguousarray(got).view(np.uint32), np.ascontiguousarray(want).view(np.uint32)), (name, i)
     assert np.array_equal(x_hat.astype(np.uint8), ref["x_hat"]) and np.array_equal(z_hat.astype(np.uint8), ref["z_hat"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,reduce_op,bias", [("c882", "mean", True), ("rsurf3", "sum", True), ("gb48", "mean", False)])
+def test_cuda_gnn_bp4_tensor_core_path(oracle, codes, name, reduce_op, bias):
+    """gemm="tf32x3": the per-node matrix products on tcgen05 tensor cores with the three-product TF32 split.
+    Not bit-exact by construction (the tensor core's accumulation order is its own); stated tolerance against
+    the oracle: |logit difference| <= 2e-5 + 1e-5 |logit| in every iteration, identical hard decisions on
+    >= 99.99 % of the qubits."""
+    import fbgnn as F
+    code = codes[name]
+    W = oracle.gnn_bp4_random_weights(seed=4, use_bias=bias)
+    B, it = 300, 6                         # 300 frames: several 128-row tiles with a ragged tail
+    sx, sz = _syndromes(oracle, code, B, 0.06, 9)
+    G = F.GNN_BP4(code, num_embed_dims=20, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, num_iter=it,
+                  reduce_op=reduce_op, activation="tanh", use_bias=bias, gemm="tf32x3")
+    G.set_weights(_weights_list(W, bias))
+    llr_hat, x_hat, z_hat = G((sx, sz))
+    ref = oracle.gnn_bp4(oracle.CodeGraph(code), W, sx, sz, it, reduce_op=reduce_op)
+    for i in range(it):
+        for got, want in ((llr_hat[i][0], ref["x_logit"][i]), (llr_hat[i][1], ref["z_logit"][i])):
+            assert got.shape == want.shape
+            assert np.all(np.abs(got - want) <= 2e-5 + 1e-5 * np.abs(want)), (name, i, float(np.abs(got - want).max()))
+    agree = np.mean((x_hat.astype(np.uint8) == ref["x_hat"]) & (z_hat.astype(np.uint8) == ref["z_hat"]))
+    assert agree >= 0.9999, agree
+
+
+@pytest.mark.gpu
+def test_tensor_core_path_rejects_unsupported_configurations(codes):
+    import fbgnn as F
+    G = F.GNN_BP4(codes["steane"], 20, 20, 40, 2, 2, reduce_op="max", gemm="tf32x3")
+    sx = np.zeros((2, codes["steane"].hx.shape[0]), np.uint8)
+    with pytest.raises(F.FbgnnError):
+        G((sx, sx))
+    with pytest.raises(ValueError):
+        F.GNN_BP4(codes["steane"], 20, 20, 40, 2, 2, gemm="bf16")
