@@ -944,8 +944,9 @@ static int gbp_run(fbgnn_code *code, fbgnn_gbp *g, int32_t num_iter, int64_t B, 
     const int n = a.X.n, mt = a.X.m + a.Z.m;
     const bool fact = g->reduce <= 1;        // mean / sum: factored edge MLPs (sender halves in a.pfc / a.pfv)
     const size_t smem_pre = sizeof(float) * 2 * 40 * 20;
-    const size_t smem_cn = fact ? sizeof(float) * GL::cn_total + smem_pre : sizeof(float) * (GL::cn_total + 40 * 128);
-    const size_t smem_vn = fact ? sizeof(float) * GL::vn_total + smem_pre : sizeof(float) * (GL::vn_total + 40 * 128);
+    const size_t smem_codes = sizeof(uint32_t) * GBP_CODE_CAP * 128;          // staged edge codes of the factored kernels
+    const size_t smem_cn = fact ? sizeof(float) * GL::cn_total + smem_pre + smem_codes : sizeof(float) * (GL::cn_total + 40 * 128);
+    const size_t smem_vn = fact ? sizeof(float) * GL::vn_total + smem_pre + smem_codes : sizeof(float) * (GL::vn_total + 40 * 128);
     const bool tb = g->act == FBGNN_ACT_TANH && g->use_bias;
     if (fact) {
         if (int rc = set_smem(k_gbp_cn_f<20, 40, 20, true, MATH>, smem_cn, ctx, "GNN_BP4 CN update")) return rc;
@@ -960,7 +961,8 @@ static int gbp_run(fbgnn_code *code, fbgnn_gbp *g, int32_t num_iter, int64_t B, 
     const unsigned g_vn = (unsigned)std::min<int64_t>((B * n + 127) / 128, (int64_t)ctx->num_sms * 8);
     const size_t smem_lg = sizeof(float) * 2 * n + n + 16;
     const bool use_tc = fact && g->gemm == FBGNN_GEMM_TF32X3 && g->act == FBGNN_ACT_TANH;
-    const size_t smem_vn_tc = sizeof(float) * tc::VnW::total, smem_cn_tc = sizeof(float) * tc::CnW::total;
+    const size_t smem_vn_tc = sizeof(float) * tc::VnW::total + sizeof(uint32_t) * GBP_CODE_CAP * 256;
+    const size_t smem_cn_tc = sizeof(float) * tc::CnW::total + sizeof(uint32_t) * GBP_CODE_CAP * 256;
     if (use_tc) {
         if (int rc = set_smem(tc::k_gbp_vn_tc<MATH>, smem_vn_tc, ctx, "GNN_BP4 VN update (tensor cores)")) return rc;
         if (int rc = set_smem(tc::k_gbp_cn_tc<MATH>, smem_cn_tc, ctx, "GNN_BP4 CN update (tensor cores)")) return rc;

@@ -184,17 +184,19 @@ __device__ __forceinline__ void gemm(Grp &g, int col_ahi, int col_alo, int kpad,
 // (hi at [0, 40), lo at [40, 80)).  Returns the sum of the message signs.
 template <typename MATH, typename SENDER>
 __device__ __forceinline__ int recv_tc(const Grp &g, int col_base, const float *__restrict__ b1, int e0, int e1,
-                                       const float *__restrict__ rows, int row_stride, SENDER sender) {
+                                       const float *__restrict__ rows, int row_stride, uint32_t *codes, int cstride,
+                                       SENDER sender) {
     constexpr int JB = 8, H = 40;
-    int ssum = 0, i0 = 0, i1 = 0;
-    bool g0 = false, g1 = false;
+    gbp_stage_codes(codes, cstride, e0, e1, sender);
+    auto code_at = [&](int e) -> uint32_t { return (e - e0 < GBP_CODE_CAP) ? codes[(e - e0) * cstride] : sender(e); };
+    int ssum = 0;
+    uint32_t c0 = 0;
     float4 nx0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), nx1 = nx0;
     if (e0 < e1) {
-        i0 = sender(e0, g0);
-        const float *pf = rows + (int64_t)i0 * row_stride;
+        c0 = code_at(e0);
+        const float *pf = rows + (int64_t)(c0 >> 1) * row_stride;
         nx0 = *reinterpret_cast<const float4 *>(pf); nx1 = *reinterpret_cast<const float4 *>(pf + 4);
     }
-    if (e0 + 1 < e1) i1 = sender(e0 + 1, g1);
 #pragma unroll 1
     for (int j = 0; j < H; j += JB) {
         float bs[JB], hs[JB];
@@ -204,17 +206,15 @@ __device__ __forceinline__ int recv_tc(const Grp &g, int col_base, const float *
         bs[0] += ba.x; bs[1] += ba.y; bs[2] += ba.z; bs[3] += ba.w; bs[4] += bb.x; bs[5] += bb.y; bs[6] += bb.z; bs[7] += bb.w;
 #pragma unroll
         for (int q = 0; q < JB; q++) hs[q] = 0.0f;
-        int ni = i1;
-        bool ng = g1, cg = g0;
+        uint32_t cc = c0;
 #pragma unroll 1
         for (int e = e0; e < e1; e++) {
             const float pq[JB] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
-            const bool neg = cg;
+            const bool neg = (cc & 1u) != 0;
             if (e + 1 < e1) {
-                const float *pf = rows + (int64_t)ni * row_stride + j;
+                cc = code_at(e + 1);
+                const float *pf = rows + (int64_t)(cc >> 1) * row_stride + j;
                 nx0 = *reinterpret_cast<const float4 *>(pf); nx1 = *reinterpret_cast<const float4 *>(pf + 4);
-                cg = ng;
-                if (e + 2 < e1) ni = sender(e + 2, ng);
             }
             if (j == 0) ssum += neg ? -1 : 1;
 #pragma unroll
@@ -224,7 +224,7 @@ __device__ __forceinline__ int recv_tc(const Grp &g, int col_base, const float *
             }
         }
         if (j + JB < H && e0 < e1) {
-            const float *pf = rows + (int64_t)i0 * row_stride + j + JB;
+            const float *pf = rows + (int64_t)(c0 >> 1) * row_stride + j + JB;
             nx0 = *reinterpret_cast<const float4 *>(pf); nx1 = *reinterpret_cast<const float4 *>(pf + 4);
         }
         uint32_t hi[JB], lo[JB];
@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(256, 2) k_gbp_vn_tc(const GbpArgs a, const flo
     Grp g = cta_setup(sm, wtc, VnW::total, bars, &tslot);
     const uint32_t sbase = smem_u32(sm);
     const float *bias = sm + VnW::BIAS;
+    uint32_t *codes = reinterpret_cast<uint32_t *>(sm + VnW::total) + threadIdx.x;      // [GBP_CODE_CAP][256]
     const int n = a.X.n, mt = a.X.m + a.Z.m, t = threadIdx.x & 127;
     const int64_t total = a.B * n, ntiles = (total + 127) / 128;
     for (int64_t tile = (int64_t)blockIdx.x * 2 + g.gid; tile < ntiles; tile += (int64_t)gridDim.x * 2) {
@@ -306,8 +307,8 @@ __global__ void __launch_bounds__(256, 2) k_gbp_vn_tc(const GbpArgs a, const flo
             const int e0 = valid ? S.vn_ptr[v] : 0, e1 = valid ? S.vn_ptr[v + 1] : 0;
             store_a<24>(g, 0, 24, own);
             gemm(g, 0, 24, 24, 80, sbase + 4 * (side ? VnW::B1Z : VnW::B1X), 48, false);
-            const int ssum = recv_tc<MATH>(g, 80, bias + side * H, e0, e1, pf_b, H,
-                                           [&](int e, bool &neg) { const int c = vn_cn[e]; neg = sy[c] != 0; return c; });
+            const int ssum = recv_tc<MATH>(g, 80, bias + side * H, e0, e1, pf_b, H, codes, 256,
+                                           [&](int e) { const uint32_t c = vn_cn[e]; return (c << 1) | (sy[c] != 0 ? 1u : 0u); });
             gemm(g, 0, 40, 40, 80, sbase + 4 * (side ? VnW::W2Z : VnW::W2X), 32, false);
             const float fs = (float)ssum, dg = (float)(e1 - e0);
             const float *b2 = bias + 2 * H + side * M;
@@ -382,6 +383,7 @@ __global__ void __launch_bounds__(256, 2) k_gbp_cn_tc(const GbpArgs a, const flo
     Grp g = cta_setup(sm, wtc, CnW::total, bars, &tslot);
     const uint32_t sbase = smem_u32(sm);
     const float *bias = sm + CnW::BIAS;
+    uint32_t *codes = reinterpret_cast<uint32_t *>(sm + CnW::total) + threadIdx.x;      // [GBP_CODE_CAP][256]
     const SideDev &S = side ? a.Z : a.X;
     const int n = a.X.n, mt = a.X.m + a.Z.m, ms = S.m, coff = side ? a.X.m : 0, t = threadIdx.x & 127;
     const idx_t *cn_vn = S.cn_vn;
@@ -412,7 +414,7 @@ __global__ void __launch_bounds__(256, 2) k_gbp_cn_tc(const GbpArgs a, const flo
         const float *pf_b = a.pfv + b * n * 2 * H + (side ? H : 0);
         store_a<24>(g, 0, 24, own);
         gemm(g, 0, 24, 24, 80, sbase + 4 * CnW::B1, 48, false);
-        recv_tc<MATH>(g, 80, bias, e0, e1, pf_b, 2 * H, [&](int e, bool &neg) { neg = false; return (int)cn_vn[e]; });
+        recv_tc<MATH>(g, 80, bias, e0, e1, pf_b, 2 * H, codes, 256, [&](int e) { return (uint32_t)cn_vn[e] << 1; });
         gemm(g, 0, 40, 40, 80, sbase + 4 * CnW::W2, 32, false);
         const float dg = (float)(e1 - e0);
         const float *b2 = bias + H;

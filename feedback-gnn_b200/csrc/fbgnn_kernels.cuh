@@ -1132,30 +1132,40 @@ __device__ __forceinline__ void gbp_sender_half(const float *__restrict__ w1t, c
     }
 }
 
-// Messages into one receiver over edges [e0, e1): SENDER(e, neg) gives the sender's row number in `rows`
-// (row_stride floats apart) and whether the message is negated.  red[M] receives the reduced message.
-// Hidden units are walked eight at a time (one 32-byte sector of every sender row per step).  Loads run ahead
-// of their use without unrolling the edge loop (its body stays inside the instruction cache): the row of edge
-// e+1 and the sender number of edge e+2 are requested before edge e is evaluated, and the first row of the
-// next step before the output-layer products of this one.
+// Messages into one receiver over edges [e0, e1).  SENDER(e) gives the edge's code: (row number of the sender
+// in `rows`, row_stride floats apart) << 1 | (1 if the message is negated).  red[M] receives the reduced
+// message.  The codes of the first GBP_CODE_CAP edges are staged once in the thread's shared-memory slots
+// (codes[k * cstride]) so the hidden-unit steps below do not repeat the dependent index / syndrome loads.
+// Hidden units are walked eight at a time (one 32-byte sector of every sender row per step); the row of edge
+// e+1 is requested before edge e is evaluated and the first row of the next step before the output-layer
+// products of this one, without unrolling the edge loop (its body stays inside the instruction cache).
+constexpr int GBP_CODE_CAP = 8;
+
+template <typename SENDER>
+__device__ __forceinline__ void gbp_stage_codes(uint32_t *codes, int cstride, int e0, int e1, SENDER sender) {
+    const int ne = min(e1 - e0, GBP_CODE_CAP);
+    for (int k = 0; k < ne; k++) codes[k * cstride] = sender(e0 + k);
+}
+
 template <int D, int H, int M, typename MATH, typename SENDER>
 __device__ __forceinline__ void gbp_recv_factored(const float *__restrict__ w, const float own[D], int e0, int e1, int act,
                                                   bool use_bias, int reduce, const float *__restrict__ rows, int row_stride,
-                                                  SENDER sender, float red[M]) {
+                                                  uint32_t *codes, int cstride, SENDER sender, float red[M]) {
     typedef GbpLayout<D, H, M> L;
     constexpr int JB = 8;
     static_assert(H % JB == 0, "H must be a multiple of 8");
+    gbp_stage_codes(codes, cstride, e0, e1, sender);
+    auto code_at = [&](int e) -> uint32_t { return (e - e0 < GBP_CODE_CAP) ? codes[(e - e0) * cstride] : sender(e); };
 #pragma unroll
     for (int i = 0; i < M; i++) red[i] = 0.0f;
-    int ssum = 0, i0 = 0, i1 = 0;
-    bool g0 = false, g1 = false;
+    int ssum = 0;
+    uint32_t c0 = 0;
     float4 nx0 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), nx1 = nx0;
     if (e0 < e1) {
-        i0 = sender(e0, g0);
-        const float *pf = rows + (int64_t)i0 * row_stride;
+        c0 = code_at(e0);
+        const float *pf = rows + (int64_t)(c0 >> 1) * row_stride;
         nx0 = *reinterpret_cast<const float4 *>(pf); nx1 = *reinterpret_cast<const float4 *>(pf + 4);
     }
-    if (e0 + 1 < e1) i1 = sender(e0 + 1, g1);
 #pragma unroll 1
     for (int j = 0; j < H; j += JB) {
         float bs[JB], hs[JB], b1[JB];
@@ -1173,17 +1183,15 @@ __device__ __forceinline__ void gbp_recv_factored(const float *__restrict__ w, c
             hs[q] = 0.0f;
             b1[q] = use_bias ? w[L::e_b1 + j + q] : 0.0f;
         }
-        int ni = i1;
-        bool ng = g1, cg = g0;
+        uint32_t cc = c0;
 #pragma unroll 1
         for (int e = e0; e < e1; e++) {
             const float pq[JB] = {nx0.x, nx0.y, nx0.z, nx0.w, nx1.x, nx1.y, nx1.z, nx1.w};
-            const bool neg = cg;
+            const bool neg = (cc & 1u) != 0;
             if (e + 1 < e1) {
-                const float *pf = rows + (int64_t)ni * row_stride + j;
+                cc = code_at(e + 1);
+                const float *pf = rows + (int64_t)(cc >> 1) * row_stride + j;
                 nx0 = *reinterpret_cast<const float4 *>(pf); nx1 = *reinterpret_cast<const float4 *>(pf + 4);
-                cg = ng;
-                if (e + 2 < e1) ni = sender(e + 2, ng);
             }
             if (j == 0) ssum += neg ? -1 : 1;
 #pragma unroll
@@ -1196,7 +1204,7 @@ __device__ __forceinline__ void gbp_recv_factored(const float *__restrict__ w, c
             }
         }
         if (j + JB < H && e0 < e1) {
-            const float *pf = rows + (int64_t)i0 * row_stride + j + JB;
+            const float *pf = rows + (int64_t)(c0 >> 1) * row_stride + j + JB;
             nx0 = *reinterpret_cast<const float4 *>(pf); nx1 = *reinterpret_cast<const float4 *>(pf + 4);
         }
 #pragma unroll
@@ -1251,6 +1259,7 @@ __global__ void __launch_bounds__(128, 4) k_gbp_cn_f(const GbpArgs a) {
     typedef GbpLayout<D, H, M> L;
     extern __shared__ float gsm[];
     float *w = gsm, *wp = gsm + L::cn_total;
+    uint32_t *codes = reinterpret_cast<uint32_t *>(wp + 2 * H * D) + threadIdx.x;      // [GBP_CODE_CAP][blockDim]
     for (int i = threadIdx.x; i < L::cn_total; i += blockDim.x) w[i] = a.w_cn[i];
     for (int i = threadIdx.x; i < 2 * H * D; i += blockDim.x) {
         const int side = i / (H * D), r = i - side * H * D, j = r / D, k = r - j * D;
@@ -1279,7 +1288,7 @@ __global__ void __launch_bounds__(128, 4) k_gbp_cn_f(const GbpArgs a) {
         const idx_t *cn_vn = S.cn_vn;
         float red[M];
         gbp_recv_factored<D, H, M, MATH>(we, own, S.cn_ptr[cc], S.cn_ptr[cc + 1], act, use_bias, a.reduce, pf_b, 2 * H,
-            [&](int e, bool &neg) { neg = false; return (int)cn_vn[e]; }, red);
+            codes, blockDim.x, [&](int e) { return (uint32_t)cn_vn[e] << 1; }, red);
 #pragma unroll
         for (int i = 0; i < M; i++) in[i] = red[i];
 #pragma unroll
@@ -1304,6 +1313,7 @@ __global__ void __launch_bounds__(128) k_gbp_vn_f(const GbpArgs a) {
     typedef GbpLayout<D, H, M> L;
     extern __shared__ float gsm[];
     float *w = gsm, *wp = gsm + L::vn_total;
+    uint32_t *codes = reinterpret_cast<uint32_t *>(wp + 2 * H * D) + threadIdx.x;      // [GBP_CODE_CAP][blockDim]
     for (int i = threadIdx.x; i < L::vn_total; i += blockDim.x) w[i] = a.w_vn[i];
     for (int i = threadIdx.x; i < 2 * H * D; i += blockDim.x) {
         const int side = i / (H * D), r = i - side * H * D, j = r / D, k = r - j * D;
@@ -1332,7 +1342,8 @@ __global__ void __launch_bounds__(128) k_gbp_vn_f(const GbpArgs a) {
             const idx_t *vn_cn = S.vn_cn;
             float red[M];
             gbp_recv_factored<D, H, M, MATH>(w + (side ? L::edge : 0), own, S.vn_ptr[v], S.vn_ptr[v + 1], act, use_bias,
-                a.reduce, pf_b, H, [&](int e, bool &neg) { const int c = vn_cn[e]; neg = sy[c] != 0; return c; }, red);
+                a.reduce, pf_b, H, codes, blockDim.x,
+                [&](int e) { const uint32_t c = vn_cn[e]; return (c << 1) | (sy[c] != 0 ? 1u : 0u); }, red);
 #pragma unroll
             for (int i = 0; i < M; i++) {
                 if (side == 0) in[i] = red[i];
