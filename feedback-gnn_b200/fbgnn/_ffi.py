@@ -89,6 +89,8 @@ _SIGNATURES = {
     "fbgnn_gbp_create": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_f32p), _vpp],
     "fbgnn_gbp_destroy": [C.c_void_p],
     "fbgnn_gbp_set_gemm": [C.c_void_p, C.c_int32],
+    "fbgnn_second_stage_grad": [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_int64, Tensor3, Tensor2,
+                                Tensor2, Tensor2, Tensor2, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_float)],
     "fbgnn_gbp_decode": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, Tensor2, Tensor2, Tensor3, Tensor3, Tensor2,
                          Tensor2],
     "fbgnn_pipeline_run": [C.c_void_p, C.POINTER(PipelineCfg), C.c_uint64, C.c_uint64, C.c_int64, Tensor2,

@@ -211,6 +211,20 @@ int fbgnn_gnn_forward(fbgnn_code *code, fbgnn_gnn *gnn, int64_t B, fbgnn_tensor3
 int fbgnn_gbp_create(fbgnn_ctx *ctx, int32_t d, int32_t H, int32_t M, int32_t activation, int32_t reduce_op,
                      const float *const *arrays, fbgnn_gbp **gbp);
 int fbgnn_gbp_destroy(fbgnn_gbp *gbp);
+/* ---- training: second stage (widening into SURVEY.md section 8(f) N3) ------------------ */
+/* Loss and weight gradients of Second_Stage_GNN_BP_Model.call under tf.GradientTape
+ * (feedback_gnn.py:395-460; training loop examples/Feedback_GNN.ipynb cells 2 and 8):
+ *   new priors = Feedback_GNN(h_vn, logit_hx, logit_hz, synd_x, synd_z);  BP4 (boxplus-phi, `num_iter`
+ *   iterations, `factor`) with the soft syndromes of every iteration;
+ *   loss = sum_{i=loss_from}^{num_iter-1} bce(1 - synd_z, x_logit_{i+1}) + bce(1 - synd_x, z_logit_{i+1}).
+ * Inputs as fbgnn_gnn_forward.  *loss (host) receives the loss; with want_grad != 0, grads (host, 3923
+ * floats) receives d loss / d weights as the row-major blocks [W0; b0] (41x3), [W1x; b1x] (5x40),
+ * [W2x; b2x] (41x20), [W1z; b1z], [W2z; b2z], [W3; b3] (44x40).  Synchronises the stream. */
+int fbgnn_second_stage_grad(fbgnn_code *code, fbgnn_gnn *gnn, int32_t num_iter, float factor, int32_t loss_from,
+                            int64_t B, fbgnn_tensor3 h_vn, fbgnn_tensor2 logit_hx, fbgnn_tensor2 logit_hz,
+                            fbgnn_tensor2 synd_x, fbgnn_tensor2 synd_z, int32_t want_grad, double *loss,
+                            float *grads);
+
 /* Select how GNN_BP4's per-node matrix products are evaluated (FBGNN_GEMM_*).  The tensor-core form
  * (fbgnn_gbp_tc.cuh) needs reduce_op mean / sum and tanh; otherwise FBGNN_E_UNSUPPORTED. */
 int fbgnn_gbp_set_gemm(fbgnn_gbp *gbp, int32_t mode);
