@@ -95,6 +95,8 @@ class Second_Stage_GNN_BP_Model:
         self.trainable = bool(trainable)
         self._ctx = ctx
         self._grads = None
+        # residual-syndrome products through float32 BLAS (exact: entries <= n < 2^24); numpy's integer matmul is slow
+        self._f32 = [np.ascontiguousarray(m, np.float32) for m in (code.hz, code.hx, code.hx_perp, code.hz_perp)]
 
     @property
     def trainable_variables(self):
@@ -121,10 +123,12 @@ class Second_Stage_GNN_BP_Model:
         # decisions of the same forward pass (feedback_gnn.py:425-426,433-452)
         new_llr = self.feedback((h, lhx, lhz, sx, sz))
         _, x_hat, z_hat = self.decoder((new_llr.transpose((0, 2, 1)), sx, sz))
-        x_diff = np.logical_xor(noise_x.T, x_hat.numpy().astype(bool).T).astype(np.int64)      # [n, B]
-        z_diff = np.logical_xor(noise_z.T, z_hat.numpy().astype(bool).T).astype(np.int64)
-        s_hat = np.concatenate([(self.hz @ x_diff) & 1, (self.hx @ z_diff) & 1], axis=0).T
-        ls_hat = np.concatenate([(self.hx_perp @ x_diff) & 1, (self.hz_perp @ z_diff) & 1], axis=0).T
+        x_diff = np.logical_xor(noise_x.T, x_hat.numpy().astype(bool).T).astype(np.float32)    # [n, B]
+        z_diff = np.logical_xor(noise_z.T, z_hat.numpy().astype(bool).T).astype(np.float32)
+        hz, hx, hxp, hzp = self._f32
+        mod2 = lambda a: a.astype(np.int64) & 1
+        s_hat = np.concatenate([mod2(hz @ x_diff), mod2(hx @ z_diff)], axis=0).T
+        ls_hat = np.concatenate([mod2(hxp @ x_diff), mod2(hzp @ z_diff)], axis=0).T
         return s_hat, ls_hat, float(loss.value)
 
     call = __call__
