@@ -534,11 +534,36 @@ static int launch_bp4_m(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t s
               : launch_bp4_t<false, DV, DC, MathExact, false>(ctx, a, grid, smem, threads);
 }
 
+// Codes whose per-frame state does not fit the shared memory of an SM: generic kernel with the float arrays in HBM.
+template <typename MATH>
+static int launch_bp4_gstate(fbgnn_ctx *ctx, Bp4Args a, int64_t grid, int threads, bool cp) {
+    const SideDev &X = a.X, &Z = a.Z;
+    const size_t smem = 2 * (((size_t)X.n + 1) & ~(size_t)1) + X.m + Z.m + X.n + 16;
+    a.state_stride = (int64_t)X.E + Z.E + ((cp ? 2 : 3) + (a.iter_logits.ptr ? 2 : 0)) * (int64_t)X.n;
+    CK(cudaMallocAsync(&a.state, sizeof(float) * (size_t)grid * a.state_stride, ctx->stream));
+    int rc;
+    if (cp) {
+        rc = set_smem(k_bp4<true, 0, 0, MATH, false, true>, smem, ctx, "quaternary BP (HBM state)");
+        if (!rc) k_bp4<true, 0, 0, MATH, false, true><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+    } else {
+        rc = set_smem(k_bp4<false, 0, 0, MATH, false, true>, smem, ctx, "quaternary BP (HBM state)");
+        if (!rc) k_bp4<false, 0, 0, MATH, false, true><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+    }
+    CK(cudaFreeAsync(a.state, ctx->stream));
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 static int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {
     if (grid <= 0) return 0;
     const bool cp = a.llr.ptr == nullptr;
     const size_t smem = bp4_smem(a.X, a.Z, cp, a.iter_logits.ptr != nullptr);
     const int threads = pick_threads(a.X.n, a.X.m + a.Z.m);
+    if (smem > ctx->smem_optin)
+        return ctx->math_mode == FBGNN_MATH_FAST ? launch_bp4_gstate<MathFast>(ctx, a, grid, threads, cp)
+                                                 : launch_bp4_gstate<MathExact>(ctx, a, grid, threads, cp);
     // both sides regular with the same degrees -> unrolled instantiation
     int dv = 0, dc = 0;
     if (a.X.reg_dv && a.X.reg_dv == a.Z.reg_dv && a.X.reg_dc && a.X.reg_dc == a.Z.reg_dc) { dv = a.X.reg_dv; dc = a.X.reg_dc; }

@@ -333,6 +333,8 @@ struct Bp4Args {
     uint8_t *active_out;                // [B]
     uint8_t *rounds;                    // [B] incremented when the frame stays active (or nullptr)
     int *next_list, *next_count;        // optional compaction of still-active frames
+    float *state;                       // GSTATE kernels: per-CTA message / prior arrays in HBM (codes beyond shared memory)
+    int64_t state_stride;               // floats per CTA
 };
 
 // Soft syndromes of the current message state (stage_two / trainable output of the reference):
@@ -382,14 +384,17 @@ __device__ void bp4_iter_logits(const Bp4Args &a, const float *mx, const float *
 // One CTA decodes one frame.  Dynamic shared memory:
 //   float msg_x[E_x], msg_z[E_z], pri[CONST_PRIOR ? 2n : 3n], (scr[2n] if iter_logits);  u16 rec[n];
 //   u8 sbx[m_x], sbz[m_z], dec[n]
-template <bool CONST_PRIOR, int DV, int DC, typename MATH, bool FPX>
+// GSTATE (codes whose state exceeds the 227 KB of an SM): the float arrays live in the CTA's slice of an HBM
+// scratch buffer (L2-resident while the CTA runs) instead; same code, same arithmetic, same results.
+template <bool CONST_PRIOR, int DV, int DC, typename MATH, bool FPX, bool GSTATE = false>
 __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     extern __shared__ float smem[];
     const SideDev &X = a.X, &Z = a.Z;
     const int n = X.n, T = blockDim.x, tid = threadIdx.x;
     const int64_t b = a.frame_list ? a.frame_list[blockIdx.x] : blockIdx.x;
-    float *mx = smem, *mz = mx + X.E, *pri = mz + Z.E, *scr2 = pri + (CONST_PRIOR ? 2 : 3) * n;
-    uint16_t *rec = (uint16_t *)(scr2 + (a.iter_logits.ptr ? 2 * n : 0));
+    float *mx = GSTATE ? a.state + (int64_t)blockIdx.x * a.state_stride : smem;
+    float *mz = mx + X.E, *pri = mz + Z.E, *scr2 = pri + (CONST_PRIOR ? 2 : 3) * n;
+    uint16_t *rec = GSTATE ? (uint16_t *)smem : (uint16_t *)(scr2 + (a.iter_logits.ptr ? 2 * n : 0));
     uint8_t *sbx = (uint8_t *)(rec + ((n + 1) & ~1)), *sbz = sbx + X.m, *dec = sbz + Z.m;
 
     for (int e = tid; e < X.E + Z.E; e += T) mx[e] = 0.0f;

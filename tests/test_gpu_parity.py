@@ -324,3 +324,34 @@ def test_dlpack_roundtrip():
     e = F.from_dlpack(v)                                  # export + import, zero copy
     assert e.ptr == v.ptr and e.shape == v.shape and e.strides == v.strides
     assert np.array_equal(e.numpy(), a.transpose(1, 0, 2))
+
+
+def test_code_larger_than_shared_memory_uses_hbm_state(oracle, weights):
+    """[[7688,50]] hypergraph-product code: 36 bytes of decoder state per qubit = 277 KB per frame, more than an SM's
+    227 KB of shared memory -- the decoder switches to the kernel variant whose message arrays live in HBM.
+    Same arithmetic: layer outputs and pipeline flags stay bit-exact with the oracle."""
+    import fbgnn as F
+    h = F.create_circulant_matrix(62, [0, 2, 5])
+    code = F.hypergraph_product(h, h)
+    assert (code.N, code.K) == (7688, 50)
+    B = 5
+    nx, nz, sx, sz = _noise_and_syndromes(oracle, code, B, 0.03, seed=5)
+    g = oracle.CodeGraph(code)
+    prior = oracle.prior_llr(0.03)
+    rng = np.random.default_rng(1)
+    llr = (prior + rng.normal(0, 0.3, (B, 3, code.N))).astype(np.float32)
+    for cn_type, it in (("boxplus-phi", 6), ("minsum", 3)):
+        dec = F.QLDPCBPDecoder(code, num_iter=it, normalization_factor=0.9, cn_type=cn_type, stage_one=True)
+        out = dec((llr, sx, sz))
+        ref = oracle.bp4(g, llr, sx, sz, it, 0.9, cn_type)
+        for k, o in zip(("Lx", "Ly", "Lz", "x_hat", "z_hat", "x_logit", "z_logit"), out):
+            assert_bitexact(np.asarray(o, dtype=ref[k].dtype), ref[k], f"large code {cn_type} {k}")
+    G = F.Feedback_GNN(code, 20, 40, 2, "mean", "tanh", True)
+    G.set_weights(weights["c882"])
+    d1 = F.QLDPCBPDecoder(code, num_iter=8, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+    d2 = F.QLDPCBPDecoder(code, num_iter=4, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+    model = F.Sandwich_BP_GNN_Evaluation_Model(code, [d1, d2], [G], num_layers=2, seed=3)
+    res = model.run(6, 0.05, want_counters=True)
+    ref = oracle.pipeline(g, [8, 4], [oracle.Gnn(weights["c882"])], 0.05, seed=3, B=6)
+    assert_bitexact(res["flags"].numpy(), ref["flags"], "large code pipeline flags")
+    assert res["counters"].tolist() == ref["counters"].tolist()
