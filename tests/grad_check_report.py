@@ -1,7 +1,7 @@
 """Directional derivatives of the second-stage loss: CUDA reverse sweep vs central differences of the float64
-restatement (development aid; the asserting version is tests/test_training.py)."""
+restatement.  Report generator for profiles/r01_gradient_check.txt (lives under tests/ because it uses the oracle; the asserting version is tests/test_training.py)."""
 import os, sys, json, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))   # tests/ -> repo root
 sys.path.insert(0, os.path.join(ROOT, "feedback-gnn_b200")); sys.path.insert(0, ROOT)
 import numpy as np
 import fbgnn as F
