@@ -150,3 +150,31 @@ def test_dataset_generators_return_undecoded_error_strings(codes, weights):
     hard = F.Feedback_GNN_Error_Model(code, d1, G, dec, wt=True, seed=21)
     hx_, hz_ = hard(400, 60)
     assert hx_.shape[0] <= ex.shape[0]                                  # the GNN round rescues some of them
+
+
+def test_second_stage_model_host_contract(codes):
+    """Constructor checks and the mapping of the packed gradient onto the Keras weight order (no GPU needed)."""
+    import fbgnn as F
+    from fbgnn import training as T
+    code = codes["steane"]
+    G = F.Feedback_GNN(code, 20, 40, 2, "mean", "tanh", True)
+    d_one = F.QLDPCBPDecoder(code, num_iter=4, cn_type="boxplus-phi", stage_one=True)
+    d_two = F.QLDPCBPDecoder(code, num_iter=4, cn_type="boxplus-phi", stage_two=True)
+    with pytest.raises(TypeError):
+        F.Second_Stage_GNN_BP_Model(code, G, d_one, num_iter=4)              # needs a stage_two decoder
+    with pytest.raises(TypeError):
+        F.First_Stage_BP_Model(code, d_two)                                  # needs a stage_one decoder
+    with pytest.raises(ValueError):
+        F.Second_Stage_GNN_BP_Model(code, G, d_two, num_iter=5)              # num_iter must match the decoder
+    with pytest.raises(NotImplementedError):
+        F.Second_Stage_GNN_BP_Model(code, G, F.QLDPCBPDecoder(code, num_iter=4, cn_type="minsum", stage_two=True), num_iter=4)
+    m = F.Second_Stage_GNN_BP_Model(code, G, d_two, num_iter=4)
+    with pytest.raises(RuntimeError):
+        m.gradients()
+    n_flat = sum(r * c for r, c in T._GRAD_BLOCKS)
+    assert n_flat == G.count_params() == 3923
+    g = m._unpack(np.arange(n_flat, dtype=np.float32))
+    assert [a.shape for a in g] == [a.shape for a in G.get_weights()]
+    assert g[0][0, 0] == 0 and g[1][0] == 40 * 3                             # [W0; b0] block: bias row last
+    assert g[2][0, 0] == 41 * 3 and g[3][0] == 41 * 3 + 4 * 40               # [W1x; b1x]
+    assert len(m.trainable_variables) == 12
