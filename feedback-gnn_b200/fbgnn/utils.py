@@ -22,6 +22,24 @@ def count_block_errors(b, b_hat):
     return int(np.sum(np.any(b != b_hat, axis=-1)))
 
 
+def compute_bler(b, b_hat):
+    """Fraction of rows in which ``b`` and ``b_hat`` differ (metrics.py:142-170)."""
+    if isinstance(b_hat, ErrorIndicator) and (b is None or _is_zero(b)):
+        return b_hat.count_nonzero_rows() / max(b_hat.shape[0], 1)
+    b, b_hat = np.asarray(b), np.asarray(b_hat)
+    return float(np.mean(np.any(b != b_hat, axis=-1).astype(np.float64)))
+
+
+def compute_ber(b, b_hat):
+    """Fraction of differing entries (metrics.py:98-118)."""
+    return float(np.mean((np.asarray(b) != np.asarray(b_hat)).astype(np.float64)))
+
+
+def count_errors(b, b_hat):
+    """Number of differing entries (metrics.py:172-192)."""
+    return int(np.sum(np.asarray(b) != np.asarray(b_hat)))
+
+
 class _Zeros:
     """Stand-in for ``tf.zeros_like(x)`` of a lazy indicator."""
 

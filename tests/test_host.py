@@ -155,3 +155,12 @@ def test_shard_ranges_cover_exactly():
             assert ranges[0][0] == 0 and sum(c for _, c in ranges) == total
             assert all(ranges[i][0] + ranges[i][1] == ranges[i + 1][0] for i in range(world - 1))
             assert max(c for _, c in ranges) - min(c for _, c in ranges) <= 1
+
+
+def test_metrics_helpers():
+    """compute_bler / compute_ber / count_errors / count_block_errors of sionna/utils/metrics.py:98-223."""
+    import fbgnn as F
+    s = np.array([[0, 0, 1], [0, 0, 0], [1, 1, 0], [0, 0, 0]])
+    z = np.zeros_like(s)
+    assert F.compute_bler(z, s) == 0.5 and F.count_block_errors(z, s) == 2
+    assert F.count_errors(z, s) == 3 and abs(F.compute_ber(z, s) - 0.25) < 1e-12
