@@ -156,6 +156,18 @@ def clip_by_value(grads, lo, hi):
     return [np.clip(g, lo, hi) for g in grads]
 
 
+class CosineDecay:
+    """tf.keras.optimizers.schedules.CosineDecay(initial_learning_rate, decay_steps, alpha=0): the schedule the
+    training notebook suggests for multi-epoch runs.  Callable with the 0-based step."""
+
+    def __init__(self, initial_learning_rate, decay_steps, alpha=0.0):
+        self.initial_learning_rate, self.decay_steps, self.alpha = float(initial_learning_rate), int(decay_steps), float(alpha)
+
+    def __call__(self, step):
+        t = min(max(step, 0), self.decay_steps) / max(self.decay_steps, 1)
+        return self.initial_learning_rate * ((1.0 - self.alpha) * 0.5 * (1.0 + np.cos(np.pi * t)) + self.alpha)
+
+
 class Adam:
     """tf.keras.optimizers.Adam (defaults beta_1=0.9, beta_2=0.999, epsilon=1e-7) on a layer's weight list."""
 

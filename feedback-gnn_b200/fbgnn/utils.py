@@ -22,6 +22,18 @@ def count_block_errors(b, b_hat):
     return int(np.sum(np.any(b != b_hat, axis=-1)))
 
 
+class BinarySource:
+    """Uniform random bits of a given shape (sionna/utils/misc.py ``BinarySource``; the quantum models hold one
+    but never call it).  ``source([batch, n]) -> float32 array``."""
+
+    def __init__(self, dtype=np.float32, seed=None, **kwargs):
+        self._dtype = dtype
+        self._rng = np.random.default_rng(seed)
+
+    def __call__(self, inputs):
+        return self._rng.integers(0, 2, size=tuple(int(x) for x in inputs)).astype(self._dtype)
+
+
 def compute_bler(b, b_hat):
     """Fraction of rows in which ``b`` and ``b_hat`` differ (metrics.py:142-170)."""
     if isinstance(b_hat, ErrorIndicator) and (b is None or _is_zero(b)):
