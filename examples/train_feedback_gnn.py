@@ -111,6 +111,10 @@ def main():
     if args.save:
         F.save_weights(G, args.save)
         print("saved", args.save)
+    shipped = {"n882": "feedback_GNN_n882_k24_wt_4_60_iter_64_16_mixed.npy",
+               "n1270": "feedback_GNN_n1270_k28_wt_10_80_iter_64_16_mixed.npy"}[args.code]
+    F.load_weights(G, os.path.join(F.WEIGHTS_DIR, shipped))
+    print("same evaluation with the weights the reference ships:", json.dumps(pipeline_bler()))
 
 
 if __name__ == "__main__":
