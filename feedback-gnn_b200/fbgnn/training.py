@@ -210,8 +210,9 @@ class _ErrorModel:
     def __init__(self, code, decoders, feedbacks, wt, p0, seed, ctx):
         self.code, self.n, self.wt = code, code.N, wt
         self.channel = Pauli(wt=wt, seed=seed, ctx=ctx)
+        # skip_inactive: frames the first stage decodes do not run the later stages (result-identical)
         self._pipe = Sandwich_BP_GNN_Evaluation_Model(code, decoders, feedbacks, num_layers=len(decoders), wt=wt,
-                                                      p0=p0, ctx=ctx)
+                                                      p0=p0, skip_inactive=True, ctx=ctx)
 
     def __call__(self, batch_size, ebno_db):
         B, p = int(np.asarray(batch_size)), float(np.asarray(ebno_db))
