@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """The reference's full training recipe for the feedback GNN, TF-free and scaled to minutes
-(examples/Generate_dataset.ipynb + examples/Feedback_GNN.ipynb of the reference, [[882,24]]):
+(examples/Generate_dataset.ipynb + examples/Feedback_GNN.ipynb of the reference; [[882,24]] or [[1270,28]]):
 
   1. "easy" strings: fixed-weight errors that BP4(64) alone fails on                       (BP4_Error_Model)
   2. coarse GNN: train with BP4(16) -> GNN -> BP4(16) on the easy strings
@@ -51,6 +51,7 @@ def train(code, G, x, z, num_iter1, num_iter2, lr, bs, max_iters, rng, tag):
 
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--code", choices=["n882", "n1270"], default="n882")
     ap.add_argument("--frames-per-weight", type=int, default=200000)
     ap.add_argument("--max-iters", type=int, default=8000)
     ap.add_argument("--bs", type=int, default=100)
@@ -60,12 +61,17 @@ def main():
     ap.add_argument("--save", default=None)
     args = ap.parse_args()
     rng = np.random.default_rng(args.seed)
-    code = F.create_QC_GHP_codes(63, F.create_cyclic_permuting_matrix(7, [27, 54, 0]), [0, 1, 6])
+    if args.code == "n882":
+        code = F.create_QC_GHP_codes(63, F.create_cyclic_permuting_matrix(7, [27, 54, 0]), [0, 1, 6])
+        weights, shipped_file, eval_ps = list(range(4, 61)), "feedback_GNN_n882_k24_wt_4_60_iter_64_16_mixed.npy", (0.12, 0.10)
+    else:
+        code = F.create_QC_GHP_codes(127, np.array([[0, -1, 51, 52, -1], [-1, 0, -1, 111, 20], [0, -1, 98, -1, 122],
+                                                    [0, 80, -1, 119, -1], [-1, 0, 5, -1, 106]]), [0, 1, 7], name="GHP_n1270_k28")
+        weights, shipped_file, eval_ps = list(range(10, 81)), "feedback_GNN_n1270_k28_wt_10_80_iter_64_16_mixed.npy", (0.13, 0.11)
     new_gnn = lambda: F.Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, reduce_op="mean",
                                      activation="tanh", use_bias=True)
     dec64 = F.QLDPCBPDecoder(code, num_iter=64, normalization_factor=1.0, cn_type="boxplus-phi")
-    weights = list(range(4, 61))
-    report = {}
+    report = {"code": args.code}
 
     t0 = time.time()
     ex, ez = collect(F.BP4_Error_Model(code, dec64, wt=True, seed=args.seed), weights, args.frames_per_weight)
@@ -97,8 +103,8 @@ def main():
         return {"frames": int(c[0]), "block_errors": int(c[2]), "bler": float(c[2]) / float(c[0]), "bp_only_failures": int(c[3])}
 
     shipped = new_gnn()
-    F.load_weights(shipped, os.path.join(F.WEIGHTS_DIR, "feedback_GNN_n882_k24_wt_4_60_iter_64_16_mixed.npy"))
-    for p in (0.12, 0.10):
+    F.load_weights(shipped, os.path.join(F.WEIGHTS_DIR, shipped_file))
+    for p in eval_ps:
         report[f"p={p}"] = {"trained_here": pipeline_bler(G, p), "coarse_here": pipeline_bler(G_coarse, p),
                             "shipped": pipeline_bler(shipped, p)}
         print(f"5. p={p}:", json.dumps(report[f"p={p}"]), flush=True)
