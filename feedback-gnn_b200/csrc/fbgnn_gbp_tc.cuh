@@ -241,15 +241,33 @@ __device__ __forceinline__ int recv_tc(const Grp &g, int col_base, const float *
     return ssum;
 }
 
+// The packed operand tiles (57 - 90 KB) come into shared memory with bulk asynchronous copies (TMA, 1-D form):
+// one thread posts the transfers against an mbarrier, nobody spends load / store instructions on them, and the
+// tensor core later reads them through the same (async) proxy that wrote them.
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_saddr, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_saddr), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+
 __device__ __forceinline__ Grp cta_setup(float *sm, const float *__restrict__ wsrc, int nfloats, uint64_t *bars, uint32_t *tslot) {
-    for (int i = threadIdx.x * 4; i < nfloats; i += blockDim.x * 4)
-        *reinterpret_cast<float4 *>(sm + i) = *reinterpret_cast<const float4 *>(wsrc + i);
+    __shared__ uint64_t load_bar;
     if (threadIdx.x < 32) tmem_alloc(tslot, 256);
-    if (threadIdx.x == 32) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); }
-    fence_async_smem();
+    if (threadIdx.x == 32) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&load_bar, 1);
+        fence_async_smem();
+        const uint32_t bytes = (uint32_t)nfloats * 4u, bar = smem_u32(&load_bar), dst = smem_u32(sm);
+        mbar_expect_tx(bar, bytes);
+        constexpr uint32_t CHUNK = 32768;                        // multiples of 16 bytes
+        for (uint32_t off = 0; off < bytes; off += CHUNK)
+            bulk_g2s(dst + off, reinterpret_cast<const char *>(wsrc) + off, min(CHUNK, bytes - off), bar);
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    mbar_wait(smem_u32(&load_bar), 0);
     Grp g;
     g.gid = threadIdx.x >> 7;
     const int t = threadIdx.x & 127;
