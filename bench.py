@@ -336,6 +336,10 @@ def main():
                 "fp32_issue_peak_ginstr_s": fma_peak / 1e9,
                 "whole_step_frac": value * TE_PER_FRAME / (sfu_peak * world),
                 "hbm_peak_gbs": _measured_peaks().get("hbm_gbs"),
+                # the same launch against the HBM roofline (why HBM is not the bound): ncu DRAM bytes / launch time
+                "hbm_achieved_gbs": (7893504 / 2368 * B) / (k_ms * 1e-3) / 1e9,
+                "hbm_frac": ((7893504 / 2368 * B) / (k_ms * 1e-3) / 1e9) / _measured_peaks().get("hbm_gbs")
+                            if _measured_peaks().get("hbm_gbs") else None,
                 "note": "algorithmic TE count of SURVEY.md 8(d) / measured MUFU peak; the shipped path evaluates "
                         "exp/log in bit-exact software (FP32 pipe) so its own bound is the FP32 issue rate "
                         "(see profiles/ for sm issue utilisation)"}
