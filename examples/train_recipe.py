@@ -64,19 +64,23 @@ def main():
     if args.code == "n882":
         code = F.create_QC_GHP_codes(63, F.create_cyclic_permuting_matrix(7, [27, 54, 0]), [0, 1, 6])
         weights, shipped_file, eval_ps = list(range(4, 61)), "feedback_GNN_n882_k24_wt_4_60_iter_64_16_mixed.npy", (0.12, 0.10)
+        easy_weights, split = weights, None
     else:
         code = F.create_QC_GHP_codes(127, np.array([[0, -1, 51, 52, -1], [-1, 0, -1, 111, 20], [0, -1, 98, -1, 122],
                                                     [0, 80, -1, 119, -1], [-1, 0, 5, -1, 106]]), [0, 1, 7], name="GHP_n1270_k28")
         weights, shipped_file, eval_ps = list(range(10, 81)), "feedback_GNN_n1270_k28_wt_10_80_iter_64_16_mixed.npy", (0.13, 0.11)
+        # Generate_dataset.ipynb cells 5, 10, 12-13: easy strings of weight 10-60, hard strings of weight 10-80 of which
+        # at most 3000 of weight 61-80 are kept
+        easy_weights, split = list(range(10, 61)), (60, 3000)
     new_gnn = lambda: F.Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, reduce_op="mean",
                                      activation="tanh", use_bias=True)
     dec64 = F.QLDPCBPDecoder(code, num_iter=64, normalization_factor=1.0, cn_type="boxplus-phi")
     report = {"code": args.code}
 
     t0 = time.time()
-    ex, ez = collect(F.BP4_Error_Model(code, dec64, wt=True, seed=args.seed), weights, args.frames_per_weight)
+    ex, ez = collect(F.BP4_Error_Model(code, dec64, wt=True, seed=args.seed), easy_weights, args.frames_per_weight)
     report["easy_strings"] = int(len(ex)); report["easy_s"] = time.time() - t0
-    print(f"1. easy: {len(ex)} BP4(64) failures out of {len(weights) * args.frames_per_weight} strings in {report['easy_s']:.1f} s", flush=True)
+    print(f"1. easy: {len(ex)} BP4(64) failures out of {len(easy_weights) * args.frames_per_weight} strings in {report['easy_s']:.1f} s", flush=True)
 
     G_coarse = new_gnn()
     it, dt = train(code, G_coarse, ex, ez, 16, 16, args.lr, args.bs, args.max_iters, rng, "coarse 16/16")
@@ -87,6 +91,14 @@ def main():
     hx, hz = collect(hard_model, weights, args.frames_per_weight)
     report["hard_strings"] = int(len(hx)); report["hard_s"] = time.time() - t0
     print(f"3. hard: {len(hx)} failures of BP4(64) -> coarse GNN -> BP4(64) in {report['hard_s']:.1f} s", flush=True)
+    if split is not None:
+        wt_of = np.sum(hx | hz, axis=1)
+        lo, hi = np.flatnonzero(wt_of <= split[0]), np.flatnonzero(wt_of > split[0])
+        if len(hi) > split[1]:
+            hi = rng.choice(hi, split[1], replace=False)
+        keep = np.concatenate([lo, hi])
+        hx, hz = hx[keep], hz[keep]
+        print(f"   kept {len(lo)} of weight <= {split[0]} and {len(hi)} above", flush=True)
 
     x_all = np.vstack([ex] + [hx] * args.hard_repeat)
     z_all = np.vstack([ez] + [hz] * args.hard_repeat)
