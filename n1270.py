@@ -58,7 +58,9 @@ factor2 = 1.0
 decoder1 = QLDPCBPDecoder(code=code, num_iter=num_iter1, normalization_factor=factor1, cn_type="boxplus-phi", trainable=False, stage_one=True)
 decoder2 = QLDPCBPDecoder(code=code, num_iter=num_iter2, normalization_factor=factor2, cn_type="boxplus-phi", trainable=False, stage_one=True)
 
-model_eval = Sandwich_BP_GNN_Evaluation_Model(code, [decoder1]+[decoder2]*nG, [G]*nG, num_layers=(nG+1))
+# skip_inactive (extension): frames whose correction already matches the syndrome skip the later rounds.
+# The reference masks those rounds' updates (feedback_gnn.py:339-340), so every output is identical.
+model_eval = Sandwich_BP_GNN_Evaluation_Model(code, [decoder1]+[decoder2]*nG, [G]*nG, num_layers=(nG+1), skip_inactive=True)
 ber_plot.simulate(model_eval,
               ebno_dbs=[p],
               batch_size=bs,
