@@ -178,3 +178,39 @@ def test_second_stage_model_host_contract(codes):
     assert g[0][0, 0] == 0 and g[1][0] == 40 * 3                             # [W0; b0] block: bias row last
     assert g[2][0, 0] == 41 * 3 and g[3][0] == 41 * 3 + 4 * 40               # [W1x; b1x]
     assert len(m.trainable_variables) == 12
+
+
+def test_weights_trained_by_this_framework_load(codes):
+    """weights/feedback_GNN_n882_k24_trained_by_fbgnn.npy: written by save_weights after examples/train_recipe.py
+    (profiles/r01_train_recipe.txt) -- the pickle format the reference's load_weights reads."""
+    import os, pickle
+    import fbgnn as F
+    path = os.path.join(F.WEIGHTS_DIR, "feedback_GNN_n882_k24_trained_by_fbgnn.npy")
+    with open(path, "rb") as f:
+        raw = pickle.load(f)                                   # plain pickle of ndarrays: no custom classes needed
+    assert len(raw) == 12 and all(isinstance(a, np.ndarray) and a.dtype == np.float32 for a in raw)
+    G = F.Feedback_GNN(codes["c882"], 20, 40, 2, "mean", "tanh", True)
+    F.load_weights(G, path)
+    assert [a.shape for a in G.get_weights()] == [a.shape for a in raw] and G.count_params() == 3923
+
+
+@pytest.mark.gpu
+def test_weights_trained_by_this_framework_match_the_shipped_ones(codes, weights):
+    """BP -> (GNN -> BP) x 3 at p = 0.12 on [[882,24]]: the weights trained here and the reference's decode the same
+    40 000 frames with error rates within 15 % of each other (recorded run: 7 772 vs 7 778 per 10^5)."""
+    import os
+    import fbgnn as F
+    code = codes["c882"]
+    d1 = F.QLDPCBPDecoder(code, num_iter=64, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+    d2 = F.QLDPCBPDecoder(code, num_iter=16, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+    res = {}
+    for name in ("trained", "shipped"):
+        G = F.Feedback_GNN(code, 20, 40, 2, "mean", "tanh", True)
+        if name == "trained":
+            F.load_weights(G, os.path.join(F.WEIGHTS_DIR, "feedback_GNN_n882_k24_trained_by_fbgnn.npy"))
+        else:
+            G.set_weights(weights["c882"])
+        m = F.Sandwich_BP_GNN_Evaluation_Model(code, [d1, d2, d2, d2], [G] * 3, num_layers=4, seed=11, skip_inactive=True)
+        res[name] = int(m.run(40000, 0.12, want_flags=False, want_diff=False, want_counters=True)["counters"][2])
+    assert 2400 < res["shipped"] < 3800, res
+    assert abs(res["trained"] - res["shipped"]) <= 0.15 * res["shipped"], res
