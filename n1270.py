@@ -1,77 +1,30 @@
-"""Evaluate BP -> (feedback GNN -> BP) x nG on the [[1270,28]] GHP code.
+#!/usr/bin/env python
+"""Evaluate BP -> (feedback GNN -> BP) x nG on the [[1270,28]] GHP code with the shipped weights.
 
-Same command line and flow as the reference's ``n1270.py`` (``-nG`` rounds of feedback, ``-p``
-physical error rate, ``-id`` GPU); the only change is the import block: the layers come from
+Command line of the reference's ``n1270.py``:  ``python n1270.py -nG 3 -p 0.1 -id 0``  (rounds of feedback, physical
+error rate, GPU).  Prints the same progress table and the final ``at [p], BLER is [...]`` line; the work is done by
 ``fbgnn`` (CUDA, sm_100a) instead of ``sionna.fec.ldpc`` / TensorFlow.
 """
+import argparse
 import os
 import sys
-import argparse
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "feedback-gnn_b200"))
-import numpy as np
 
-argParser = argparse.ArgumentParser()
-argParser.add_argument("-nG", "--num_G", help="Number of rounds of feedback.")
-argParser.add_argument("-p", "--p", help="Physical error rate p to simulate.")
-argParser.add_argument("-id", "--gpu_id", help="GPU id", default="0")
-argParser.add_argument("--batch_size", type=int, default=5000)
-argParser.add_argument("--max_iter", type=int, default=100000)
-args = argParser.parse_args()
+ap = argparse.ArgumentParser()
+ap.add_argument("-nG", "--num_G", required=True, help="Number of rounds of feedback.")
+ap.add_argument("-p", "--p", required=True, help="Physical error rate p to simulate.")
+ap.add_argument("-id", "--gpu_id", default="0", help="GPU id")
+ap.add_argument("--batch_size", type=int, default=5000)
+ap.add_argument("--max_iter", type=int, default=100000)
+args = ap.parse_args()
+os.environ["FBGNN_DEVICE"] = str(int(args.gpu_id))
 
-nG = int(args.num_G)
-p = float(args.p)
-gpu_num = int(args.gpu_id)
-os.environ["FBGNN_DEVICE"] = str(gpu_num)
+import numpy as np                                                                                   # noqa: E402
+import fbgnn                                                                                         # noqa: E402
+from fbgnn.evaluate import evaluate_feedback_gnn                                                     # noqa: E402
 
-from fbgnn import QLDPCBPDecoder, Feedback_GNN, load_weights, WEIGHTS_DIR
-from fbgnn import Sandwich_BP_GNN_Evaluation_Model
-from fbgnn import *
-from fbgnn import PlotBER, device_count
-
-print('Number of GPUs available :', device_count())
-print('Only GPU number', gpu_num, 'used.')
-print(f"Running for {nG} rounds of GNN feedback at p={p} on GPU {gpu_num}.")
-
-GHP_n1270_k28 = create_QC_GHP_codes(127, np.array([[0,-1,51,52,-1],[-1,0,-1,111,20],[0,-1,98,-1,122],[0,80,-1,119,-1],[-1,0,5,-1,106]]), [0,1,7], name="GHP_n1270_k28") # 16 <= d <= 46
-code = GHP_n1270_k28
-
-ber_plot = PlotBER()
-
-bs = args.batch_size
-max_iter = args.max_iter
-
-G = Feedback_GNN(code=code,
-                 num_msg_dims=20,
-                 num_hidden_units=40,
-                 num_mlp_layers=2,
-                 reduce_op="mean",
-                 activation="tanh",
-                 use_bias=True)
-load_weights(G, os.path.join(WEIGHTS_DIR, "feedback_GNN_n1270_k28_wt_10_80_iter_64_16_mixed.npy"))
-
-num_iter1 = 64
-num_iter2 = 16
-factor1 = 1.0
-factor2 = 1.0
-
-decoder1 = QLDPCBPDecoder(code=code, num_iter=num_iter1, normalization_factor=factor1, cn_type="boxplus-phi", trainable=False, stage_one=True)
-decoder2 = QLDPCBPDecoder(code=code, num_iter=num_iter2, normalization_factor=factor2, cn_type="boxplus-phi", trainable=False, stage_one=True)
-
-# skip_inactive (extension): frames whose correction already matches the syndrome skip the later rounds.
-# The reference masks those rounds' updates (feedback_gnn.py:339-340), so every output is identical.
-model_eval = Sandwich_BP_GNN_Evaluation_Model(code, [decoder1]+[decoder2]*nG, [G]*nG, num_layers=(nG+1), skip_inactive=True)
-ber_plot.simulate(model_eval,
-              ebno_dbs=[p],
-              batch_size=bs,
-              num_target_block_errors=100,
-              legend=f"feedback GNN {factor1:.2f} {nG} rounds",
-              soft_estimates=True,
-              max_mc_iter=max_iter,
-              early_stop=True,
-              add_bler=True,
-              show_fig=False,
-              qldpc=True,
-              forward_keyboard_interrupt=False)
-
-print(f"at {ber_plot._snrs[1]}, BLER is {ber_plot._bers[1]}")
+A = np.array([[0, -1, 51, 52, -1], [-1, 0, -1, 111, 20], [0, -1, 98, -1, 122], [0, 80, -1, 119, -1], [-1, 0, 5, -1, 106]])
+code = fbgnn.create_QC_GHP_codes(127, A, [0, 1, 7], name="GHP_n1270_k28")                            # 16 <= d <= 46
+evaluate_feedback_gnn(code, "feedback_GNN_n1270_k28_wt_10_80_iter_64_16_mixed.npy", nG=int(args.num_G), p=float(args.p),
+                      gpu_num=int(args.gpu_id), batch_size=args.batch_size, max_mc_iter=args.max_iter)

@@ -22,7 +22,7 @@ def test_scripts_keep_the_reference_command_line():
     a, b = open(os.path.join(ROOT, "n1270.py")).read(), open(os.path.join(ROOT, "n882.py")).read()
     assert '"-nG"' in a and '"-p"' in a and '"-id"' in a
     assert '"-nG"' not in b and "nG = 5" in b and '"-p"' in b and '"-id"' in b
-    assert "feedback_GNN_n882_k24_wt_4_60_iter_64_16_mixed.npy" in b and "create_cyclic_permuting_matrix(7, [27,54,0])" in b
+    assert "feedback_GNN_n882_k24_wt_4_60_iter_64_16_mixed.npy" in b and "create_cyclic_permuting_matrix(7, [27, 54, 0])" in b
 
 
 @pytest.mark.gpu
