@@ -174,28 +174,23 @@ def main():
         return
     if args.warmup < 3:
         args.warmup = 3
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-
     os.environ.setdefault("FBGNN_DEVICE", str(local_rank))
     import fbgnn as F
     from fbgnn import _ffi
-    from fbgnn.distributed import allreduce_counters
+    from fbgnn.distributed import init_from_env
     ctx = F.default_context()
+    # one process per GPU; the only collective is the counter all-reduce (NCCL inside libfbgnn.so, on ctx's stream)
+    comm = init_from_env(ctx)
     code = build_code()
     B = args.frames_per_step
     per_rank_frames = (args.steps + args.warmup) * B
     model = build_model(code, seed=2, first_frame=rank * per_rank_frames)
 
     def barrier():
-        ctx.sync()
-        if dist is not None:
-            dist.barrier()
-            torch.cuda.synchronize()
+        comm.barrier()                                 # stream sync + one-element all-reduce + stream sync
+
+    def max_over_ranks(x):
+        return float(comm.allreduce_f64([x], "max")[0])
 
     # ---- device-timed throughput: noise sampled in-kernel, nothing leaves the GPU but the counters
     for _ in range(args.warmup):
@@ -210,16 +205,14 @@ def main():
     ctx.timer_start()
     for _ in range(args.steps):
         r = model.run(B, P_NOISE, want_flags=False, want_diff=False, want_counters=True)
-        counters += r["counters"]
+        # the path's one collective, once per step inside the timed region: the global counters a
+        # target-error stopping rule polls (sim_ber, misc.py:710-716)
+        counters = counters + comm.allreduce_sum(r["counters"])
     ms = ctx.timer_stop()
     barrier()
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    if dist is not None:
-        t = torch.tensor([ms], device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        counters = allreduce_counters(counters, device=f"cuda:{local_rank}")
+    ms = max_over_ranks(ms)
     total_frames = args.steps * B * world
     value = total_frames / (ms * 1e-3)
 
@@ -235,10 +228,7 @@ def main():
         fast_counters += model.run(B, P_NOISE, want_flags=False, want_diff=False, want_counters=True)["counters"]
     fast_ms = ctx.timer_stop()
     ctx.set_math("exact")
-    if dist is not None:
-        t = torch.tensor([fast_ms], device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        fast_ms = float(t.item())
+    fast_ms = max_over_ranks(fast_ms)
     fast_value = fast_steps * B * world / (fast_ms * 1e-3)
 
     # ---- the same workload with round skipping (result-identical; what low-p sweeps use)
@@ -253,10 +243,7 @@ def main():
         skip_counters += model.run(B, P_NOISE, want_flags=False, want_diff=False, want_counters=True)["counters"]
     skip_ms = ctx.timer_stop()
     model.skip_inactive = False
-    if dist is not None:
-        t = torch.tensor([skip_ms], device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        skip_ms = float(t.item())
+    skip_ms = max_over_ranks(skip_ms)
     skip_value = skip_steps * B * world / (skip_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers
@@ -286,15 +273,11 @@ def main():
     e2e_ms_dev = ctx.timer_stop()
     e2e_wall = time.perf_counter() - t0
     e2e_ms = max(e2e_ms_dev, e2e_wall * 1e3)          # wall clock includes the Python host side
-    if dist is not None:
-        t = torch.tensor([e2e_ms], device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_ms = float(t.item())
+    e2e_ms = max_over_ranks(e2e_ms)
     e2e_value = e2e_steps * B * world / (e2e_ms * 1e-3)
 
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        comm.close()
         return
 
     # ---- roofline of the dominant kernel (k_bp4, 64 iterations from the constant prior), timed alone
@@ -382,8 +365,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
-    if dist is not None:
-        dist.destroy_process_group()
+    comm.close()
 
 
 def _measured_peaks():

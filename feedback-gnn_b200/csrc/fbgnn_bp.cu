@@ -1,0 +1,153 @@
+// fbgnn_bp.cu -- launch configuration of the BP kernels and the decoder entry points of the C ABI.
+#include "fbgnn_internal.h"
+
+// ------------------------------------------------------------------ launch helpers ------
+// Threads per CTA for the one-frame-per-CTA kernels: the multiple of 32 in [128, 512] that
+// wastes the fewest lanes over the variable-node and check-node passes.
+static int pick_threads(int n_items_a, int n_items_b) {
+    auto eff = [&](int t) {
+        const double pa = (double)((n_items_a + t - 1) / t) * t, pb = (double)((n_items_b + t - 1) / t) * t;
+        return (double)(n_items_a + n_items_b) / (pa + pb);
+    };
+    int best = 256;
+    for (int t = 128; t <= 512; t += 32)
+        if (eff(t) > eff(best) + 0.004) best = t;      // keep 256 unless another size is clearly better
+    return best;
+}
+
+static size_t bp4_smem(const SideDev &X, const SideDev &Z, bool const_prior, bool iter_logits) {
+    return sizeof(float) * ((size_t)X.E + Z.E + ((const_prior ? 2 : 3) + (iter_logits ? 2 : 0)) * (size_t)X.n) +
+           2 * (((size_t)X.n + 1) & ~(size_t)1) + X.m + Z.m + X.n + 16;
+}
+
+template <bool CP, int DV, int DC, typename MATH, bool FPX>
+static int launch_bp4_t(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t smem, int threads) {
+    if (int rc = set_smem(k_bp4<CP, DV, DC, MATH, FPX>, smem, ctx, "quaternary BP")) return rc;
+    k_bp4<CP, DV, DC, MATH, FPX><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+template <int DV, int DC>
+static int launch_bp4_m(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t smem, int threads, bool cp) {
+    if (ctx->math_mode == FBGNN_MATH_FAST)
+        return cp ? launch_bp4_t<true, DV, DC, MathFast, false>(ctx, a, grid, smem, threads)
+                  : launch_bp4_t<false, DV, DC, MathFast, false>(ctx, a, grid, smem, threads);
+    // fixed-point exit: exact arithmetic, regular graph, boxplus-phi, long runs (the bookkeeping costs ~5 %
+    // per unsaturated iteration and a 16-iteration stage does not converge-and-saturate in time)
+    const bool fpx = DV > 0 && a.cn_type == 0 && a.num_iter >= 32 && !a.iter_logits.ptr;
+    if (fpx)
+        return cp ? launch_bp4_t<true, DV, DC, MathExact, true>(ctx, a, grid, smem, threads)
+                  : launch_bp4_t<false, DV, DC, MathExact, true>(ctx, a, grid, smem, threads);
+    return cp ? launch_bp4_t<true, DV, DC, MathExact, false>(ctx, a, grid, smem, threads)
+              : launch_bp4_t<false, DV, DC, MathExact, false>(ctx, a, grid, smem, threads);
+}
+
+// Codes whose per-frame state does not fit the shared memory of an SM: generic kernel with the float arrays in HBM.
+template <typename MATH>
+static int launch_bp4_gstate(fbgnn_ctx *ctx, Bp4Args a, int64_t grid, int threads, bool cp) {
+    const SideDev &X = a.X, &Z = a.Z;
+    const size_t smem = 2 * (((size_t)X.n + 1) & ~(size_t)1) + X.m + Z.m + X.n + 16;
+    a.state_stride = (int64_t)X.E + Z.E + ((cp ? 2 : 3) + (a.iter_logits.ptr ? 2 : 0)) * (int64_t)X.n;
+    CK(cudaMallocAsync(&a.state, sizeof(float) * (size_t)grid * a.state_stride, ctx->stream));
+    int rc;
+    if (cp) {
+        rc = set_smem(k_bp4<true, 0, 0, MATH, false, true>, smem, ctx, "quaternary BP (HBM state)");
+        if (!rc) k_bp4<true, 0, 0, MATH, false, true><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+    } else {
+        rc = set_smem(k_bp4<false, 0, 0, MATH, false, true>, smem, ctx, "quaternary BP (HBM state)");
+        if (!rc) k_bp4<false, 0, 0, MATH, false, true><<<(unsigned)grid, threads, smem, ctx->stream>>>(a);
+    }
+    CK(cudaFreeAsync(a.state, ctx->stream));
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {
+    if (grid <= 0) return 0;
+    const bool cp = a.llr.ptr == nullptr;
+    const size_t smem = bp4_smem(a.X, a.Z, cp, a.iter_logits.ptr != nullptr);
+    const int threads = pick_threads(a.X.n, a.X.m + a.Z.m);
+    if (smem > ctx->smem_optin)
+        return ctx->math_mode == FBGNN_MATH_FAST ? launch_bp4_gstate<MathFast>(ctx, a, grid, threads, cp)
+                                                 : launch_bp4_gstate<MathExact>(ctx, a, grid, threads, cp);
+    // both sides regular with the same degrees -> unrolled instantiation
+    int dv = 0, dc = 0;
+    if (a.X.reg_dv && a.X.reg_dv == a.Z.reg_dv && a.X.reg_dc && a.X.reg_dc == a.Z.reg_dc) { dv = a.X.reg_dv; dc = a.X.reg_dc; }
+    if (dv == 3 && dc == 6) return launch_bp4_m<3, 6>(ctx, a, grid, smem, threads, cp);
+    if (dv == 4 && dc == 8) return launch_bp4_m<4, 8>(ctx, a, grid, smem, threads, cp);
+    if (dv == 5 && dc == 10) return launch_bp4_m<5, 10>(ctx, a, grid, smem, threads, cp);
+    return launch_bp4_m<0, 0>(ctx, a, grid, smem, threads, cp);
+}
+
+// ------------------------------------------------------------------ decoders ------------
+extern "C" int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                                fbgnn_tensor3 llr, float prior, fbgnn_tensor2 synd_x, fbgnn_tensor2 synd_z,
+                                fbgnn_tensor2 Lx, fbgnn_tensor2 Ly, fbgnn_tensor2 Lz, fbgnn_tensor2 x_hat,
+                                fbgnn_tensor2 z_hat, fbgnn_tensor2 x_logit, fbgnn_tensor2 z_logit,
+                                fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z, fbgnn_tensor3 iter_logits) {
+    REQUIRE(code, "code is NULL");
+    REQUIRE(cn_type >= 0 && cn_type <= 2, "unknown cn_type %d", cn_type);
+    REQUIRE(num_iter >= 0 && B >= 0, "num_iter and B must be non-negative");
+    REQUIRE(synd_x.ptr && synd_z.ptr, "syndromes are NULL");
+    fbgnn_ctx *ctx = code->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    Bp4Args a{};
+    a.X = code->X->dev; a.Z = code->Z->dev;
+    a.cn_type = cn_type; a.num_iter = num_iter; a.factor = factor;
+    a.llr = v3<const float>(llr); a.prior = prior;
+    a.sx = v2<const uint8_t>(synd_x); a.sz = v2<const uint8_t>(synd_z);
+    a.Lx = v2<float>(Lx); a.Ly = v2<float>(Ly); a.Lz = v2<float>(Lz);
+    a.xh = v2<uint8_t>(x_hat); a.zh = v2<uint8_t>(z_hat);
+    a.xl = v2<float>(x_logit); a.zl = v2<float>(z_logit);
+    a.msg_x = v2<float>(msg_x); a.msg_z = v2<float>(msg_z);
+    a.iter_logits = v3<float>(iter_logits);
+    return launch_bp4(ctx, a, B);
+}
+
+static size_t bp2_smem(const SideDev &S) { return sizeof(float) * ((size_t)S.E + S.n) + S.m + S.n + 16; }
+
+template <int DV, int DC, typename MATH>
+static int launch_bp2_t(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B, size_t smem) {
+    if (int rc = set_smem(k_bp2<DV, DC, MATH>, smem, ctx, "binary BP")) return rc;
+    k_bp2<DV, DC, MATH><<<(unsigned)B, pick_threads(a.S.n, a.S.m), smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+template <int DV, int DC>
+static int launch_bp2_m(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B, size_t smem) {
+    return ctx->math_mode == FBGNN_MATH_FAST ? launch_bp2_t<DV, DC, MathFast>(ctx, a, B, smem)
+                                             : launch_bp2_t<DV, DC, MathExact>(ctx, a, B, smem);
+}
+
+int launch_bp2(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B) {
+    if (B <= 0) return 0;
+    const size_t smem = bp2_smem(a.S);
+    if (a.S.reg_dv == 3 && a.S.reg_dc == 6) return launch_bp2_m<3, 6>(ctx, a, B, smem);
+    if (a.S.reg_dv == 4 && a.S.reg_dc == 8) return launch_bp2_m<4, 8>(ctx, a, B, smem);
+    if (a.S.reg_dv == 5 && a.S.reg_dc == 10) return launch_bp2_m<5, 10>(ctx, a, B, smem);
+    return launch_bp2_m<0, 0>(ctx, a, B, smem);
+}
+
+extern "C" int fbgnn_bp2_decode(fbgnn_graph *g, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                                fbgnn_tensor2 llr, fbgnn_tensor2 synd, fbgnn_tensor2 soft, fbgnn_tensor2 hard) {
+    REQUIRE(g, "graph is NULL");
+    REQUIRE(cn_type >= 0 && cn_type <= 2, "unknown cn_type %d", cn_type);
+    REQUIRE(num_iter >= 0 && B >= 0, "num_iter and B must be non-negative");
+    REQUIRE(llr.ptr, "llr is NULL");
+    REQUIRE(soft.ptr || hard.ptr, "no output requested");
+    if (int rc = need_decodable(g)) return rc;
+    fbgnn_ctx *ctx = g->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    Bp2Args a{};
+    a.S = g->dev; a.cn_type = cn_type; a.num_iter = num_iter; a.factor = factor;
+    a.llr = v2<const float>(llr); a.synd = v2<const uint8_t>(synd);
+    a.soft = v2<float>(soft); a.hard = v2<uint8_t>(hard);
+    return launch_bp2(ctx, a, B);
+}
+

@@ -1,0 +1,106 @@
+// fbgnn_gnn.cu -- feedback GNN: weight packing, launch selection, C ABI.
+#include "fbgnn_internal.h"
+
+// ------------------------------------------------------------------ feedback GNN --------
+template <int H, int M>
+static void pack_gnn(std::vector<float> &w, const float *W0, const float *b0, const float *W1x,
+                     const float *b1x, const float *W2x, const float *b2x, const float *W1z,
+                     const float *b1z, const float *W2z, const float *b2z, const float *W3, const float *b3) {
+    typedef GnnLayout<H, M> L;
+    w.assign(L::total, 0.0f);
+    auto put = [&](int off, const float *src, int count) { if (src) std::memcpy(&w[off], src, sizeof(float) * count); };
+    put(L::W1x, W1x, 4 * H); put(L::b1x, b1x, H); put(L::W2x, W2x, H * M); put(L::b2x, b2x, M);
+    put(L::W1z, W1z, 4 * H); put(L::b1z, b1z, H); put(L::W2z, W2z, H * M); put(L::b2z, b2z, M);
+    put(L::W3, W3, (2 * M + 3) * H); put(L::b3, b3, H); put(L::W0, W0, H * 3); put(L::b0, b0, 3);
+}
+
+extern "C" int fbgnn_gnn_create(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t activation, int32_t reduce_op,
+                                const float *W0, const float *b0, const float *W1x, const float *b1x,
+                                const float *W2x, const float *b2x, const float *W1z, const float *b1z,
+                                const float *W2z, const float *b2z, const float *W3, const float *b3,
+                                fbgnn_gnn **out) {
+    REQUIRE(ctx && out, "NULL argument");
+    REQUIRE(W0 && W1x && W2x && W1z && W2z && W3, "weight matrices must not be NULL");
+    REQUIRE(activation >= 0 && activation <= 2, "unknown activation %d", activation);
+    REQUIRE(reduce_op >= 0 && reduce_op <= 3, "unknown reduce_op %d", reduce_op);
+    const bool any_b = b0 || b1x || b2x || b1z || b2z || b3, all_b = b0 && b1x && b2x && b1z && b2z && b3;
+    REQUIRE(any_b == all_b, "either all biases or none must be given");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    std::vector<float> w;
+    if (H == 40 && M == 20) pack_gnn<40, 20>(w, W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3);
+    else if (H == 20 && M == 20) pack_gnn<20, 20>(w, W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3);
+    else if (H == 64 && M == 32) pack_gnn<64, 32>(w, W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3);
+    else return fail(FBGNN_E_UNSUPPORTED, "Feedback_GNN with num_hidden_units=%d, num_msg_dims=%d is not "
+                     "compiled into this build (available: 40/20, 20/20, 64/32)", H, M);
+    fbgnn_gnn *g = new fbgnn_gnn();
+    g->ctx = ctx; g->H = H; g->M = M; g->act = activation; g->reduce = reduce_op; g->use_bias = all_b ? 1 : 0;
+    g->total = (int)w.size();
+    CK(cudaMalloc(&g->weights, w.size() * sizeof(float)));
+    CK(cudaMemcpy(g->weights, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    *out = g;
+    return 0;
+}
+
+extern "C" int fbgnn_gnn_destroy(fbgnn_gnn *g) {
+    if (!g) return 0;
+    cudaSetDevice(g->ctx->device);
+    cudaStreamSynchronize(g->ctx->stream);
+    cudaFree(g->weights);
+    delete g;
+    return 0;
+}
+
+template <int H, int M, int DV, bool TB, bool FACT, typename MATH>
+static int launch_gnn_t(fbgnn_ctx *ctx, const GnnArgs &a) {
+    const size_t smem = sizeof(float) * GnnLayout<H, M>::total;
+    if (int rc = set_smem(k_gnn<H, M, DV, TB, FACT, MATH>, smem, ctx, "feedback GNN")) return rc;
+    const int64_t items = a.num_frames * a.X.n;
+    int64_t blocks = (items + 127) / 128;
+    blocks = std::min<int64_t>(blocks, (int64_t)ctx->num_sms * 8);
+    k_gnn<H, M, DV, TB, FACT, MATH><<<(unsigned)blocks, 128, smem, ctx->stream>>>(a);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
+template <int H, int M, int DV, bool TB, bool FACT = true>
+static int launch_gnn_m(fbgnn_ctx *ctx, const GnnArgs &a) {
+    return ctx->math_mode == FBGNN_MATH_FAST ? launch_gnn_t<H, M, DV, TB, FACT, MathFast>(ctx, a)
+                                             : launch_gnn_t<H, M, DV, TB, FACT, MathExact>(ctx, a);
+}
+
+int launch_gnn(fbgnn_ctx *ctx, const fbgnn_gnn *g, GnnArgs &a) {
+    if (a.num_frames <= 0) return 0;
+    a.weights = g->weights; a.act = g->act; a.reduce = g->reduce; a.use_bias = g->use_bias;
+    const bool reg3 = a.X.reg_dv == 3 && a.Z.reg_dv == 3;      // the (3,6)-regular GHP / bivariate codes
+    const bool tb = g->act == FBGNN_ACT_TANH && g->use_bias;   // the shipped configuration
+    const bool fact = g->reduce <= 1;                          // mean / sum: output layer after the reduction
+    if (g->H == 40 && g->M == 20) {
+        if (!fact) return launch_gnn_m<40, 20, 0, false, false>(ctx, a);
+        if (reg3 && tb) return launch_gnn_m<40, 20, 3, true>(ctx, a);
+        if (reg3) return launch_gnn_m<40, 20, 3, false>(ctx, a);
+        return tb ? launch_gnn_m<40, 20, 0, true>(ctx, a) : launch_gnn_m<40, 20, 0, false>(ctx, a);
+    }
+    if (g->H == 20 && g->M == 20) return fact ? launch_gnn_m<20, 20, 0, false>(ctx, a) : launch_gnn_m<20, 20, 0, false, false>(ctx, a);
+    if (g->H == 64 && g->M == 32) return fact ? launch_gnn_m<64, 32, 0, false>(ctx, a) : launch_gnn_m<64, 32, 0, false, false>(ctx, a);
+    return fail(FBGNN_E_UNSUPPORTED, "unsupported GNN dimensions");
+}
+
+extern "C" int fbgnn_gnn_forward(fbgnn_code *code, fbgnn_gnn *gnn, int64_t B, fbgnn_tensor3 h_vn,
+                                 fbgnn_tensor2 logit_hx, fbgnn_tensor2 logit_hz, fbgnn_tensor2 synd_x,
+                                 fbgnn_tensor2 synd_z, fbgnn_tensor3 out) {
+    REQUIRE(code && gnn, "NULL handle");
+    REQUIRE(h_vn.ptr && logit_hx.ptr && logit_hz.ptr && synd_x.ptr && synd_z.ptr && out.ptr, "NULL tensor");
+    REQUIRE(B >= 0, "B must be non-negative");
+    fbgnn_ctx *ctx = code->ctx;
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    GnnArgs a{};
+    a.X = code->X->dev; a.Z = code->Z->dev;
+    a.num_frames = B;
+    a.h_vn = v3<const float>(h_vn);
+    a.logit_hx = v2<const float>(logit_hx); a.logit_hz = v2<const float>(logit_hz);
+    a.sx = v2<const uint8_t>(synd_x); a.sz = v2<const uint8_t>(synd_z);
+    a.out = v3<float>(out);
+    return launch_gnn(ctx, gnn, a);
+}
+

@@ -387,7 +387,7 @@ __device__ void bp4_iter_logits(const Bp4Args &a, const float *mx, const float *
 // GSTATE (codes whose state exceeds the 227 KB of an SM): the float arrays live in the CTA's slice of an HBM
 // scratch buffer (L2-resident while the CTA runs) instead; same code, same arithmetic, same results.
 template <bool CONST_PRIOR, int DV, int DC, typename MATH, bool FPX, bool GSTATE = false>
-__global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
+static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     extern __shared__ float smem[];
     const SideDev &X = a.X, &Z = a.Z;
     const int n = X.n, T = blockDim.x, tid = threadIdx.x;
@@ -557,7 +557,7 @@ struct Bp2Args {
 
 // smem: float msg[E], llr[n]; u8 sb[m], dec[n].  (DV, DC) > 0: regular graph, unrolled (boxplus-phi only).
 template <int DV, int DC, typename MATH>
-__global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
+static __global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
     extern __shared__ float smem[];
     const SideDev &S = a.S;
     const int n = S.n, T = blockDim.x, tid = threadIdx.x;
@@ -841,7 +841,7 @@ __device__ __forceinline__ void gnn_body(const GnnArgs &a, const WSRC w) {
 }
 
 template <int H, int M, int DV, bool TANH_BIAS, bool FACT, typename MATH>
-__global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
+static __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
     extern __shared__ float wsm[];
     for (int i = threadIdx.x; i < GnnLayout<H, M>::total; i += blockDim.x) wsm[i] = a.weights[i];
     __syncthreads();
@@ -989,7 +989,7 @@ __device__ __forceinline__ void gbp_node(const float *__restrict__ w, const floa
 // UpdateCNEmbeddings.call (gnn.py:574-610): one thread per (frame, check), X checks then Z checks.
 // smem: weights[cn_total] + base[H][blockDim]
 template <int D, int H, int M, typename MATH>
-__global__ void __launch_bounds__(128) k_gbp_cn(const GbpArgs a) {
+static __global__ void __launch_bounds__(128) k_gbp_cn(const GbpArgs a) {
     typedef GbpLayout<D, H, M> L;
     extern __shared__ float gsm[];
     float *w = gsm, *base = gsm + L::cn_total + threadIdx.x;
@@ -1050,7 +1050,7 @@ __global__ void __launch_bounds__(128) k_gbp_cn(const GbpArgs a) {
 
 // UpdateVNEmbeddings.call (gnn.py:716-750): one thread per (frame, variable node)
 template <int D, int H, int M, typename MATH>
-__global__ void __launch_bounds__(128) k_gbp_vn(const GbpArgs a) {
+static __global__ void __launch_bounds__(128) k_gbp_vn(const GbpArgs a) {
     typedef GbpLayout<D, H, M> L;
     extern __shared__ float gsm[];
     float *w = gsm, *base = gsm + L::vn_total + threadIdx.x;
@@ -1235,7 +1235,7 @@ __device__ __forceinline__ void gbp_recv_factored(const float *__restrict__ w, c
 
 // initial sender halves of the variable nodes (h_vn as stored), before the first CN update
 template <int D, int H, int M>
-__global__ void __launch_bounds__(128) k_gbp_pre_vn(const GbpArgs a) {
+static __global__ void __launch_bounds__(128) k_gbp_pre_vn(const GbpArgs a) {
     typedef GbpLayout<D, H, M> L;
     extern __shared__ float gsm[];
     float *wp = gsm;                                                   // [2][H][D]
@@ -1260,7 +1260,7 @@ __global__ void __launch_bounds__(128) k_gbp_pre_vn(const GbpArgs a) {
 // UpdateCNEmbeddings.call, factored; also writes the new check embedding's sender half for the VN update.
 // smem: weights[cn_total] + sender-half weights of update_h_vn's msg_mlp_{x,z} [2][H][D]
 template <int D, int H, int M, bool TB, typename MATH>
-__global__ void __launch_bounds__(128, 4) k_gbp_cn_f(const GbpArgs a) {
+static __global__ void __launch_bounds__(128, 4) k_gbp_cn_f(const GbpArgs a) {
     typedef GbpLayout<D, H, M> L;
     extern __shared__ float gsm[];
     float *w = gsm, *wp = gsm + L::cn_total;
@@ -1314,7 +1314,7 @@ __global__ void __launch_bounds__(128, 4) k_gbp_cn_f(const GbpArgs a) {
 
 // UpdateVNEmbeddings.call, factored; also writes the new variable embedding's sender halves for the CN update.
 template <int D, int H, int M, bool TB, typename MATH>
-__global__ void __launch_bounds__(128) k_gbp_vn_f(const GbpArgs a) {
+static __global__ void __launch_bounds__(128) k_gbp_vn_f(const GbpArgs a) {
     typedef GbpLayout<D, H, M> L;
     extern __shared__ float gsm[];
     float *w = gsm, *wp = gsm + L::vn_total;
@@ -1369,7 +1369,7 @@ __global__ void __launch_bounds__(128) k_gbp_vn_f(const GbpArgs a) {
 // embed_to_llr + cal_logit + make_hard_decision (gnn.py:281-314, 358-366): one CTA per frame.
 // smem: float lxp[n], lzp[n] (phi2 of |llr_x'|, |llr_z'|); u8 sgn[n]
 template <int D, typename MATH>
-__global__ void k_gbp_logit(const GbpArgs a) {
+static __global__ void k_gbp_logit(const GbpArgs a) {
     extern __shared__ float lsm[];
     const int n = a.X.n, T = blockDim.x, tid = threadIdx.x;
     const int64_t b = blockIdx.x;
@@ -1465,7 +1465,7 @@ __device__ __forceinline__ float frame_uniform(uint64_t seed, uint64_t frame, ui
 }
 
 // smem: u8 nb[n] (+ u16 idx[n] in fixed-weight mode)
-__global__ void k_sample(const SampleArgs a) {
+static __global__ void k_sample(const SampleArgs a) {
     extern __shared__ uint8_t nb[];
     const int n = a.X.n, T = blockDim.x, tid = threadIdx.x;
     const int64_t b = blockIdx.x;
@@ -1529,7 +1529,7 @@ struct SyndromeArgs {
     View2<const uint8_t> noise;         // (b, v)
     View2<uint8_t> synd;                // (c, b)
 };
-__global__ void k_syndrome(const SyndromeArgs a) {
+static __global__ void k_syndrome(const SyndromeArgs a) {
     extern __shared__ uint8_t nb[];
     const int64_t b = blockIdx.x;
     for (int v = threadIdx.x; v < a.S.n; v += blockDim.x) nb[v] = a.noise(b, v) & 1;
@@ -1568,7 +1568,7 @@ __device__ __forceinline__ unsigned long long osd_key(float x, int idx) {
 }
 
 // smem: max(npad * 8, W * Rp * 4) bytes shared by the sort keys and the matrix; u16 order[n], inv[n], piv[R]
-__global__ void __launch_bounds__(256) k_osd0(const Osd0Args a) {
+static __global__ void __launch_bounds__(256) k_osd0(const Osd0Args a) {
     extern __shared__ unsigned long long osd_smem[];
     const SideDev &S = a.S;
     const int n = S.n, R = S.m, T = blockDim.x, tid = threadIdx.x;
@@ -1674,7 +1674,7 @@ struct OsdLlrArgs {
     float *out;                         // [B][3][n] (planes 0, 1 written)
 };
 template <typename MATH>
-__global__ void k_osd_llr(const OsdLlrArgs a) {
+static __global__ void k_osd_llr(const OsdLlrArgs a) {
     const int64_t items = a.num_frames * a.n;
     for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
         const int64_t fi = it / a.n;
@@ -1701,7 +1701,7 @@ struct FinalArgs {
 };
 
 // smem: u8 d[n]; u32 xw[W], zw[W]
-__global__ void k_final(const FinalArgs a) {
+static __global__ void k_final(const FinalArgs a) {
     extern __shared__ uint8_t dsm[];
     const int n = a.X.n, T = blockDim.x, tid = threadIdx.x, W = (n + 31) / 32;
     const int64_t b = blockIdx.x;
@@ -1761,7 +1761,7 @@ __global__ void k_final(const FinalArgs a) {
 }
 
 // ------------------------------------------------------------------ probes ------------
-__global__ void k_math_probe(int fn, const float *x, float *y, int64_t n) {
+static __global__ void k_math_probe(int fn, const float *x, float *y, int64_t n) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float v = x[i];
@@ -1780,7 +1780,7 @@ __global__ void k_math_probe(int fn, const float *x, float *y, int64_t n) {
 }
 
 // MUFU throughput: chains of ex2.approx, 8 independent chains per thread
-__global__ void k_sfu_peak(float *out, int iters) {
+static __global__ void k_sfu_peak(float *out, int iters) {
     float v[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) v[j] = -1.0f - 0.001f * (float)(threadIdx.x + j);
@@ -1795,7 +1795,7 @@ __global__ void k_sfu_peak(float *out, int iters) {
 }
 
 // FP32 FMA issue rate: 8 independent FFMA chains per thread
-__global__ void k_fma_peak(float *out, int iters) {
+static __global__ void k_fma_peak(float *out, int iters) {
     float v[8];
     const float a = 0.999f + 1e-6f * (float)threadIdx.x, c = 1e-3f;
 #pragma unroll
@@ -1810,7 +1810,7 @@ __global__ void k_fma_peak(float *out, int iters) {
     if (s == 123.456f) out[0] = s;
 }
 
-__global__ void k_fill(uint32_t *p, int64_t n, uint32_t v) {
+static __global__ void k_fill(uint32_t *p, int64_t n, uint32_t v) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         p[i] = v;
 }

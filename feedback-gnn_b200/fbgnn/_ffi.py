@@ -89,6 +89,7 @@ _SIGNATURES = {
     "fbgnn_gbp_create": [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(_f32p), _vpp],
     "fbgnn_gbp_destroy": [C.c_void_p],
     "fbgnn_gbp_set_gemm": [C.c_void_p, C.c_int32],
+    "fbgnn_gbp_set_chunk": [C.c_void_p, C.c_int64],
     "fbgnn_second_stage_grad": [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_int64, Tensor3, Tensor2,
                                 Tensor2, Tensor2, Tensor2, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_float)],
     "fbgnn_gbp_decode": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int64, Tensor2, Tensor2, Tensor3, Tensor3, Tensor2,
@@ -98,6 +99,13 @@ _SIGNATURES = {
     "fbgnn_bsc_pipeline_run": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
                                C.c_uint64, C.c_uint64, C.c_int64, Tensor2, C.c_void_p, C.POINTER(C.c_int64),
                                C.c_void_p, _i32p],
+    "fbgnn_comm_unique_id": [C.POINTER(C.c_uint8)],
+    "fbgnn_comm_init_rank": [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)],
+    "fbgnn_comm_info": [C.c_void_p, _i32p, _i32p, _i32p],
+    "fbgnn_allreduce_counters": [C.c_void_p, C.POINTER(C.c_int64), C.c_int32],
+    "fbgnn_allreduce_f64": [C.c_void_p, C.POINTER(C.c_double), C.c_int32, C.c_int32],
+    "fbgnn_comm_barrier": [C.c_void_p],
+    "fbgnn_comm_destroy": [C.c_void_p],
     "fbgnn_sfu_peak": [C.c_void_p, C.POINTER(C.c_double)],
     "fbgnn_fma_peak": [C.c_void_p, C.POINTER(C.c_double)],
     "fbgnn_math_probe": [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int64],

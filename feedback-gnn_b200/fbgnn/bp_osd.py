@@ -52,7 +52,9 @@ class OSD0_Decoder:
     call = __call__
 
 
-def _indicators(flags, rows):
+def _indicators(flags, rows, dense=None):
+    """(zeros_like(ls_hat), ls_hat) of the reference (bp_osd.py:196-197, 273-274) as lazy indicators; ``dense``
+    materialises ls_hat when the model kept the residual errors."""
     cache = {}
 
     def host_flags():
@@ -60,11 +62,9 @@ def _indicators(flags, rows):
             cache["f"] = flags.numpy()
         return cache["f"]
 
-    def dense():
-        raise _ffi.FbgnnError("dense ls_hat is not kept by the OSD models; use frame_flags()")
-
     ls_hat = ErrorIndicator(lambda: (host_flags() >> 1) & 1, rows, dense)
-    zeros = ErrorIndicator(lambda: np.zeros_like(host_flags()), rows, dense)
+    zeros = ErrorIndicator(lambda: np.zeros_like(host_flags()), rows,
+                           None if dense is None else (lambda: np.zeros((len(host_flags()), rows), np.int64)))
     return zeros, ls_hat
 
 
@@ -88,8 +88,14 @@ class BP4_OSD_Model:
         return self._inner.run(batch_size, p, **kw)
 
     def __call__(self, batch_size, ebno_db):
-        res = self._inner.run(batch_size, float(np.asarray(ebno_db)), want_diff=False)
-        return _indicators(res["flags"], self.code.lx.shape[0] + self.code.lz.shape[0])
+        res = self._inner.run(batch_size, float(np.asarray(ebno_db)), want_diff=True)
+        xd, zd = res["x_diff"], res["z_diff"]
+
+        def dense():      # ls_hat = [lz . x_diff ; lx . z_diff] (bp_osd.py:188-194)
+            x, z = xd.numpy().astype(np.int64), zd.numpy().astype(np.int64)
+            return np.concatenate([(x @ np.asarray(self.code.lz).T) & 1, (z @ np.asarray(self.code.lx).T) & 1], axis=1)
+
+        return _indicators(res["flags"], self.code.lx.shape[0] + self.code.lz.shape[0], dense)
 
     call = __call__
 

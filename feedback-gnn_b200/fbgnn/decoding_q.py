@@ -44,12 +44,13 @@ class QLDPCBPDecoder:
                  **kwargs):
         if cn_type not in CN_TYPES:
             raise ValueError('Unknown node type.')
-        if trainable and not stage_two:
+        if trainable and not (stage_one or stage_two):
             # In the reference `trainable` creates no variables (every weight is commented out, decoding_q.py:
             # 114-135, 240-242, 748-749); it only switches the per-iteration soft syndromes on (:743, :794), over the
             # rows of hx_perp / hz_perp unless stage_one / stage_two select hz / hx (:35-37).  The notebook that
-            # uses it passes stage_two=True as well (Feedback_GNN.ipynb cell 8); that combination is supported.
-            raise NotImplementedError("trainable=True without stage_two=True (soft syndromes over the dense "
+            # uses it passes stage_two=True as well (Feedback_GNN.ipynb cell 8); that combination is supported, and
+            # with stage_one=True the flag has no effect at all (the stage_one return comes first, :792-793).
+            raise NotImplementedError("trainable=True without stage_one / stage_two (soft syndromes over the dense "
                                       "hx_perp / hz_perp rows) is not provided; pass stage_two=True")
         self._code = code
         self._cn_type = cn_type

@@ -62,7 +62,7 @@ class Feedback_GNN:
         self._use_bias = bool(use_bias)
         self._ctx = ctx
         self._weights = None
-        self._handle = None
+        self._handles = {}
         self._is_built = False
 
     # -- Keras-like weight handling --------------------------------------------------------
@@ -105,12 +105,12 @@ class Feedback_GNN:
         return int(sum(w.size for w in self._weights))
 
     def _drop_handle(self):
-        if getattr(self, "_handle", None) is not None:
+        for h in getattr(self, "_handles", {}).values():
             try:
-                _ffi.lib().fbgnn_gnn_destroy(self._handle)
+                _ffi.lib().fbgnn_gnn_destroy(h[1])
             except Exception:
                 pass
-            self._handle = None
+        self._handles = {}
 
     def __del__(self):
         self._drop_handle()
@@ -118,9 +118,10 @@ class Feedback_GNN:
     def device_handle(self, ctx=None):
         """fbgnn_gnn handle holding the current weights."""
         self.build()
-        if self._handle is None:
+        ctx = ctx or self._ctx or _ffi.default_context()
+        ent = self._handles.get(id(ctx))          # one device copy of the weights per context (GPU)
+        if ent is None or ent[0] is not ctx:
             import ctypes as C
-            ctx = ctx or self._ctx or _ffi.default_context()
             if self._use_bias:
                 W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3 = self._weights
             else:
@@ -131,8 +132,8 @@ class Feedback_GNN:
             _ffi.call("fbgnn_gnn_create", ctx.handle, self._num_hidden_units, self._num_msg_dims,
                       ACTS[self._activation], REDUCE[self._reduce_op],
                       *[fp(a) for a in (W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3)], C.byref(h))
-            self._handle = h
-        return self._handle
+            self._handles[id(ctx)] = (ctx, h)
+        return self._handles[id(ctx)][1]
 
     # -- forward ---------------------------------------------------------------------------
     def __call__(self, inputs):
@@ -164,9 +165,13 @@ class Feedback_GNN:
 class ErrorIndicator:
     """Lazy ``[B, rows]`` 0/1 matrix whose row-wise "any" is already known (see module doc)."""
 
-    def __init__(self, flags_fn, rows, materialise):
+    def __init__(self, flags_fn, rows, materialise=None):
         self._flags_fn, self._rows, self._materialise = flags_fn, rows, materialise
         self._flags = None
+
+    def has_dense(self):
+        """False when only the per-frame flags exist (the dense matrix was not kept on the device)."""
+        return self._materialise is not None
 
     def frame_flags(self):
         """uint8 [B]: 1 where the row of the matrix has any non-zero entry."""
@@ -182,6 +187,8 @@ class ErrorIndicator:
         return int(self.frame_flags().sum())
 
     def numpy(self):
+        if self._materialise is None:
+            raise _ffi.FbgnnError("the dense matrix is not kept by this model; use frame_flags() / count_nonzero_rows()")
         return self._materialise()
 
     def __array__(self, dtype=None, copy=None):
@@ -256,6 +263,8 @@ class Sandwich_BP_GNN_Evaluation_Model:
         keep = None
         if noise is not None:
             keep = (ctx.asarray(_to_u8(noise[0]), np.uint8), ctx.asarray(_to_u8(noise[1]), np.uint8))
+            if keep[0].shape != (B, dev.n) or keep[1].shape != (B, dev.n):
+                raise ValueError(f"noise_x / noise_z must have shape [{B},{dev.n}], got {keep[0].shape} / {keep[1].shape}")
             nx, nz = keep[0].t2(), keep[1].t2()
         flags = ctx.empty((B,), np.uint8) if want_flags else None
         xd = ctx.empty((B, dev.n), np.uint8) if want_diff else None
@@ -345,6 +354,8 @@ class BP_BSC_Model:
         keep = None
         if noise is not None:
             keep = ctx.asarray(_to_u8(noise), np.uint8)
+            if keep.shape != (B, self.n):
+                raise ValueError(f"noise must have shape [{B},{self.n}], got {keep.shape}")
             nz = keep.t2()
         d = self.decoder
         _ffi.call("fbgnn_bsc_pipeline_run", g.handle, lg.handle if lg is not None else None,
@@ -382,10 +393,7 @@ class BP_BSC_Model:
                 cache["f"] = flags.numpy()
             return cache["f"]
 
-        def dense():
-            raise _ffi.FbgnnError("dense s_hat / ls_hat of BP_BSC_Model are not kept; use frame_flags()")
-
-        return (ErrorIndicator(lambda: host_flags() & 1, self.pcm.shape[0], dense),
-                ErrorIndicator(lambda: (host_flags() >> 1) & 1, self.logical_pcm.shape[0], dense))
+        return (ErrorIndicator(lambda: host_flags() & 1, self.pcm.shape[0]),
+                ErrorIndicator(lambda: (host_flags() >> 1) & 1, self.logical_pcm.shape[0]))
 
     call = __call__

@@ -18,19 +18,32 @@ import numpy as np
 WEIGHTS_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "weights")
 
 
+# everything a weights file may name: numpy's array reconstruction helpers (old and new module paths) and the
+# TensorFlow tensor constructor the shipped files were written with.  Anything else is refused, so loading a
+# weights file cannot run arbitrary code (plain pickle.load, as the reference uses, can).
+_ALLOWED_NUMPY = {("multiarray", "_reconstruct"), ("multiarray", "scalar"), ("numeric", "_frombuffer"),
+                  ("", "ndarray"), ("", "dtype")}
+
+
 class _WeightsUnpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module.startswith("tensorflow"):
             if name == "convert_to_tensor":
                 return lambda x, *a, **k: np.asarray(x)
             raise pickle.UnpicklingError(f"unsupported TensorFlow object {module}.{name} in weights file")
-        if module.startswith("numpy.core"):
-            module = module.replace("numpy.core", "numpy._core", 1)
-            try:
-                return super().find_class(module, name)
-            except (ImportError, AttributeError):
-                return super().find_class(module.replace("numpy._core", "numpy.core", 1), name)
-        return super().find_class(module, name)
+        for root in ("numpy.core", "numpy._core", "numpy"):
+            if module == root or module.startswith(root + "."):
+                sub = module[len(root):].lstrip(".")
+                if (sub, name) not in _ALLOWED_NUMPY:
+                    break
+                target = "numpy._core" + ("." + sub if sub else "") if root != "numpy" else module
+                if sub == "":
+                    return getattr(np, name)
+                try:
+                    return super().find_class(target, name)
+                except (ImportError, AttributeError):
+                    return super().find_class("numpy.core." + sub, name)
+        raise pickle.UnpicklingError(f"refusing to load {module}.{name} from a weights file")
 
 
 def read_weights(model_path):
@@ -80,7 +93,7 @@ class GNN_BP4:
     def __init__(self, code, num_embed_dims, num_msg_dims, num_hidden_units, num_mlp_layers, num_iter,
                  reduce_op="mean", activation="tanh", clip_llr_to=None, use_attributes=False,
                  node_attribute_dims=0, msg_attribute_dims=0, use_bias=False, input_embed=False,
-                 loss_type="boxplus-phi", ctx=None, gemm="fma"):
+                 loss_type="boxplus-phi", ctx=None, gemm="fma", chunk_frames=0):
         if int(num_mlp_layers) != 2 or use_attributes:
             raise NotImplementedError("this build provides 2-layer MLPs without node/edge attributes")
         if loss_type != "boxplus-phi":
@@ -90,6 +103,7 @@ class GNN_BP4:
         if gemm not in GEMM_MODES:
             raise ValueError("gemm must be 'fma' or 'tf32x3'")
         self._gemm = gemm
+        self._chunk_frames = int(chunk_frames)          # extension: frames per pass over the batch (0 = automatic)
         self._code = code
         self._d, self._M, self._H = int(num_embed_dims), int(num_msg_dims), int(num_hidden_units)
         self._num_iter = int(num_iter)
@@ -174,6 +188,7 @@ class GNN_BP4:
                       REDUCE[self._reduce_op], arr, C.byref(h))
             self._handle = h
             _ffi.call("fbgnn_gbp_set_gemm", h, GEMM_MODES[self._gemm])
+            _ffi.call("fbgnn_gbp_set_chunk", h, self._chunk_frames)
         return self._handle
 
     def __call__(self, inputs):

@@ -44,11 +44,15 @@ def compute_bler(b, b_hat):
 
 def compute_ber(b, b_hat):
     """Fraction of differing entries (metrics.py:98-118)."""
+    if isinstance(b_hat, ErrorIndicator) and not b_hat.has_dense() and (b is None or _is_zero(b)):
+        return b_hat.count_nonzero_rows() / max(b_hat.shape[0] * b_hat.shape[1], 1)     # one count per frame in error
     return float(np.mean((np.asarray(b) != np.asarray(b_hat)).astype(np.float64)))
 
 
 def count_errors(b, b_hat):
     """Number of differing entries (metrics.py:172-192)."""
+    if isinstance(b_hat, ErrorIndicator) and not b_hat.has_dense() and (b is None or _is_zero(b)):
+        return b_hat.count_nonzero_rows()
     return int(np.sum(np.asarray(b) != np.asarray(b_hat)))
 
 
@@ -135,8 +139,17 @@ def sim_ber(mc_fun, ebno_dbs, batch_size, max_mc_iter, soft_estimates=False, num
                     block_e = count_block_errors(zeros_like(l_hat), l_hat)
                     bit_n = s_hat.shape[0]
                     block_n = l_hat.shape[0]
+                elif isinstance(outputs[1], ErrorIndicator) and not outputs[1].has_dense():
+                    # OSD / BSC models driven with qldpc=False (OSD.ipynb cells 2-3): the device keeps one
+                    # flag per frame, not the dense ls_hat, so a frame in error counts as one "bit" error
+                    l_hat = outputs[1]
+                    bit_e = block_e = l_hat.count_nonzero_rows()
+                    bit_n = l_hat.shape[0] * l_hat.shape[1]
+                    block_n = l_hat.shape[0]
                 else:
-                    b, b_hat = np.asarray(outputs[0]), np.asarray(outputs[1])
+                    b = outputs[0]
+                    b = np.zeros(b.shape, np.int64) if isinstance(b, ErrorIndicator) and not b.has_dense() else np.asarray(b)
+                    b_hat = np.asarray(outputs[1])
                     if soft_estimates:
                         b_hat = hard_decisions(b_hat)
                     bit_e = int(np.sum(b != b_hat))

@@ -228,6 +228,9 @@ int fbgnn_second_stage_grad(fbgnn_code *code, fbgnn_gnn *gnn, int32_t num_iter, 
 /* Select how GNN_BP4's per-node matrix products are evaluated (FBGNN_GEMM_*).  The tensor-core form
  * (fbgnn_gbp_tc.cuh) needs reduce_op mean / sum and tanh; otherwise FBGNN_E_UNSUPPORTED. */
 int fbgnn_gbp_set_gemm(fbgnn_gbp *gbp, int32_t mode);
+/* The embeddings of a batch live in HBM ((n + m)(d + H) + n H floats per frame); fbgnn_gbp_decode walks the batch
+ * in chunks of a few GB.  max_frames > 0 caps the chunk (tests force several chunks with a ragged tail); 0 = automatic. */
+int fbgnn_gbp_set_chunk(fbgnn_gbp *gbp, int64_t max_frames);
 /* GNN_BP4.call: synd_x uint8 [B,m_x], synd_z uint8 [B,m_z] contiguous, batch first (gnn.py:385-386);
  * x_logit float32 (iteration, row, b) with m_z + k_z rows = [hz_logit; lz_logit], z_logit with m_x + k_x rows
  * = [hx_logit; lx_logit] (either may be NULL); x_hat, z_hat uint8 (v, b): the argmin decision. */
@@ -275,6 +278,31 @@ int fbgnn_bsc_pipeline_run(fbgnn_graph *graph, fbgnn_graph *logical, int32_t cn_
                            int32_t num_iter, float factor, float llr_const, float p, uint64_t seed,
                            uint64_t first_frame, int64_t B, fbgnn_tensor2 noise, uint8_t *flags,
                            int64_t *counters, fbgnn_graph *osd_basis, const int32_t *osd_pivot);
+
+/* ---- multi-GPU: the one collective of the path ------------------------- */
+/* Monte-Carlo frames shard across the GPUs of a box by global frame id; nothing but the counters is
+ * ever exchanged.  One process per GPU: rank 0 makes an id (fbgnn_comm_unique_id), hands the 128 bytes
+ * to the other ranks by any host channel (fbgnn/distributed.py uses a rendezvous file), and every rank
+ * attaches its context with fbgnn_comm_init_rank (ncclCommInitRank; collective).  NCCL is bound at run
+ * time (libnccl.so.2, or $FBGNN_NCCL_LIB); a context without a communicator is a 1-rank job and the
+ * reductions below are identities.  The reference has no counterpart (one process per --gpu_id,
+ * n1270.py:10-26); the host loop that needs the global counters is sim_ber's stopping rule
+ * (sionna/utils/misc.py:710-716). */
+#define FBGNN_COMM_ID_BYTES 128
+#define FBGNN_COMM_MAX_ELEMS 64
+#define FBGNN_RED_SUM 0
+#define FBGNN_RED_MAX 1
+int fbgnn_comm_unique_id(uint8_t id[FBGNN_COMM_ID_BYTES]);
+int fbgnn_comm_init_rank(fbgnn_ctx *ctx, int32_t nranks, int32_t rank, const uint8_t id[FBGNN_COMM_ID_BYTES]);
+int fbgnn_comm_info(fbgnn_ctx *ctx, int32_t *nranks, int32_t *rank, int32_t *nccl_version);
+/* in-place sum over ranks of HOST int64 counters[count] (count <= FBGNN_COMM_MAX_ELEMS): staged through the
+ * context's device buffer, ncclAllReduce on the context's stream, synchronises. */
+int fbgnn_allreduce_counters(fbgnn_ctx *ctx, int64_t *counters, int32_t count);
+/* the same for HOST doubles with FBGNN_RED_SUM / FBGNN_RED_MAX (bench.py: max over ranks of the device time) */
+int fbgnn_allreduce_f64(fbgnn_ctx *ctx, double *values, int32_t count, int32_t op);
+/* stream sync + a one-element all-reduce */
+int fbgnn_comm_barrier(fbgnn_ctx *ctx);
+int fbgnn_comm_destroy(fbgnn_ctx *ctx);
 
 /* ---- measurement helpers ---------------------------------------------------------------- */
 /* Measured MUFU (ex2.approx) throughput of the device in transcendental evaluations / s:

@@ -5,7 +5,13 @@ BASELINE.json configs[3]: the [[882,24]] code, nG = 5 (n882.py), 10^8 frames spl
 global frame-id ranges, one per GPU; the only collective is the sum of the four int64 counters.
 
     python sweep.py --code n882 -nG 5 -p 0.05 --frames 100000000
-    torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 sweep.py --code n882 -nG 5 -p 0.05 --frames 1e8
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 sweep.py --code n882 \
+        -nG 5 -p 0.05 --frames 1e8 --checkpoint counters.json
+
+One process per GPU (any launcher that exports RANK / WORLD_SIZE / LOCAL_RANK); the counter all-reduce is NCCL
+inside libfbgnn.so -- nothing here imports PyTorch.  With --checkpoint every rank records its local counters and
+the index of its last finished batch every --checkpoint_every batches; re-running the same command resumes
+from there (a 10^8-frame run that dies after an hour loses at most a few batches).
 
 Results are independent of the number of GPUs and of the batch size (the noise of a frame is a
 function of (seed, global frame id) only).  Rounds are skipped for frames whose correction already
@@ -32,19 +38,16 @@ def main():
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--target_block_errors", type=int, default=None)
     ap.add_argument("--full_work", action="store_true", help="run every round on every frame (as the reference does)")
+    ap.add_argument("--checkpoint", default=None, help="counters.json: per-rank progress, resumed when present")
+    ap.add_argument("--checkpoint_every", type=int, default=8, help="batches between checkpoint writes")
+    ap.add_argument("--stop_after_batches", type=int, default=None, help="(tests) die after this many batches")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    device = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
-        device = f"cuda:{local_rank}"
     os.environ.setdefault("FBGNN_DEVICE", str(local_rank))
     import fbgnn as F
-    from fbgnn.distributed import run_sharded
+    from fbgnn.distributed import init_from_env, run_sharded
+    comm = init_from_env()
     if args.code == "n882":
         code = F.create_QC_GHP_codes(63, F.create_cyclic_permuting_matrix(7, [27, 54, 0]), [0, 1, 6])
         wfile = "feedback_GNN_n882_k24_wt_4_60_iter_64_16_mixed.npy"
@@ -62,13 +65,49 @@ def main():
     model = F.Sandwich_BP_GNN_Evaluation_Model(code, [d1] + [d2] * nG, [G] * nG, num_layers=nG + 1, seed=args.seed,
                                                skip_inactive=not args.full_work)
 
+    done_batches = [0]
+
     def run(first, count):
+        if args.stop_after_batches is not None and done_batches[0] >= args.stop_after_batches:
+            os._exit(17)                                   # simulated crash (no cleanup, like a real one)
+        done_batches[0] += 1
         model.next_frame = first
         return model.run(count, args.p, want_flags=False, want_diff=False, want_counters=True)["counters"]
 
+    # ---- checkpoint / resume.  Each rank keeps its last two checkpoints {next_batch: local counters}; every rank
+    # runs the same number of batches, so the ranks agree on the newest batch index ALL of them have recorded.
+    key = dict(code=code.name, nG=nG, p=args.p, seed=args.seed, frames=int(args.frames), batch=args.batch, world=world,
+               full_work=bool(args.full_work))
+    ck_path = None if args.checkpoint is None else f"{args.checkpoint}.rank{rank}"
+    history = {}
+    if ck_path and os.path.exists(ck_path):
+        with open(ck_path) as f:
+            ck = json.load(f)
+        if ck.get("key") == key:
+            history = {int(k): v for k, v in ck["history"].items()}
+    newest = max(history) if history else 0
+    common = int(-comm.allreduce_f64([-float(newest)], "max")[0])          # min over ranks
+    if common not in history:
+        common = 0                                                          # too far apart: start over
+    common = int(-comm.allreduce_f64([-float(common)], "max")[0])
+    first_batch = common
+    base = np.array(history[common], np.int64) if common else np.zeros(4, np.int64)
+    history = {common: base.tolist()} if common else {}
+
+    def on_batch(i, local):
+        if ck_path and ((i + 1) % args.checkpoint_every == 0):
+            history[i + 1] = (base + local).tolist()
+            for k in sorted(history)[:-2]:
+                del history[k]
+            tmp = ck_path + ".tmp"
+            with open(tmp, "w") as f:
+                json.dump({"key": key, "history": history}, f)
+            os.replace(tmp, ck_path)
+
     t0 = time.perf_counter()
     total = run_sharded(run, int(args.frames), args.batch, rank, world, target_block_errors=args.target_block_errors,
-                        poll_every=4, device=device)
+                        poll_every=4, comm=comm, first_batch=first_batch, on_batch=on_batch)
+    total = total + comm.allreduce_sum(base)
     dt = time.perf_counter() - t0
     if rank == 0:
         frames, flagged, block, s0 = (int(v) for v in total)
@@ -76,8 +115,7 @@ def main():
                           "frames": frames, "flagged": flagged, "block_errors": block, "stage0_failures": s0,
                           "bler": block / max(frames, 1), "seconds": dt, "frames_per_s": frames / dt,
                           "skip_inactive": not args.full_work}), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    comm.close()
 
 
 if __name__ == "__main__":

@@ -95,6 +95,8 @@ def test_constructor_validation(codes):
         F.LDPCBPDecoder([[1, 0]])
     with pytest.raises(NotImplementedError):
         F.QLDPCBPDecoder(code, trainable=True)
+    F.QLDPCBPDecoder(code, trainable=True, stage_one=True)   # the stage_one return comes first (decoding_q.py:792-793)
+    F.QLDPCBPDecoder(code, trainable=True, stage_two=True)
     d = F.QLDPCBPDecoder(code)                              # reference defaults, decoding_q.py:18-22
     assert (d.cn_type, d.num_iter, d.normalization_factor) == ("boxplus", 32, 0.625)
     d2 = F.LDPCBPDecoder(code.hx)                           # decoding.py:264-268
@@ -145,6 +147,64 @@ def test_sim_ber_and_plotber_with_a_fake_model(capsys):
     s_hat, ls_hat = model(64, 0.5)
     assert F.count_block_errors(np.zeros((64, 10)), np.asarray(s_hat)) == F.count_block_errors(None, s_hat)
     assert s_hat.shape == (64, 10)
+
+
+def test_osd_models_drive_plotber_like_the_reference(capsys):
+    """OSD.ipynb cells 2-3 call PlotBER.simulate(osd_model, ..., qldpc=False): the models return
+    (zeros_like(ls_hat), ls_hat).  The BSC-based model keeps only per-frame flags on the device, so its indicators
+    have no dense form; sim_ber must still count one error per failing frame instead of raising."""
+    import fbgnn as F
+    from fbgnn.bp_osd import _indicators
+
+    class Flags:                      # stands in for the device flags array
+        def __init__(self, a):
+            self.a = a
+
+        def numpy(self):
+            return self.a
+
+    def model(batch_size, ebno_db):
+        rng = np.random.default_rng(int(ebno_db * 1000))
+        return _indicators(Flags(((rng.random(batch_size) < ebno_db).astype(np.uint8)) << 1), 24)
+
+    zeros, ls_hat = model(100, 0.3)
+    assert not ls_hat.has_dense() and ls_hat.shape == (100, 24)
+    with pytest.raises(F.FbgnnError):
+        np.asarray(ls_hat)
+    plot = F.PlotBER()
+    ber, bler = plot.simulate(model, ebno_dbs=[0.3, 0.1], batch_size=400, num_target_block_errors=50, legend="osd",
+                              max_mc_iter=10, early_stop=True, add_bler=True, show_fig=False, qldpc=False,
+                              forward_keyboard_interrupt=False)
+    assert 0.2 < bler[0] < 0.4 and 0.05 < bler[1] < 0.15
+    assert np.allclose(ber, bler / 24)                # one count per failing frame over B x 24 entries
+    assert F.count_errors(None, ls_hat) == ls_hat.count_nonzero_rows()
+    # with the residual errors kept (BP4_OSD_Model) the dense matrix exists and is what the reference returns
+    dense = np.zeros((100, 24), np.int64)
+    dense[ls_hat.frame_flags() > 0, 3] = 1
+    z2, l2 = _indicators(Flags(ls_hat.frame_flags() << 1), 24, lambda: dense)
+    assert l2.has_dense() and np.array_equal(np.asarray(l2), dense) and not np.asarray(z2).any()
+
+
+def test_weights_unpickler_refuses_foreign_globals(tmp_path):
+    import pickle
+    import fbgnn as F
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("true",))
+
+    path = tmp_path / "evil.npy"
+    with open(path, "wb") as f:
+        pickle.dump([Evil()], f)
+    with pytest.raises(pickle.UnpicklingError):
+        F.read_weights(str(path))
+
+
+def test_model_run_validates_given_noise_shapes(codes):
+    """run(noise=...) must reject arrays that are not [batch_size, n] before they reach the kernels."""
+    import fbgnn as F
+    src = open(os.path.join(ROOT, "feedback-gnn_b200", "fbgnn", "feedback_gnn.py")).read()
+    assert src.count("must have shape [{B},") == 2
 
 
 def test_shard_ranges_cover_exactly():

@@ -66,14 +66,15 @@ def _stack(r):
     return np.stack([r["Lx"], r["Ly"], r["Lz"]], -1)
 
 
-@pytest.mark.parametrize("cn_type", ["boxplus-phi", "minsum", "boxplus"])
-def test_c_oracle_vs_numpy_oracle_teacher_forced(oracle, codes, cn_type):
+@pytest.mark.parametrize("name,cn_type", [("c882", "boxplus-phi"), ("c882", "minsum"), ("c882", "boxplus"),
+                                          ("c1270", "boxplus-phi"), ("c1270", "minsum")])
+def test_c_oracle_vs_numpy_oracle_teacher_forced(oracle, codes, c1270, name, cn_type):
     """One BP4 iteration from the C oracle's own state, recomputed with numpy's libm and numpy's
     reductions.  The two float32 evaluations agree to ~1e-6 except where the reference formula
     phi(x) = softplus(x) - log(exp(x)-1) cancels: there the error is bounded in
     absolute terms by the quantisation of the two ~equal terms."""
     from oracle import np_oracle as N
-    code = codes["c882"]
+    code = c1270 if name == "c1270" else codes[name]
     g = oracle.CodeGraph(code)
     X, Z = N.Side(code.hx), N.Side(code.hz)
     assert np.array_equal(X.cn_of_edge, g.X.vn_cn) and np.array_equal(Z.cn_of_edge, g.Z.vn_cn)
@@ -104,9 +105,10 @@ def test_c_oracle_vs_numpy_oracle_teacher_forced(oracle, codes, cn_type):
         assert np.all(np.abs(n_[key] - a[key]) <= _tol(a[key], "boxplus-phi", n_[key]))
 
 
-def test_c_oracle_vs_numpy_oracle_gnn_and_bp2(oracle, codes, weights):
+@pytest.mark.parametrize("name", ["c882", "c1270"])
+def test_c_oracle_vs_numpy_oracle_gnn_and_bp2(oracle, codes, c1270, weights, name):
     from oracle import np_oracle as N
-    code = codes["c882"]
+    code = c1270 if name == "c1270" else codes[name]
     g = oracle.CodeGraph(code)
     X, Z = N.Side(code.hx), N.Side(code.hz)
     B = 32
@@ -115,8 +117,8 @@ def test_c_oracle_vs_numpy_oracle_gnn_and_bp2(oracle, codes, weights):
     sz = (code.hz @ nx.T.astype(np.int64)) & 1
     r = oracle.bp4(g, float(oracle.prior_llr(0.05)), sx, sz, 16)
     for red in ("mean", "sum", "max", "min"):
-        oc = oracle.gnn(g, oracle.Gnn(weights["c882"], "tanh", red), _stack(r), r["z_logit"], r["x_logit"], sx, sz)
-        on = N.gnn(X, Z, weights["c882"], _stack(r), r["z_logit"], r["x_logit"], sx, sz, reduce_op=red)
+        oc = oracle.gnn(g, oracle.Gnn(weights[name], "tanh", red), _stack(r), r["z_logit"], r["x_logit"], sx, sz)
+        on = N.gnn(X, Z, weights[name], _stack(r), r["z_logit"], r["x_logit"], sx, sz, reduce_op=red)
         assert np.allclose(oc, on, rtol=1e-5, atol=2e-6), red
     # binary decoder, one iteration at a time is not needed: it has no cancellation in the VN update
     noise = oracle.bsc(2, 0, B, code.N, 0.03)
