@@ -70,7 +70,8 @@ int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {
     if (grid <= 0) return 0;
     const bool cp = a.llr.ptr == nullptr;
     const size_t smem = bp4_smem(a.X, a.Z, cp, a.iter_logits.ptr != nullptr);
-    const int threads = pick_threads(a.X.n, a.X.m + a.Z.m);
+    int threads = pick_threads(a.X.n, a.X.m + a.Z.m);
+    if (const char *t = getenv("FBGNN_BP4_THREADS")) threads = std::max(32, std::min(512, atoi(t) / 32 * 32));   // lab knob
     if (smem > ctx->smem_optin)
         return ctx->math_mode == FBGNN_MATH_FAST ? launch_bp4_gstate<MathFast>(ctx, a, grid, threads, cp)
                                                  : launch_bp4_gstate<MathExact>(ctx, a, grid, threads, cp);

@@ -106,6 +106,17 @@ struct MathFast {
     static __device__ __forceinline__ float atanh(float x) { return 0.5f * (log(1.0f + x) - log(1.0f - x)); }
 };
 
+// Lab knobs (make lab ..., tools/lab_bench.py): compile-time experiments, all bit-exact.  Measured on B200
+// (profiles/r02_lab_k_bp4_variants.txt, headline pipeline): group 1 / 2 / 3 / 6 = 184.0 / 188.2 / 189.3 / 185.0 k
+// frames/s with the lean cores, 182.2 k without them.
+#ifndef FBGNN_PHI_GROUP
+#define FBGNN_PHI_GROUP 3          // phi call sites of a check evaluated under one warp vote: the G polynomial chains
+                                   // interleave (the single-site form leaves the warp latency-bound on one Horner chain)
+#endif
+#ifndef FBGNN_LEAN
+#define FBGNN_LEAN 1               // no clamps inside the voted evaluations (identity for the lanes that use them)
+#endif
+
 // ------------------------------------------------------------------ saturated fast paths
 // Value-dependent shortcuts that return exactly what the full evaluation returns:
 //   phi(x) = phi(clip_hi) = +0          for x >= 16.635532,
@@ -115,16 +126,58 @@ struct MathFast {
 // Once a frame has converged nearly every message sits in these regimes; a warp whose lanes are all
 // saturated skips the polynomial evaluation altogether (the vote only decides whether the full path
 // is executed, never which value a lane takes).
+// phi without the input clamp: for 8.5e-8 < x < 16.635532 the clamp is the identity
+__device__ __forceinline__ float phi4_open(float x) {
+    float e = fb_expf_core(x);
+    float sp = (x > FB_SOFTPLUS_THR) ? x : fb_log1pf_ge1(e);
+    return FB_SUB(sp, fb_logf(FB_SUB(e, 1.0f)));
+}
+__device__ __forceinline__ float phi2_open(float x) {
+    float e = fb_expf_core(x);
+    return FB_SUB(fb_logf(FB_ADD(e, 1.0f)), fb_logf(FB_SUB(e, 1.0f)));
+}
+template <typename MATH, bool PHI4>
+__device__ __forceinline__ float phi_eval(float x) {
+    if (FBGNN_LEAN && MATH::kSaturationShortcuts) return PHI4 ? phi4_open(x) : phi2_open(x);
+    return PHI4 ? MATH::phi4(x) : MATH::phi2(x);
+}
+
 template <typename MATH, bool PHI4>
 __device__ __forceinline__ float phi_sat(float x) {
     if (!MATH::kSaturationShortcuts) return PHI4 ? MATH::phi4(x) : MATH::phi2(x);
     const bool hi = x >= FB_PHI_CLIP_HI, lo = x <= FB_PHI_CLIP_LO;
     float r = hi ? 0.0f : FB_PHI_CLIP_HI;
     if (__any_sync(__activemask(), !(hi || lo))) {
-        const float f = PHI4 ? MATH::phi4(x) : MATH::phi2(x);
+        const float f = phi_eval<MATH, PHI4>(x);
         r = (hi || lo) ? r : f;
     }
     return r;
+}
+
+// G call sites under one vote: the G independent polynomial chains interleave (ILP) at the price of evaluating
+// all G when any lane needs any of them.  Values are those of phi_sat.
+template <typename MATH, bool PHI4, int G>
+__device__ __forceinline__ void phi_sat_group(const float x[G], float r[G]) {
+    if (!MATH::kSaturationShortcuts) {
+#pragma unroll
+        for (int k = 0; k < G; k++) r[k] = PHI4 ? MATH::phi4(x[k]) : MATH::phi2(x[k]);
+        return;
+    }
+    bool sat[G], need = false;
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+        const bool hi = x[k] >= FB_PHI_CLIP_HI, lo = x[k] <= FB_PHI_CLIP_LO;
+        sat[k] = hi || lo;
+        r[k] = hi ? 0.0f : FB_PHI_CLIP_HI;
+        need = need || !sat[k];
+    }
+    if (__any_sync(__activemask(), need)) {
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            const float f = phi_eval<MATH, PHI4>(x[k]);
+            r[k] = sat[k] ? r[k] : f;
+        }
+    }
 }
 
 template <typename MATH>
@@ -134,7 +187,13 @@ __device__ __forceinline__ float logaddexp_sat(float a, float b) {
     const bool sat = FB_SUB(mn, mx) < -17.5f;
     float r = FB_ADD(0.0f, mx);
     if (__any_sync(__activemask(), !sat)) {
-        const float f = MATH::logaddexp(a, b);
+        float f;
+        if (FBGNN_LEAN) {           // exp without the -87 clamp: d >= -17.5 on the lanes that keep f
+            const float t = fb_expf_core(FB_SUB(mn, mx));
+            f = FB_ADD(fb_logf(FB_ADD(1.0f, t)), mx);
+        } else {
+            f = MATH::logaddexp(a, b);
+        }
         r = sat ? r : f;
     }
     return r;
@@ -246,22 +305,31 @@ __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge
     int par = synd_bit;
 #pragma unroll
     for (int k = 0; k < DC; k++) e[k] = cn_edge[c * DC + k];
+    constexpr int GRP = (FBGNN_PHI_GROUP > 0 && DC % FBGNN_PHI_GROUP == 0) ? FBGNN_PHI_GROUP : (DC % 2 == 0 ? 2 : 1);
+    float xin[DC];
 #pragma unroll
     for (int k = 0; k < DC; k++) {
         const float m = msg[e[k]];
         const uint32_t sgn = (m < 0.0f) ? 1u : 0u;
         neg |= sgn << k;
         par ^= (int)sgn;
-        a[k] = phi_sat<MATH, PHI4>(fabsf(m));
+        xin[k] = fabsf(m);
     }
+#pragma unroll
+    for (int k = 0; k < DC; k += GRP) phi_sat_group<MATH, PHI4, GRP>(xin + k, a + k);
     float T = 0.0f;
 #pragma unroll
     for (int k = 0; k < DC; k++) T = FB_ADD(T, a[k]);
     bool stable = FPX && rec != nullptr;
+    float xo[DC], vo[DC];
+#pragma unroll
+    for (int k = 0; k < DC; k++) xo[k] = FB_SUB(T, a[k]);
+#pragma unroll
+    for (int k = 0; k < DC; k += GRP) phi_sat_group<MATH, PHI4, GRP>(xo + k, vo + k);
 #pragma unroll
     for (int k = 0; k < DC; k++) {
-        const float x = FB_SUB(T, a[k]);
-        float v = phi_sat<MATH, PHI4>(x);
+        const float x = xo[k];
+        float v = vo[k];
         const uint32_t s = ((uint32_t)par ^ (neg >> k)) & 1u;
         v = __int_as_float(__float_as_int(v) ^ (int)(s << 31));
         msg[e[k]] = FB_MUL(v, factor);
