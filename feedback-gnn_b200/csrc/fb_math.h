@@ -214,4 +214,137 @@ FB_HD float fb_atanhf(float x) {
     return FB_MUL(0.5f, FB_SUB(a, b));
 }
 
+/* ================================================================================================
+ * SFU arithmetic (FBGNN_MATH_SFU): the same formulas with exp and log built on the GPU's special-
+ * function unit -- MUFU.EX2 (ex2.approx) and MUFU.LG2 (lg2.approx) -- instead of polynomials.
+ *
+ *   exp(x) : Cody-Waite reduction x = n ln2 + r in FMAs (as fb_expf_core); the argument of the MUFU,
+ *            r log2(e), is rounded to a multiple of 2^-23 by adding 1.5 (one FMA), so the MUFU only ever
+ *            sees the 2^23 + 8193 float32 values w = u - 1.5 with u in [1 - 2^-12, 2 + 2^-10]; 2^n goes into
+ *            the exponent field.
+ *   log(x) : exponent split as fb_logf; the MUFU only sees the mantissa m in [sqrt(1/2), sqrt(2)) -- exactly
+ *            2^23 float32 values, where lg2.approx is absolutely accurate to 2^-22.
+ *
+ * Because the MUFU inputs are confined to two finite sets, the hardware functions are TABLES: the
+ * repository carries them as measured on a B200 (tests/golden/sfu_b200_*.xz, written by
+ * tools/dump_sfu_tables.py), the CPU oracle looks the values up, and the CUDA kernels stay bit-identical
+ * to the oracle in this arithmetic too.  Accuracy: 2-3 ulp per exp / log instead of 1.  The saturation
+ * constants of phi (phi(<= 8.5e-8) = 16.635532, phi(>= 16.635532) = 0: the reference's known answers) and
+ * the rule that a second term below e^-17.5 leaves logaddexp at its larger argument are part of this
+ * specification, not consequences of rounding.  tanh / atanh (feedback GNN, "boxplus" check nodes) are
+ * the polynomial ones in both arithmetics.
+ * ================================================================================================ */
+#define FB_SFU_EX2_BASE   0x3F7FF000          /* bits of u for table entry 0:  1 - 2^-12           */
+#define FB_SFU_EX2_COUNT  ((1 << 23) + 8193)  /* entries up to u = 2 + 2^-10 (bits 0x40001000)      */
+#define FB_SFU_LG2_BASE   0x3f3504f3          /* bits of the smallest mantissa, sqrt(1/2)          */
+#define FB_SFU_LG2_COUNT  (1 << 23)
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ float fb_mufu_ex2(float w, float u) {
+    (void)u; float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(w)); return y;
+}
+__device__ __forceinline__ float fb_mufu_lg2(float m) {
+    float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(m)); return y;
+}
+#elif !defined(__CUDACC__)
+/* host: the MUFU as measured on the hardware (tables installed through fb_sfu_set_tables) */
+static const float *fb_sfu_ex2_tab = 0, *fb_sfu_lg2_tab = 0;
+static inline void fb_sfu_set_tables(const float *ex2_tab, const float *lg2_tab) {
+    fb_sfu_ex2_tab = ex2_tab; fb_sfu_lg2_tab = lg2_tab;
+}
+static inline float fb_mufu_ex2(float w, float u) {
+    int64_t i = (int64_t)FB_F2I(u) - FB_SFU_EX2_BASE; (void)w;
+    if (i < 0) i = 0;
+    if (i >= FB_SFU_EX2_COUNT) i = FB_SFU_EX2_COUNT - 1;
+    return fb_sfu_ex2_tab[i];
+}
+static inline float fb_mufu_lg2(float m) {
+    int64_t i = (int64_t)FB_F2I(m) - FB_SFU_LG2_BASE;
+    if (i < 0) i = 0;
+    if (i >= FB_SFU_LG2_COUNT) i = FB_SFU_LG2_COUNT - 1;
+    return fb_sfu_lg2_tab[i];
+}
+#else
+/* host side of a .cu file: never evaluated (the library has no CPU compute path) */
+static inline float fb_mufu_ex2(float w, float u) { (void)w; (void)u; return 0.0f; }
+static inline float fb_mufu_lg2(float m) { (void)m; return 0.0f; }
+#endif
+
+/* exp(x) for -87 <= x <= 88 */
+FB_HD float fb_sfu_expf_core(float x) {
+    const float magic = 12582912.0f;
+    float t = FB_FMA(x, 1.44269504088896341f, magic);
+    float fn = FB_SUB(t, magic);
+    float r = FB_FMA(fn, -0.693359375f, x);
+    r = FB_FMA(fn, 2.12194440e-4f, r);
+    float u = FB_FMA(r, 1.44269504088896341f, 1.5f);          /* r log2(e) on the 2^-23 grid, offset by 1.5 */
+    float y = fb_mufu_ex2(FB_SUB(u, 1.5f), u);
+    return FB_I2F(FB_F2I(y) + (int32_t)((uint32_t)FB_F2I(t) << 23));
+}
+FB_HD float fb_sfu_expf(float x) { return fb_sfu_expf_core(FB_FMAX(x, -87.0f)); }
+
+/* log(x) for positive normal x */
+FB_HD float fb_sfu_logf(float x) {
+    int32_t ix = FB_F2I(x);
+    int32_t eb = (ix - 0x3f3504f3) & (int32_t)0xff800000;
+    float m = FB_I2F(ix - eb);
+    float fe = (float)eb;
+    float l2 = fb_mufu_lg2(m);
+    return FB_FMA(fe, 0.693147180559945f * 1.1920928955078125e-7f, FB_MUL(l2, 0.693147180559945f));
+}
+
+FB_HD float fb_sfu_softplusf(float x) {
+    float xc = FB_FMIN(x, FB_SOFTPLUS_THR);
+    float e = fb_sfu_expf(xc);
+    float l = fb_sfu_logf(FB_ADD(1.0f, e));
+    float r = (x < -FB_SOFTPLUS_THR) ? e : l;
+    return (x > FB_SOFTPLUS_THR) ? x : r;
+}
+
+/* log(exp(a) + exp(b)) for mn - mx >= -17.5 (the caller's side of the specification handles the rest) */
+FB_HD float fb_sfu_logaddexp_open(float mx, float d) {
+    float t = fb_sfu_expf_core(d);
+    return FB_ADD(fb_sfu_logf(FB_ADD(1.0f, t)), mx);
+}
+FB_HD float fb_sfu_logaddexpf(float a, float b) {
+    float mx = FB_FMAX(a, b);
+    float mn = FB_FMIN(a, b);
+    float d = FB_SUB(mn, mx);
+    float f = fb_sfu_logaddexp_open(mx, FB_FMAX(d, -17.5f));
+    return (d < -17.5f) ? FB_ADD(0.0f, mx) : f;
+}
+
+/* phi on the open interval (8.5e-8, 16.635532).  Never negative: the two logs are one function of ordered
+ * arguments, the outer max guards the seam between binades; the inner max keeps log away from zero. */
+FB_HD float fb_sfu_phi4_open(float x) {
+    float e = fb_sfu_expf_core(x);
+    float sp = (x > FB_SOFTPLUS_THR) ? x : fb_sfu_logf(FB_ADD(1.0f, e));
+    float lg = fb_sfu_logf(FB_FMAX(FB_SUB(e, 1.0f), 1.1920928955078125e-7f));
+    return FB_FMAX(FB_SUB(sp, lg), 0.0f);
+}
+FB_HD float fb_sfu_phi2_open(float x) {
+    float e = fb_sfu_expf_core(x);
+    float lg = fb_sfu_logf(FB_FMAX(FB_SUB(e, 1.0f), 1.1920928955078125e-7f));
+    return FB_FMAX(FB_SUB(fb_sfu_logf(FB_ADD(e, 1.0f)), lg), 0.0f);
+}
+FB_HD float fb_sfu_phi4f(float x) {
+    float f = fb_sfu_phi4_open(FB_FMIN(FB_FMAX(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI));
+    f = (x <= FB_PHI_CLIP_LO) ? FB_PHI_CLIP_HI : f;
+    return (x >= FB_PHI_CLIP_HI) ? 0.0f : f;
+}
+FB_HD float fb_sfu_phi2f(float x) {
+    float f = fb_sfu_phi2_open(FB_FMIN(FB_FMAX(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI));
+    f = (x <= FB_PHI_CLIP_LO) ? FB_PHI_CLIP_HI : f;
+    return (x >= FB_PHI_CLIP_HI) ? 0.0f : f;
+}
+
+#if !defined(__CUDACC__)
+/* ---- host-side arithmetic selection (the CPU oracle): 0 = exact (default), 1 = SFU ------------ */
+static int fb_math_mode = 0;
+static inline float fb_m_softplusf(float x) { return fb_math_mode ? fb_sfu_softplusf(x) : fb_softplusf(x); }
+static inline float fb_m_logaddexpf(float a, float b) { return fb_math_mode ? fb_sfu_logaddexpf(a, b) : fb_logaddexpf(a, b); }
+static inline float fb_m_phi4f(float x) { return fb_math_mode ? fb_sfu_phi4f(x) : fb_phi4f(x); }
+static inline float fb_m_phi2f(float x) { return fb_math_mode ? fb_sfu_phi2f(x) : fb_phi2f(x); }
+#endif
+
 #endif /* FBGNN_FB_MATH_H */

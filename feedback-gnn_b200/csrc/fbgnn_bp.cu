@@ -31,12 +31,17 @@ static int launch_bp4_t(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t s
 
 template <int DV, int DC>
 static int launch_bp4_m(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t smem, int threads, bool cp) {
-    if (ctx->math_mode == FBGNN_MATH_FAST)
-        return cp ? launch_bp4_t<true, DV, DC, MathFast, false>(ctx, a, grid, smem, threads)
-                  : launch_bp4_t<false, DV, DC, MathFast, false>(ctx, a, grid, smem, threads);
-    // fixed-point exit: exact arithmetic, regular graph, boxplus-phi, long runs (the bookkeeping costs ~5 %
-    // per unsaturated iteration and a 16-iteration stage does not converge-and-saturate in time)
+    // fixed-point exit: regular graph, boxplus-phi, long runs (the bookkeeping costs ~5 % per unsaturated iteration
+    // and a 16-iteration stage does not converge-and-saturate in time).  Valid in both arithmetics: the saturation
+    // constants are exact in each.
     const bool fpx = DV > 0 && a.cn_type == 0 && a.num_iter >= 32 && !a.iter_logits.ptr;
+    if (ctx->math_mode == FBGNN_MATH_SFU) {
+        if (fpx)
+            return cp ? launch_bp4_t<true, DV, DC, MathSfu, true>(ctx, a, grid, smem, threads)
+                      : launch_bp4_t<false, DV, DC, MathSfu, true>(ctx, a, grid, smem, threads);
+        return cp ? launch_bp4_t<true, DV, DC, MathSfu, false>(ctx, a, grid, smem, threads)
+                  : launch_bp4_t<false, DV, DC, MathSfu, false>(ctx, a, grid, smem, threads);
+    }
     if (fpx)
         return cp ? launch_bp4_t<true, DV, DC, MathExact, true>(ctx, a, grid, smem, threads)
                   : launch_bp4_t<false, DV, DC, MathExact, true>(ctx, a, grid, smem, threads);
@@ -73,7 +78,7 @@ int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {
     int threads = pick_threads(a.X.n, a.X.m + a.Z.m);
     if (const char *t = getenv("FBGNN_BP4_THREADS")) threads = std::max(32, std::min(512, atoi(t) / 32 * 32));   // lab knob
     if (smem > ctx->smem_optin)
-        return ctx->math_mode == FBGNN_MATH_FAST ? launch_bp4_gstate<MathFast>(ctx, a, grid, threads, cp)
+        return ctx->math_mode == FBGNN_MATH_SFU ? launch_bp4_gstate<MathSfu>(ctx, a, grid, threads, cp)
                                                  : launch_bp4_gstate<MathExact>(ctx, a, grid, threads, cp);
     // both sides regular with the same degrees -> unrolled instantiation
     int dv = 0, dc = 0;
@@ -122,7 +127,7 @@ static int launch_bp2_t(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B, size_t smem
 
 template <int DV, int DC>
 static int launch_bp2_m(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B, size_t smem) {
-    return ctx->math_mode == FBGNN_MATH_FAST ? launch_bp2_t<DV, DC, MathFast>(ctx, a, B, smem)
+    return ctx->math_mode == FBGNN_MATH_SFU ? launch_bp2_t<DV, DC, MathSfu>(ctx, a, B, smem)
                                              : launch_bp2_t<DV, DC, MathExact>(ctx, a, B, smem);
 }
 

@@ -107,7 +107,7 @@ extern "C" int fbgnn_timer_stop(fbgnn_ctx *ctx, float *ms) {
 
 extern "C" int fbgnn_ctx_set_math(fbgnn_ctx *ctx, int32_t mode) {
     REQUIRE(ctx, "ctx is NULL");
-    REQUIRE(mode == FBGNN_MATH_EXACT || mode == FBGNN_MATH_FAST, "unknown math mode %d", mode);
+    REQUIRE(mode == FBGNN_MATH_EXACT || mode == FBGNN_MATH_SFU, "unknown math mode %d", mode);
     ctx->math_mode = mode;
     return 0;
 }
@@ -491,9 +491,10 @@ extern "C" int fbgnn_fma_peak(fbgnn_ctx *ctx, double *instr_per_s) {
 
 extern "C" int fbgnn_math_probe(fbgnn_ctx *ctx, const char *fn, const float *x, float *y, int64_t n) {
     REQUIRE(ctx && fn && x && y && n >= 0, "bad argument");
-    static const char *names[] = {"exp", "log", "log1p", "softplus", "phi4", "phi2", "tanh", "atanh"};
+    static const char *names[] = {"exp", "log", "log1p", "softplus", "phi4", "phi2", "tanh", "atanh", "mufu_ex2",
+                                  "mufu_lg2", "sfu_exp", "sfu_log", "sfu_softplus", "sfu_phi4", "sfu_phi2"};
     int id = -1;
-    for (int i = 0; i < 8; i++) if (!std::strcmp(fn, names[i])) id = i;
+    for (int i = 0; i < 15; i++) if (!std::strcmp(fn, names[i])) id = i;
     REQUIRE(id >= 0, "unknown probe function '%s'", fn);
     if (set_device(ctx)) return FBGNN_E_CUDA;
     if (n == 0) return 0;

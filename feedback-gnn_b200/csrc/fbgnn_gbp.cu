@@ -256,7 +256,7 @@ extern "C" int fbgnn_gbp_decode(fbgnn_code *code, fbgnn_gbp *g, int32_t num_iter
         if (zl.ptr) zl.ptr = (float *)zl.ptr + b0 * zl.s2;
         xh.ptr = (uint8_t *)xh.ptr + b0 * xh.s1;
         zh.ptr = (uint8_t *)zh.ptr + b0 * zh.s1;
-        rc = ctx->math_mode == FBGNN_MATH_FAST ? gbp_run<MathFast>(code, g, num_iter, nb, a, xl, zl, xh, zh)
+        rc = ctx->math_mode == FBGNN_MATH_SFU ? gbp_run<MathSfu>(code, g, num_iter, nb, a, xl, zl, xh, zh)
                                                : gbp_run<MathExact>(code, g, num_iter, nb, a, xl, zl, xh, zh);
     }
     CK(cudaFreeAsync(h_vn, st)); CK(cudaFreeAsync(hcx, st)); CK(cudaFreeAsync(hcz, st)); CK(cudaFreeAsync(lg, st));

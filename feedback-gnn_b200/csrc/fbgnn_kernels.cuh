@@ -56,11 +56,13 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.9604644775390625e-08f; }
 
 // ------------------------------------------------------------------ math policies -----
-// MathExact: the arithmetic specification (fb_math.h) -- software exp/log/tanh on the FP32 pipe,
-// bit-identical to the CPU oracle.  This is the default and the path every parity test covers.
-// MathFast (opt-in, fbgnn_ctx_set_math): the same formulas with the MUFU approximations
-// ex2.approx / lg2.approx / rcp.approx (2 ulp each).  Not bit-exact; statistically equivalent
-// (tests/test_gpu_fastmath.py) and ~2.5x faster because the path becomes SFU-bound.
+// MathExact: exp / log as polynomials on the FP32 pipe (fb_math.h, the restatement of Eigen's CPU kernels TF runs).
+// MathSfu  : exp / log on the special-function unit (MUFU.EX2 / MUFU.LG2 with range reductions that confine the MUFU
+//            inputs to two finite sets; fb_math.h "SFU arithmetic").  2-3 ulp instead of 1, ~2.3x fewer instructions
+//            per transcendental.
+// Both are bit-identical to the CPU oracle in the same arithmetic (the oracle evaluates the MUFU through tables
+// measured on the hardware), both carry the reference's saturation constants exactly, and the published logical
+// error rates are reproduced in both (tests/test_gpu_sfu.py).  tanh / atanh are the polynomial ones in both.
 struct MathExact {
     static constexpr bool kSaturationShortcuts = true;
     static __device__ __forceinline__ float softplus(float x) { return fb_softplusf(x); }
@@ -69,41 +71,33 @@ struct MathExact {
     static __device__ __forceinline__ float phi2(float x) { return fb_phi2f(x); }
     static __device__ __forceinline__ float tanh(float x) { return fb_tanhf(x); }
     static __device__ __forceinline__ float atanh(float x) { return fb_atanhf(x); }
+    // clamp-free forms for lanes known to be inside the open intervals (same bits as the full functions there)
+    static __device__ __forceinline__ float phi4_open(float x) {
+        float e = fb_expf_core(x);
+        float sp = (x > FB_SOFTPLUS_THR) ? x : fb_log1pf_ge1(e);
+        return FB_SUB(sp, fb_logf(FB_SUB(e, 1.0f)));
+    }
+    static __device__ __forceinline__ float phi2_open(float x) {
+        float e = fb_expf_core(x);
+        return FB_SUB(fb_logf(FB_ADD(e, 1.0f)), fb_logf(FB_SUB(e, 1.0f)));
+    }
+    static __device__ __forceinline__ float logaddexp_open(float mx, float d) {      // d = mn - mx >= -17.5
+        const float t = fb_expf_core(d);
+        return FB_ADD(fb_logf(FB_ADD(1.0f, t)), mx);
+    }
 };
 
-struct MathFast {
-    static constexpr bool kSaturationShortcuts = false;   // its phi is not exactly constant at the clips
-    static __device__ __forceinline__ float ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-    static __device__ __forceinline__ float lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-    static __device__ __forceinline__ float rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-    static __device__ __forceinline__ float exp(float x) { return ex2(x * 1.4426950408889634f); }
-    static __device__ __forceinline__ float log(float x) { return lg2(x) * 0.6931471805599453f; }
-    static __device__ __forceinline__ float softplus(float x) {
-        const float e = exp(fminf(x, FB_SOFTPLUS_THR));
-        const float r = (x < -FB_SOFTPLUS_THR) ? e : log(1.0f + e);
-        return (x > FB_SOFTPLUS_THR) ? x : r;
-    }
-    static __device__ __forceinline__ float logaddexp(float a, float b) {
-        const float mx = fmaxf(a, b), mn = fminf(a, b);
-        return log(1.0f + exp(mn - mx)) + mx;
-    }
-    static __device__ __forceinline__ float phi4(float x) {
-        x = fminf(fmaxf(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI);
-        const float e = exp(x);
-        const float sp = (x > FB_SOFTPLUS_THR) ? x : log(1.0f + e);
-        return sp - log(fmaxf(e - 1.0f, 1.1920929e-7f));     // exp(clip_lo) must not round to 1
-    }
-    static __device__ __forceinline__ float phi2(float x) {
-        x = fminf(fmaxf(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI);
-        const float e = exp(x);
-        return log(e + 1.0f) - log(fmaxf(e - 1.0f, 1.1920929e-7f));
-    }
-    static __device__ __forceinline__ float tanh(float x) {
-        const float t = ex2(fabsf(x) * -2.8853900817779268f);          // exp(-2|x|)
-        const float r = (1.0f - t) * rcp(1.0f + t);
-        return copysignf(r, x);
-    }
-    static __device__ __forceinline__ float atanh(float x) { return 0.5f * (log(1.0f + x) - log(1.0f - x)); }
+struct MathSfu {
+    static constexpr bool kSaturationShortcuts = true;
+    static __device__ __forceinline__ float softplus(float x) { return fb_sfu_softplusf(x); }
+    static __device__ __forceinline__ float logaddexp(float a, float b) { return fb_sfu_logaddexpf(a, b); }
+    static __device__ __forceinline__ float phi4(float x) { return fb_sfu_phi4f(x); }
+    static __device__ __forceinline__ float phi2(float x) { return fb_sfu_phi2f(x); }
+    static __device__ __forceinline__ float tanh(float x) { return fb_tanhf(x); }
+    static __device__ __forceinline__ float atanh(float x) { return fb_atanhf(x); }
+    static __device__ __forceinline__ float phi4_open(float x) { return fb_sfu_phi4_open(x); }
+    static __device__ __forceinline__ float phi2_open(float x) { return fb_sfu_phi2_open(x); }
+    static __device__ __forceinline__ float logaddexp_open(float mx, float d) { return fb_sfu_logaddexp_open(mx, d); }
 };
 
 // Lab knobs (make lab ..., tools/lab_bench.py): compile-time experiments, all bit-exact.  Measured on B200
@@ -126,19 +120,10 @@ struct MathFast {
 // Once a frame has converged nearly every message sits in these regimes; a warp whose lanes are all
 // saturated skips the polynomial evaluation altogether (the vote only decides whether the full path
 // is executed, never which value a lane takes).
-// phi without the input clamp: for 8.5e-8 < x < 16.635532 the clamp is the identity
-__device__ __forceinline__ float phi4_open(float x) {
-    float e = fb_expf_core(x);
-    float sp = (x > FB_SOFTPLUS_THR) ? x : fb_log1pf_ge1(e);
-    return FB_SUB(sp, fb_logf(FB_SUB(e, 1.0f)));
-}
-__device__ __forceinline__ float phi2_open(float x) {
-    float e = fb_expf_core(x);
-    return FB_SUB(fb_logf(FB_ADD(e, 1.0f)), fb_logf(FB_SUB(e, 1.0f)));
-}
 template <typename MATH, bool PHI4>
 __device__ __forceinline__ float phi_eval(float x) {
-    if (FBGNN_LEAN && MATH::kSaturationShortcuts) return PHI4 ? phi4_open(x) : phi2_open(x);
+    // inside a voted evaluation only the lanes with 8.5e-8 < x < 16.635532 keep the value: no clamp needed
+    if (FBGNN_LEAN && MATH::kSaturationShortcuts) return PHI4 ? MATH::phi4_open(x) : MATH::phi2_open(x);
     return PHI4 ? MATH::phi4(x) : MATH::phi2(x);
 }
 
@@ -188,9 +173,8 @@ __device__ __forceinline__ float logaddexp_sat(float a, float b) {
     float r = FB_ADD(0.0f, mx);
     if (__any_sync(__activemask(), !sat)) {
         float f;
-        if (FBGNN_LEAN) {           // exp without the -87 clamp: d >= -17.5 on the lanes that keep f
-            const float t = fb_expf_core(FB_SUB(mn, mx));
-            f = FB_ADD(fb_logf(FB_ADD(1.0f, t)), mx);
+        if (FBGNN_LEAN) {           // exp without its clamp: d >= -17.5 on the lanes that keep f
+            f = MATH::logaddexp_open(mx, FB_SUB(mn, mx));
         } else {
             f = MATH::logaddexp(a, b);
         }
@@ -1842,7 +1826,14 @@ static __global__ void k_math_probe(int fn, const float *x, float *y, int64_t n)
         case 4: r = fb_phi4f(v); break;
         case 5: r = fb_phi2f(v); break;
         case 6: r = fb_tanhf(v); break;
-        default: r = fb_atanhf(v); break;
+        case 7: r = fb_atanhf(v); break;
+        case 8: r = fb_mufu_ex2(v, 0.0f); break;        // raw MUFU.EX2 (tools/dump_sfu_tables.py)
+        case 9: r = fb_mufu_lg2(v); break;              // raw MUFU.LG2
+        case 10: r = fb_sfu_expf(v); break;
+        case 11: r = fb_sfu_logf(v); break;
+        case 12: r = fb_sfu_softplusf(v); break;
+        case 13: r = fb_sfu_phi4f(v); break;
+        default: r = fb_sfu_phi2f(v); break;
     }
     y[i] = r;
 }

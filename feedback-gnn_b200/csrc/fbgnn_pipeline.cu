@@ -153,7 +153,7 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
         // BP4_OSD_Model (bp_osd.py:80-197): frames still mismatching get both parts re-solved by OSD-0
         OsdLlrArgs la{n, cur_list, cur_count, w.L, w.P};
         const int64_t blocks = std::min<int64_t>((cur_count * n + 255) / 256, (int64_t)ctx->num_sms * 8);
-        if (ctx->math_mode == FBGNN_MATH_FAST) k_osd_llr<MathFast><<<(unsigned)blocks, 256, 0, st>>>(la);
+        if (ctx->math_mode == FBGNN_MATH_SFU) k_osd_llr<MathSfu><<<(unsigned)blocks, 256, 0, st>>>(la);
         else k_osd_llr<MathExact><<<(unsigned)blocks, 256, 0, st>>>(la);
         CK(cudaGetLastError());
         ctx->launches++;

@@ -158,13 +158,15 @@ class Context:
         call("fbgnn_ctx_sync", self.handle)
 
     def set_math(self, mode):
-        """"exact" (default; bit-identical to the CPU oracle) or "fast" (MUFU approximations)."""
-        call("fbgnn_ctx_set_math", self.handle, {"exact": 0, "fast": 1}[mode])
+        """Arithmetic of the decoders launched from now on: "exact" (exp / log as polynomials on the FP32 pipe) or
+        "sfu" (exp / log on the special-function unit; "fast" is the former name).  Both are bit-identical to the CPU
+        oracle in the same arithmetic (csrc/fb_math.h)."""
+        call("fbgnn_ctx_set_math", self.handle, {"exact": 0, "sfu": 1, "fast": 1}[mode])
 
     def get_math(self):
         m = C.c_int32()
         call("fbgnn_ctx_get_math", self.handle, C.byref(m))
-        return ["exact", "fast"][m.value]
+        return ["exact", "sfu"][m.value]
 
     def timer_start(self):
         call("fbgnn_timer_start", self.handle)

@@ -59,8 +59,10 @@ extern "C" {
 #define FBGNN_CN_MINSUM  2           /* "minsum"      */
 
 /* arithmetic of the decoders (fbgnn_ctx_set_math) */
-#define FBGNN_MATH_EXACT 0           /* default: software exp/log/tanh, bit-identical to the CPU oracle */
-#define FBGNN_MATH_FAST  1           /* MUFU ex2/lg2/rcp approximations: ~2 ulp per call, not bit-exact  */
+#define FBGNN_MATH_EXACT 0           /* exp / log as polynomials on the FP32 pipe (1 ulp)                              */
+#define FBGNN_MATH_SFU   1           /* exp / log on the special-function unit (MUFU.EX2 / LG2, 2-3 ulp), ~2.3x fewer   */
+                                     /* instructions; both are bit-identical to the CPU oracle in the same arithmetic  */
+#define FBGNN_MATH_FAST  FBGNN_MATH_SFU   /* former name */
 
 /* Feedback_GNN options */
 #define FBGNN_ACT_TANH   0
@@ -311,7 +313,8 @@ int fbgnn_sfu_peak(fbgnn_ctx *ctx, double *evals_per_s);
 /* Measured FP32 FMA issue rate (thread-instructions / s), the bound of the exact-arithmetic path */
 int fbgnn_fma_peak(fbgnn_ctx *ctx, double *instr_per_s);
 /* Elementwise probes of the arithmetic specification (tests): fn in {"exp","log","log1p",
- * "softplus","phi4","phi2","tanh","atanh"}; x,y device float32 [n]. */
+ * "softplus","phi4","phi2","tanh","atanh"} (exact arithmetic), {"sfu_exp","sfu_log","sfu_softplus","sfu_phi4","sfu_phi2"}
+ * (SFU arithmetic) and the raw hardware functions {"mufu_ex2","mufu_lg2"} (tools/dump_sfu_tables.py); x,y device float32 [n]. */
 int fbgnn_math_probe(fbgnn_ctx *ctx, const char *fn, const float *x, float *y, int64_t n);
 
 #ifdef __cplusplus

@@ -74,6 +74,44 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+# ------------------------------------------------------------------ arithmetic selection --
+_sfu_keep = None
+
+
+def set_math(mode):
+    """"exact" (software exp / log, default) or "sfu" (MUFU.EX2 / MUFU.LG2 through the tables measured on a
+    B200, oracle/sfu_tables.py): the arithmetic of every oracle call from now on (fb_math.h)."""
+    global _sfu_keep
+    L = lib()
+    if mode == "sfu":
+        if _sfu_keep is None:
+            from . import sfu_tables
+            _sfu_keep = sfu_tables.tables()
+            L.orc_set_sfu_tables(_p(_sfu_keep[0]), _p(_sfu_keep[1]))
+    elif mode != "exact":
+        raise ValueError("math mode must be 'exact' or 'sfu'")
+    rc = L.orc_set_math(1 if mode == "sfu" else 0)
+    assert rc == 0, rc
+
+
+def get_math():
+    return ["exact", "sfu"][lib().orc_get_math()]
+
+
+class math:
+    """``with oracle.math("sfu"): ...``"""
+
+    def __init__(self, mode):
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = get_math()
+        set_math(self.mode)
+
+    def __exit__(self, *exc):
+        set_math(self.prev)
+
+
 def _i32(a):
     return np.ascontiguousarray(a, dtype=np.int32)
 

@@ -195,7 +195,7 @@ static void cn_update(const orc_side_t *S, int cn_type, int phi4, float factor,
             for (int k = k0; k < k1; k++) {
                 float m = msg[S->cn_edge[k]];
                 if (m < 0.0f) sgn = -sgn;
-                float a = phi4 ? fb_phi4f(fabsf(m)) : fb_phi2f(fabsf(m));
+                float a = phi4 ? fb_m_phi4f(fabsf(m)) : fb_m_phi2f(fabsf(m));
                 work[k - k0] = a;
                 T = FB_ADD(T, a);
             }
@@ -204,7 +204,7 @@ static void cn_update(const orc_side_t *S, int cn_type, int phi4, float factor,
                 int e = S->cn_edge[k];
                 float s = (msg[e] < 0.0f) ? -sgn : sgn;
                 float x = FB_SUB(T, work[k - k0]);
-                float v = phi4 ? fb_phi4f(x) : fb_phi2f(x);
+                float v = phi4 ? fb_m_phi4f(x) : fb_m_phi2f(x);
                 msg[e] = FB_MUL(FB_MUL(s, v), factor);
             }
         } else if (cn_type == ORC_CN_TANH) {
@@ -292,8 +292,8 @@ static void bp4_logits(int n, const orc_rows_t *rows_x, const orc_rows_t *rows_z
                        float *x_logit, float *z_logit, float *wa, float *wb) {
     /* wa = llr_x', wb = llr_z' */
     for (int v = 0; v < n; v++) {
-        wb[v] = FB_SUB(fb_softplusf(-Lx[v]), fb_logaddexpf(-Lz[v], -Ly[v]));
-        wa[v] = FB_SUB(fb_softplusf(-Lz[v]), fb_logaddexpf(-Lx[v], -Ly[v]));
+        wb[v] = FB_SUB(fb_m_softplusf(-Lx[v]), fb_m_logaddexpf(-Lz[v], -Ly[v]));
+        wa[v] = FB_SUB(fb_m_softplusf(-Lz[v]), fb_m_logaddexpf(-Lx[v], -Ly[v]));
     }
     for (int side = 0; side < 2; side++) {
         const orc_rows_t *R = side ? rows_z : rows_x;
@@ -305,9 +305,9 @@ static void bp4_logits(int n, const orc_rows_t *rows_x, const orc_rows_t *rows_z
             for (int k = R->ptr[r]; k < R->ptr[r + 1]; k++) {
                 float m = l[R->col[k]];
                 if (m < 0.0f) sgn = -sgn;
-                T = FB_ADD(T, fb_phi4f(fabsf(m)));
+                T = FB_ADD(T, fb_m_phi4f(fabsf(m)));
             }
-            out[r] = FB_MUL(sgn, fb_phi4f(T));
+            out[r] = FB_MUL(sgn, fb_m_phi4f(T));
         }
     }
 }
@@ -351,15 +351,15 @@ static void bp4_frame_il(const orc_side_t *X, const orc_side_t *Z, int cn_type, 
             float ly = FB_ADD(FB_ADD(Sz, Sx), llry[v]);
             float lx = FB_ADD(Sz, llrx[v]);
             float lz = FB_ADD(Sx, llrz[v]);
-            float num_hx = fb_softplusf(-lx);
-            float num_hz = fb_softplusf(-lz);
+            float num_hx = fb_m_softplusf(-lx);
+            float num_hz = fb_m_softplusf(-lz);
             for (int e = X->vn_ptr[v]; e < X->vn_ptr[v + 1]; e++) {
                 float a = FB_SUB(lz, mx[e]), b = FB_SUB(ly, mx[e]);
-                mx[e] = FB_SUB(num_hx, fb_logaddexpf(-a, -b));
+                mx[e] = FB_SUB(num_hx, fb_m_logaddexpf(-a, -b));
             }
             for (int e = Z->vn_ptr[v]; e < Z->vn_ptr[v + 1]; e++) {
                 float a = FB_SUB(lx, mz[e]), b = FB_SUB(ly, mz[e]);
-                mz[e] = FB_SUB(num_hz, fb_logaddexpf(-a, -b));
+                mz[e] = FB_SUB(num_hz, fb_m_logaddexpf(-a, -b));
             }
         }
         cn_update(X, cn_type, 1, factor, sx, mx, work);
@@ -746,8 +746,8 @@ static uint8_t pipeline_frame(const orc_side_t *X, const orc_side_t *Z, const or
             /* bp_osd.py:135-144: osd_llrz = softplus(-llrx) - logsumexp(-llrz, -llry), osd_llrx likewise */
             float *lz_ = wa, *lx_ = wa + n;
             for (int v = 0; v < n; v++) {
-                lz_[v] = FB_SUB(fb_softplusf(-L[v]), fb_logaddexpf(-L[2 * n + v], -L[n + v]));
-                lx_[v] = FB_SUB(fb_softplusf(-L[2 * n + v]), fb_logaddexpf(-L[v], -L[n + v]));
+                lz_[v] = FB_SUB(fb_m_softplusf(-L[v]), fb_m_logaddexpf(-L[2 * n + v], -L[n + v]));
+                lx_[v] = FB_SUB(fb_m_softplusf(-L[2 * n + v]), fb_m_logaddexpf(-L[v], -L[n + v]));
             }
             const int Rx = cfg->basis_x->m, Rz = cfg->basis_z->m, Rm = Rx > Rz ? Rx : Rz;
             int32_t *order = (int32_t *)malloc(sizeof(int32_t) * (size_t)(2 * n + Rm + 1));
@@ -1056,9 +1056,9 @@ static float gbp_soft_row(const orc_rows_t *R, int r, const float *l) {
     for (int k = R->ptr[r]; k < R->ptr[r + 1]; k++) {
         float m = l[R->col[k]];
         if (m < 0.0f) sgn = -sgn;
-        T = FB_ADD(T, fb_phi2f(fabsf(m)));
+        T = FB_ADD(T, fb_m_phi2f(fabsf(m)));
     }
-    return FB_MUL(sgn, fb_phi2f(T));
+    return FB_MUL(sgn, fb_m_phi2f(T));
 }
 
 /* One frame of GNN_BP4.call.  sx [m_x], sz [m_z]; x_logit [num_iter][m_z + k_z], z_logit [num_iter][m_x + k_x]
@@ -1085,8 +1085,8 @@ static void gbp_frame(const orc_gbp_t *G, const orc_side_t *X, const orc_side_t 
                 llr[c * n + v] = a;
             }
             const float Lx = llr[v], Ly = llr[n + v], Lz = llr[2 * n + v];
-            lzp[v] = FB_SUB(fb_softplusf(-Lx), fb_logaddexpf(-Lz, -Ly));
-            lxp[v] = FB_SUB(fb_softplusf(-Lz), fb_logaddexpf(-Lx, -Ly));
+            lzp[v] = FB_SUB(fb_m_softplusf(-Lx), fb_m_logaddexpf(-Lz, -Ly));
+            lxp[v] = FB_SUB(fb_m_softplusf(-Lz), fb_m_logaddexpf(-Lx, -Ly));
         }
         float *xo = x_logit + (size_t)it * (Z->m + lz->m), *zo = z_logit + (size_t)it * (X->m + lx->m);
         for (int r = 0; r < Z->m; r++) xo[r] = lgz[r] = gbp_soft_row(&hzr, r, lxp);
@@ -1148,8 +1148,14 @@ ORC_VEC(orc_phi4f, fb_phi4f)
 ORC_VEC(orc_phi2f, fb_phi2f)
 ORC_VEC(orc_tanhf, fb_tanhf)
 ORC_VEC(orc_atanhf, fb_atanhf)
+/* in the arithmetic selected by orc_set_math */
+ORC_VEC(orc_m_softplusf, fb_m_softplusf)
+ORC_VEC(orc_m_phi4f, fb_m_phi4f)
+ORC_VEC(orc_m_phi2f, fb_m_phi2f)
+ORC_VEC(orc_sfu_expf, fb_sfu_expf)
+ORC_VEC(orc_sfu_logf, fb_sfu_logf)
 void orc_logaddexpf(const float *a, const float *b, float *y, int64_t n) {
-    for (int64_t i = 0; i < n; i++) y[i] = fb_logaddexpf(a[i], b[i]);
+    for (int64_t i = 0; i < n; i++) y[i] = fb_m_logaddexpf(a[i], b[i]);
 }
 
 int orc_num_threads(void) {
@@ -1159,6 +1165,17 @@ int orc_num_threads(void) {
     return 1;
 #endif
 }
+/* arithmetic of every oracle function from now on: 0 = exact (software libm, default), 1 = SFU (MUFU tables;
+ * needs orc_set_sfu_tables first).  See fb_math.h. */
+int orc_set_math(int mode) {
+    if (mode != 0 && mode != 1) return -1;
+    if (mode == 1 && (!fb_sfu_ex2_tab || !fb_sfu_lg2_tab)) return -2;
+    fb_math_mode = mode;
+    return 0;
+}
+int orc_get_math(void) { return fb_math_mode; }
+void orc_set_sfu_tables(const float *ex2_tab, const float *lg2_tab) { fb_sfu_set_tables(ex2_tab, lg2_tab); }
+
 void orc_set_num_threads(int t) {
 #ifdef _OPENMP
     omp_set_num_threads(t);
