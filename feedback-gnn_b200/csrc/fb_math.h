@@ -222,22 +222,25 @@ FB_HD float fb_atanhf(float x) {
  *            r log2(e), is rounded to a multiple of 2^-23 by adding 1.5 (one FMA), so the MUFU only ever
  *            sees the 2^23 + 8193 float32 values w = u - 1.5 with u in [1 - 2^-12, 2 + 2^-10]; 2^n goes into
  *            the exponent field.
- *   log(x) : exponent split as fb_logf; the MUFU only sees the mantissa m in [sqrt(1/2), sqrt(2)) -- exactly
- *            2^23 float32 values, where lg2.approx is absolutely accurate to 2^-22.
+ *   log(x) : exponent split as fb_logf; the MUFU only sees the mantissa m in [sqrt(1/2), sqrt(2)), where
+ *            lg2.approx is absolutely accurate to 2^-22.  Arguments known to lie in [1, 2] (the 1 + exp(d), d <= 0,
+ *            of logaddexp) skip the split: the table runs on to 2.0, 13 302 542 float32 values in all.
+ *   1/q    : MUFU.RCP on q in [1, 2] (2^23 + 1 values), used by tanh = (1 - t) / (1 + t), t = exp(-2|x|).
  *
- * Because the MUFU inputs are confined to two finite sets, the hardware functions are TABLES: the
+ * Because the MUFU inputs are confined to three finite sets, the hardware functions are TABLES: the
  * repository carries them as measured on a B200 (tests/golden/sfu_b200_*.xz, written by
  * tools/dump_sfu_tables.py), the CPU oracle looks the values up, and the CUDA kernels stay bit-identical
  * to the oracle in this arithmetic too.  Accuracy: 2-3 ulp per exp / log instead of 1.  The saturation
  * constants of phi (phi(<= 8.5e-8) = 16.635532, phi(>= 16.635532) = 0: the reference's known answers) and
  * the rule that a second term below e^-17.5 leaves logaddexp at its larger argument are part of this
- * specification, not consequences of rounding.  tanh / atanh (feedback GNN, "boxplus" check nodes) are
- * the polynomial ones in both arithmetics.
+ * specification, not consequences of rounding.
  * ================================================================================================ */
 #define FB_SFU_EX2_BASE   0x3F7FF000          /* bits of u for table entry 0:  1 - 2^-12           */
 #define FB_SFU_EX2_COUNT  ((1 << 23) + 8193)  /* entries up to u = 2 + 2^-10 (bits 0x40001000)      */
 #define FB_SFU_LG2_BASE   0x3f3504f3          /* bits of the smallest mantissa, sqrt(1/2)          */
-#define FB_SFU_LG2_COUNT  (1 << 23)
+#define FB_SFU_LG2_COUNT  (0x40000000 - 0x3f3504f3 + 1)   /* up to and including 2.0               */
+#define FB_SFU_RCP_BASE   0x3F800000          /* q = 1.0                                           */
+#define FB_SFU_RCP_COUNT  ((1 << 23) + 1)     /* up to and including 2.0                           */
 
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ float fb_mufu_ex2(float w, float u) {
@@ -246,11 +249,14 @@ __device__ __forceinline__ float fb_mufu_ex2(float w, float u) {
 __device__ __forceinline__ float fb_mufu_lg2(float m) {
     float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(m)); return y;
 }
+__device__ __forceinline__ float fb_mufu_rcp(float q) {
+    float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(q)); return y;
+}
 #elif !defined(__CUDACC__)
 /* host: the MUFU as measured on the hardware (tables installed through fb_sfu_set_tables) */
-static const float *fb_sfu_ex2_tab = 0, *fb_sfu_lg2_tab = 0;
-static inline void fb_sfu_set_tables(const float *ex2_tab, const float *lg2_tab) {
-    fb_sfu_ex2_tab = ex2_tab; fb_sfu_lg2_tab = lg2_tab;
+static const float *fb_sfu_ex2_tab = 0, *fb_sfu_lg2_tab = 0, *fb_sfu_rcp_tab = 0;
+static inline void fb_sfu_set_tables(const float *ex2_tab, const float *lg2_tab, const float *rcp_tab) {
+    fb_sfu_ex2_tab = ex2_tab; fb_sfu_lg2_tab = lg2_tab; fb_sfu_rcp_tab = rcp_tab;
 }
 static inline float fb_mufu_ex2(float w, float u) {
     int64_t i = (int64_t)FB_F2I(u) - FB_SFU_EX2_BASE; (void)w;
@@ -264,10 +270,17 @@ static inline float fb_mufu_lg2(float m) {
     if (i >= FB_SFU_LG2_COUNT) i = FB_SFU_LG2_COUNT - 1;
     return fb_sfu_lg2_tab[i];
 }
+static inline float fb_mufu_rcp(float q) {
+    int64_t i = (int64_t)FB_F2I(q) - FB_SFU_RCP_BASE;
+    if (i < 0) i = 0;
+    if (i >= FB_SFU_RCP_COUNT) i = FB_SFU_RCP_COUNT - 1;
+    return fb_sfu_rcp_tab[i];
+}
 #else
 /* host side of a .cu file: never evaluated (the library has no CPU compute path) */
 static inline float fb_mufu_ex2(float w, float u) { (void)w; (void)u; return 0.0f; }
 static inline float fb_mufu_lg2(float m) { (void)m; return 0.0f; }
+static inline float fb_mufu_rcp(float q) { (void)q; return 0.0f; }
 #endif
 
 /* exp(x) for -87 <= x <= 88 */
@@ -293,6 +306,9 @@ FB_HD float fb_sfu_logf(float x) {
     return FB_FMA(fe, 0.693147180559945f * 1.1920928955078125e-7f, FB_MUL(l2, 0.693147180559945f));
 }
 
+/* log(x) for 1 <= x <= 2: no exponent split */
+FB_HD float fb_sfu_logf_1to2(float x) { return FB_MUL(fb_mufu_lg2(x), 0.693147180559945f); }
+
 FB_HD float fb_sfu_softplusf(float x) {
     float xc = FB_FMIN(x, FB_SOFTPLUS_THR);
     float e = fb_sfu_expf(xc);
@@ -303,8 +319,8 @@ FB_HD float fb_sfu_softplusf(float x) {
 
 /* log(exp(a) + exp(b)) for mn - mx >= -17.5 (the caller's side of the specification handles the rest) */
 FB_HD float fb_sfu_logaddexp_open(float mx, float d) {
-    float t = fb_sfu_expf_core(d);
-    return FB_ADD(fb_sfu_logf(FB_ADD(1.0f, t)), mx);
+    float t = fb_sfu_expf_core(d);                       /* 0 < t <= 1 */
+    return FB_ADD(fb_sfu_logf_1to2(FB_ADD(1.0f, t)), mx);
 }
 FB_HD float fb_sfu_logaddexpf(float a, float b) {
     float mx = FB_FMAX(a, b);
@@ -338,6 +354,18 @@ FB_HD float fb_sfu_phi2f(float x) {
     return (x >= FB_PHI_CLIP_HI) ? 0.0f : f;
 }
 
+/* tanh(x) = sign(x) (1 - t) / (1 + t), t = exp(-2 |x|); |x| >= 10 gives exactly 1 */
+FB_HD float fb_sfu_tanhf(float x) {
+    float ax = FB_FMIN(FB_I2F(FB_F2I(x) & 0x7fffffff), 10.0f);
+    float t = fb_sfu_expf_core(FB_MUL(ax, -2.0f));
+    float r = FB_MUL(FB_SUB(1.0f, t), fb_mufu_rcp(FB_ADD(1.0f, t)));
+    return FB_I2F(FB_F2I(r) | (FB_F2I(x) & (int32_t)0x80000000));
+}
+/* atanh for |x| <= 1 - 1e-7 */
+FB_HD float fb_sfu_atanhf(float x) {
+    return FB_MUL(0.5f, FB_SUB(fb_sfu_logf(FB_ADD(1.0f, x)), fb_sfu_logf(FB_SUB(1.0f, x))));
+}
+
 #if !defined(__CUDACC__)
 /* ---- host-side arithmetic selection (the CPU oracle): 0 = exact (default), 1 = SFU ------------ */
 static int fb_math_mode = 0;
@@ -345,6 +373,8 @@ static inline float fb_m_softplusf(float x) { return fb_math_mode ? fb_sfu_softp
 static inline float fb_m_logaddexpf(float a, float b) { return fb_math_mode ? fb_sfu_logaddexpf(a, b) : fb_logaddexpf(a, b); }
 static inline float fb_m_phi4f(float x) { return fb_math_mode ? fb_sfu_phi4f(x) : fb_phi4f(x); }
 static inline float fb_m_phi2f(float x) { return fb_math_mode ? fb_sfu_phi2f(x) : fb_phi2f(x); }
+static inline float fb_m_tanhf(float x) { return fb_math_mode ? fb_sfu_tanhf(x) : fb_tanhf(x); }
+static inline float fb_m_atanhf(float x) { return fb_math_mode ? fb_sfu_atanhf(x) : fb_atanhf(x); }
 #endif
 
 #endif /* FBGNN_FB_MATH_H */

@@ -492,9 +492,10 @@ extern "C" int fbgnn_fma_peak(fbgnn_ctx *ctx, double *instr_per_s) {
 extern "C" int fbgnn_math_probe(fbgnn_ctx *ctx, const char *fn, const float *x, float *y, int64_t n) {
     REQUIRE(ctx && fn && x && y && n >= 0, "bad argument");
     static const char *names[] = {"exp", "log", "log1p", "softplus", "phi4", "phi2", "tanh", "atanh", "mufu_ex2",
-                                  "mufu_lg2", "sfu_exp", "sfu_log", "sfu_softplus", "sfu_phi4", "sfu_phi2"};
+                                  "mufu_lg2", "sfu_exp", "sfu_log", "sfu_softplus", "sfu_phi4", "sfu_phi2", "mufu_rcp",
+                                  "sfu_tanh", "sfu_atanh"};
     int id = -1;
-    for (int i = 0; i < 15; i++) if (!std::strcmp(fn, names[i])) id = i;
+    for (int i = 0; i < 18; i++) if (!std::strcmp(fn, names[i])) id = i;
     REQUIRE(id >= 0, "unknown probe function '%s'", fn);
     if (set_device(ctx)) return FBGNN_E_CUDA;
     if (n == 0) return 0;

@@ -65,8 +65,8 @@ static int launch_gnn_t(fbgnn_ctx *ctx, const GnnArgs &a) {
 
 template <int H, int M, int DV, bool TB, bool FACT = true>
 static int launch_gnn_m(fbgnn_ctx *ctx, const GnnArgs &a) {
-    // the feedback GNN's only transcendental is tanh, which is the polynomial one in both arithmetics
-    return launch_gnn_t<H, M, DV, TB, FACT, MathExact>(ctx, a);
+    return ctx->math_mode == FBGNN_MATH_SFU ? launch_gnn_t<H, M, DV, TB, FACT, MathSfu>(ctx, a)
+                                             : launch_gnn_t<H, M, DV, TB, FACT, MathExact>(ctx, a);
 }
 
 int launch_gnn(fbgnn_ctx *ctx, const fbgnn_gnn *g, GnnArgs &a) {

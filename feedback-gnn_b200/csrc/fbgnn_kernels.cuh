@@ -62,7 +62,7 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.96
 //            per transcendental.
 // Both are bit-identical to the CPU oracle in the same arithmetic (the oracle evaluates the MUFU through tables
 // measured on the hardware), both carry the reference's saturation constants exactly, and the published logical
-// error rates are reproduced in both (tests/test_gpu_sfu.py).  tanh / atanh are the polynomial ones in both.
+// error rates are reproduced in both (tests/test_gpu_sfu.py).
 struct MathExact {
     static constexpr bool kSaturationShortcuts = true;
     static __device__ __forceinline__ float softplus(float x) { return fb_softplusf(x); }
@@ -93,8 +93,8 @@ struct MathSfu {
     static __device__ __forceinline__ float logaddexp(float a, float b) { return fb_sfu_logaddexpf(a, b); }
     static __device__ __forceinline__ float phi4(float x) { return fb_sfu_phi4f(x); }
     static __device__ __forceinline__ float phi2(float x) { return fb_sfu_phi2f(x); }
-    static __device__ __forceinline__ float tanh(float x) { return fb_tanhf(x); }
-    static __device__ __forceinline__ float atanh(float x) { return fb_atanhf(x); }
+    static __device__ __forceinline__ float tanh(float x) { return fb_sfu_tanhf(x); }
+    static __device__ __forceinline__ float atanh(float x) { return fb_sfu_atanhf(x); }
     static __device__ __forceinline__ float phi4_open(float x) { return fb_sfu_phi4_open(x); }
     static __device__ __forceinline__ float phi2_open(float x) { return fb_sfu_phi2_open(x); }
     static __device__ __forceinline__ float logaddexp_open(float mx, float d) { return fb_sfu_logaddexp_open(mx, d); }
@@ -1829,6 +1829,9 @@ static __global__ void k_math_probe(int fn, const float *x, float *y, int64_t n)
         case 7: r = fb_atanhf(v); break;
         case 8: r = fb_mufu_ex2(v, 0.0f); break;        // raw MUFU.EX2 (tools/dump_sfu_tables.py)
         case 9: r = fb_mufu_lg2(v); break;              // raw MUFU.LG2
+        case 15: r = fb_mufu_rcp(v); break;             // raw MUFU.RCP
+        case 16: r = fb_sfu_tanhf(v); break;
+        case 17: r = fb_sfu_atanhf(v); break;
         case 10: r = fb_sfu_expf(v); break;
         case 11: r = fb_sfu_logf(v); break;
         case 12: r = fb_sfu_softplusf(v); break;

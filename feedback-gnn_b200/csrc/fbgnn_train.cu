@@ -50,7 +50,11 @@ extern "C" int fbgnn_second_stage_grad(fbgnn_code *code, fbgnn_gnn *gnn, int32_t
     ga.logit_hx = v2<const float>(logit_hx); ga.logit_hz = v2<const float>(logit_hz);
     ga.sx = v2<const uint8_t>(synd_x); ga.sz = v2<const uint8_t>(synd_z);
     ga.out = View3<float>{llr, (int64_t)3 * n, 3, 1};                     // (b, v, k)
+    // the reverse sweep below differentiates the exact arithmetic: run the forward GNN in it as well
+    const int saved_math = ctx->math_mode;
+    ctx->math_mode = FBGNN_MATH_EXACT;
     int rc = launch_gnn(ctx, gnn, ga);
+    ctx->math_mode = saved_math;
 
     train::Bp4GradArgs ba{};
     ba.X = X; ba.Z = Z; ba.num_iter = num_iter; ba.loss_from = loss_from; ba.factor = factor; ba.B = B;

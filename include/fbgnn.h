@@ -314,7 +314,7 @@ int fbgnn_sfu_peak(fbgnn_ctx *ctx, double *evals_per_s);
 int fbgnn_fma_peak(fbgnn_ctx *ctx, double *instr_per_s);
 /* Elementwise probes of the arithmetic specification (tests): fn in {"exp","log","log1p",
  * "softplus","phi4","phi2","tanh","atanh"} (exact arithmetic), {"sfu_exp","sfu_log","sfu_softplus","sfu_phi4","sfu_phi2"}
- * (SFU arithmetic) and the raw hardware functions {"mufu_ex2","mufu_lg2"} (tools/dump_sfu_tables.py); x,y device float32 [n]. */
+ * "sfu_tanh","sfu_atanh" (SFU arithmetic) and the raw hardware functions {"mufu_ex2","mufu_lg2","mufu_rcp"} (tools/dump_sfu_tables.py); x,y device float32 [n]. */
 int fbgnn_math_probe(fbgnn_ctx *ctx, const char *fn, const float *x, float *y, int64_t n);
 
 #ifdef __cplusplus

@@ -211,7 +211,7 @@ static void cn_update(const orc_side_t *S, int cn_type, int phi4, float factor,
             /* decoding_q.py:327-361 */
             float P = 1.0f;
             for (int k = k0; k < k1; k++) {
-                float t = fb_tanhf(FB_MUL(msg[S->cn_edge[k]], 0.5f));
+                float t = fb_m_tanhf(FB_MUL(msg[S->cn_edge[k]], 0.5f));
                 if (t == 0.0f) t = 1e-12f;
                 work[k - k0] = t;
                 P = FB_MUL(P, t);
@@ -221,7 +221,7 @@ static void cn_update(const orc_side_t *S, int cn_type, int phi4, float factor,
                 float v = FB_MUL(FB_DIV(1.0f, work[k - k0]), P);
                 if (fabsf(v) < 1e-7f) v = 0.0f;
                 v = FB_FMIN(FB_FMAX(v, -FB_ATANH_CLIP), FB_ATANH_CLIP);
-                v = FB_MUL(2.0f, fb_atanhf(v));
+                v = FB_MUL(2.0f, fb_m_atanhf(v));
                 msg[S->cn_edge[k]] = FB_MUL(v, factor);
             }
         } else {
@@ -486,7 +486,7 @@ void orc_bp2(const orc_side_t *S, int cn_type, int num_iter, float factor, int64
 
 /* ---------------------------------------------------------------- feedback GNN ----- */
 static float gnn_act(int act, float x) {
-    if (act == 0) return fb_tanhf(x);
+    if (act == 0) return fb_m_tanhf(x);
     if (act == 1) return x > 0.0f ? x : 0.0f;
     return x;
 }
@@ -1154,6 +1154,8 @@ ORC_VEC(orc_m_phi4f, fb_m_phi4f)
 ORC_VEC(orc_m_phi2f, fb_m_phi2f)
 ORC_VEC(orc_sfu_expf, fb_sfu_expf)
 ORC_VEC(orc_sfu_logf, fb_sfu_logf)
+ORC_VEC(orc_m_tanhf, fb_m_tanhf)
+ORC_VEC(orc_m_atanhf, fb_m_atanhf)
 void orc_logaddexpf(const float *a, const float *b, float *y, int64_t n) {
     for (int64_t i = 0; i < n; i++) y[i] = fb_m_logaddexpf(a[i], b[i]);
 }
@@ -1169,12 +1171,12 @@ int orc_num_threads(void) {
  * needs orc_set_sfu_tables first).  See fb_math.h. */
 int orc_set_math(int mode) {
     if (mode != 0 && mode != 1) return -1;
-    if (mode == 1 && (!fb_sfu_ex2_tab || !fb_sfu_lg2_tab)) return -2;
+    if (mode == 1 && (!fb_sfu_ex2_tab || !fb_sfu_lg2_tab || !fb_sfu_rcp_tab)) return -2;
     fb_math_mode = mode;
     return 0;
 }
 int orc_get_math(void) { return fb_math_mode; }
-void orc_set_sfu_tables(const float *ex2_tab, const float *lg2_tab) { fb_sfu_set_tables(ex2_tab, lg2_tab); }
+void orc_set_sfu_tables(const float *ex2_tab, const float *lg2_tab, const float *rcp_tab) { fb_sfu_set_tables(ex2_tab, lg2_tab, rcp_tab); }
 
 void orc_set_num_threads(int t) {
 #ifdef _OPENMP

@@ -37,15 +37,18 @@ def test_hardware_matches_the_committed_tables(sfu, oracle):
         _ffi.call("fbgnn_math_probe", ctx.handle, fn.encode(), dx.ptr, dy.ptr, x.size)
         return dy.numpy()
 
-    ex2, lg2 = T.tables()
+    ex2, lg2, rcp = T.tables()
     rng = np.random.default_rng(1)
-    for fn, inputs, table in (("mufu_ex2", T.ex2_inputs(), ex2), ("mufu_lg2", T.lg2_inputs(), lg2)):
+    for fn, inputs, table in (("mufu_ex2", T.ex2_inputs(), ex2), ("mufu_lg2", T.lg2_inputs(), lg2),
+                              ("mufu_rcp", T.rcp_inputs(), rcp)):
         P.assert_bitexact(probe(fn, inputs), table, fn)             # exhaustive: all 2^23 (+8193) entries
     cases = {"sfu_exp": ("sfu_expf", rng.uniform(-100, 88, 400000)),
              "sfu_log": ("sfu_logf", np.exp(rng.uniform(-80, 80, 400000))),
              "sfu_softplus": ("m_softplusf", rng.uniform(-110, 110, 400000)),
              "sfu_phi4": ("m_phi4f", np.exp(rng.uniform(np.log(1e-8), np.log(30), 400000))),
-             "sfu_phi2": ("m_phi2f", np.exp(rng.uniform(np.log(1e-8), np.log(30), 400000)))}
+             "sfu_phi2": ("m_phi2f", np.exp(rng.uniform(np.log(1e-8), np.log(30), 400000))),
+             "sfu_tanh": ("m_tanhf", rng.uniform(-20, 20, 400000)),
+             "sfu_atanh": ("m_atanhf", rng.uniform(-0.9999999, 0.9999999, 400000))}
     for fn, (ofn, x) in cases.items():
         x = x.astype(np.float32)
         P.assert_bitexact(probe(fn, x), oracle.math_fn(ofn, x), fn)
@@ -56,6 +59,19 @@ def test_hardware_matches_the_committed_tables(sfu, oracle):
 def test_bp4_layer_bitexact_sfu(sfu, codes, oracle, name, B, p, cn_type, factor):
     import test_gpu_parity as P
     P.test_bp4_layer_bitexact(codes, oracle, name, B, p, cn_type, factor)
+
+
+@pytest.mark.parametrize("reduce_op", ["mean", "max"])
+def test_gnn_layers_bitexact_sfu(sfu, codes, c1270, oracle, weights, reduce_op):
+    """Feedback_GNN and GNN_BP4 with tanh on the SFU (exp + MUFU.RCP)."""
+    import test_gpu_baseline_configs as C
+    import test_gpu_parity as P
+    import test_gnn_bp4 as G
+    P.test_gnn_layer_bitexact(codes, oracle, weights, "c882", "c882", reduce_op)
+    if reduce_op == "mean":
+        C.test_gnn_layer_bitexact_c1270(c1270, oracle, weights)
+        P.test_gnn_irregular_code_and_relu(codes, oracle)
+        G.test_cuda_gnn_bp4_bitexact(oracle, codes, "c882", "mean", True)
 
 
 @pytest.mark.parametrize("name", ["rsurf3", "c882"])

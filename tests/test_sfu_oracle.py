@@ -15,9 +15,11 @@ def sfu_oracle(oracle):
 def test_tables_load_and_are_sane():
     from oracle import sfu_tables as T
     assert T.available()
-    ex2, lg2 = T.tables()
-    assert ex2.size == T.EX2_COUNT and lg2.size == T.LG2_COUNT
-    assert np.all(np.diff(ex2) >= 0) and np.all(np.diff(lg2) >= 0)          # the MUFU is monotone on both sets
+    ex2, lg2, rcp = T.tables()
+    assert ex2.size == T.EX2_COUNT and lg2.size == T.LG2_COUNT and rcp.size == T.RCP_COUNT
+    assert np.all(np.diff(ex2) >= 0) and np.all(np.diff(lg2) >= 0) and np.all(np.diff(rcp) <= 0)     # monotone
+    assert rcp[0] == 1.0 and rcp[-1] == 0.5 and lg2[-1] == 1.0
+    assert np.max(np.abs(rcp * T.rcp_inputs().astype(np.float64) - 1)) < 2.0 ** -22.5
     assert ex2[0x3fc00000 - T.EX2_BASE] == 1.0 and lg2[0x3f800000 - T.LG2_BASE] == 0.0
     # within a few ulp / 2^-22 of the true functions (PTX: ex2.approx 2 ulp, lg2.approx 2^-22 absolute on (0.5, 2))
     w = T.ex2_inputs().astype(np.float64)
@@ -43,6 +45,10 @@ def test_sfu_functions_accuracy_and_known_answers(sfu_oracle):
     xs = np.exp(rng.uniform(np.log(8.5e-8), np.log(16.635532), 500000)).astype(np.float32)
     ps = O.math_fn("m_phi4f", xs)
     assert ps.min() >= 0.0 and ps.max() <= np.float32(16.635532) + np.float32(0.7)
+    t = rng.uniform(-12, 12, 300000).astype(np.float32)
+    th = O.math_fn("m_tanhf", t)
+    assert np.max(np.abs(th - np.tanh(t.astype(np.float64)))) < 4e-7 and np.all(np.abs(th) <= 1.0)
+    assert O.math_fn("m_tanhf", np.array([0.0, 30.0, -30.0], np.float32)).tolist() == [0.0, 1.0, -1.0]
     sp = O.math_fn("m_softplusf", np.array([-100, -20, -1, 0, 1, 13.9, 14, 50], np.float32))
     assert np.allclose(sp, np.logaddexp(0, np.array([-100, -20, -1, 0, 1, 13.9, 14, 50], np.float64)), rtol=3e-7, atol=2e-7)
 
