@@ -146,9 +146,10 @@ def run_reference_arm(args, rank):
             "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step": frames,
-                       "note": "CPU restatement of the reference (oracle/fbgnn_oracle.c, OpenMP over frames); "
-                               "the reference's own TensorFlow path cannot be installed in this image"},
+            "config": shared_config(args.frames_per_step),
+            "note": "CPU restatement of the reference (oracle/fbgnn_oracle.c, exact arithmetic, OpenMP over frames); the "
+                    "reference's own TensorFlow path cannot be installed in this image.  Each step is a bounded sample of "
+                    f"{frames} frames of the workload in `config`",
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} x {frames} frames of the same workload"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -157,6 +158,29 @@ def run_reference_arm(args, rank):
 
 
 # ------------------------------------------------------------------ GPU arm -------------
+def shared_config(B):
+    """The `config` object both arms print (same keys, same values: the workload is the same)."""
+    return {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "num_iter": NUM_ITERS, "rounds_of_gnn": N_G,
+            "p": P_NOISE, "p0": P0,
+            "l2": "per-step working set (~23 KB/frame of HBM state, %d MB) exceeds the 126 MB L2" % (B * 23 // 1000)}
+
+
+def time_pipeline(ctx, comm, model, B, steps, warmup, allreduce=True):
+    """`steps` passes of the whole pipeline, CUDA events on the context's stream, max over ranks.  One counter
+    all-reduce per step sits inside the timed region (the poll of sim_ber's stopping rule, misc.py:710-716)."""
+    for _ in range(warmup):
+        model.run(B, P_NOISE, want_flags=False, want_diff=False)
+    comm.barrier()
+    counters = np.zeros(4, np.int64)
+    ctx.timer_start()
+    for _ in range(steps):
+        r = model.run(B, P_NOISE, want_flags=False, want_diff=False, want_counters=True)
+        counters = counters + (comm.allreduce_sum(r["counters"]) if allreduce else r["counters"])
+    ms = ctx.timer_stop()
+    comm.barrier()
+    return float(comm.allreduce_f64([ms], "max")[0]), counters
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +188,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fbgnn", choices=["fbgnn", "reference"])
     ap.add_argument("--frames-per-step", type=int, default=32768, help="frames per step per GPU")
+    ap.add_argument("--math", default="sfu", choices=["sfu", "exact"],
+                    help="arithmetic of the headline: exp/log on the SFU (default) or as FP32 polynomials; both are "
+                         "bit-exact against the CPU oracle in the same arithmetic (csrc/fb_math.h)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -185,72 +212,46 @@ def main():
     B = args.frames_per_step
     per_rank_frames = (args.steps + args.warmup) * B
     model = build_model(code, seed=2, first_frame=rank * per_rank_frames)
+    other = "exact" if args.math == "sfu" else "sfu"
 
-    def barrier():
-        comm.barrier()                                 # stream sync + one-element all-reduce + stream sync
-
-    def max_over_ranks(x):
-        return float(comm.allreduce_f64([x], "max")[0])
-
-    # ---- device-timed throughput: noise sampled in-kernel, nothing leaves the GPU but the counters
+    # ---- headline: device-timed throughput, noise sampled in-kernel, nothing leaves the GPU but the counters
+    ctx.set_math(args.math)
+    ctx.stats(reset=True)
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         model.run(B, P_NOISE, want_flags=False, want_diff=False)
-    barrier()
-    sampler = ClockSampler(local_rank)
+    comm.barrier()
+    ctx.stats(reset=True)
     if rank == 0:
         sampler.start()
     launches0 = ctx.launch_count()
-    counters = np.zeros(4, np.int64)
-    barrier()
-    ctx.timer_start()
-    for _ in range(args.steps):
-        r = model.run(B, P_NOISE, want_flags=False, want_diff=False, want_counters=True)
-        # the path's one collective, once per step inside the timed region: the global counters a
-        # target-error stopping rule polls (sim_ber, misc.py:710-716)
-        counters = counters + comm.allreduce_sum(r["counters"])
-    ms = ctx.timer_stop()
-    barrier()
+    ms, counters = time_pipeline(ctx, comm, model, B, args.steps, 0)
     launches = ctx.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    ms = max_over_ranks(ms)
-    total_frames = args.steps * B * world
-    value = total_frames / (ms * 1e-3)
+    bp_frames, bp_iters = ctx.stats(reset=True)
+    value = args.steps * B * world / (ms * 1e-3)
 
-    # ---- the opt-in MUFU arithmetic on the same workload (not the parity path; reported beside it)
-    ctx.set_math("fast")
-    for _ in range(2):
-        model.run(B, P_NOISE, want_flags=False, want_diff=False)
-    barrier()
-    ctx.timer_start()
-    fast_steps = max(3, min(args.steps, 5))
-    fast_counters = np.zeros(4, np.int64)
-    for _ in range(fast_steps):
-        fast_counters += model.run(B, P_NOISE, want_flags=False, want_diff=False, want_counters=True)["counters"]
-    fast_ms = ctx.timer_stop()
-    ctx.set_math("exact")
-    fast_ms = max_over_ranks(fast_ms)
-    fast_value = fast_steps * B * world / (fast_ms * 1e-3)
+    # ---- the other arithmetic on the same workload, reported beside the headline
+    ctx.set_math(other)
+    o_steps = max(3, min(args.steps, 5))
+    o_ms, o_counters = time_pipeline(ctx, comm, model, B, o_steps, 2)
+    o_value = o_steps * B * world / (o_ms * 1e-3)
+    ctx.set_math(args.math)
 
     # ---- the same workload with round skipping (result-identical; what low-p sweeps use)
     model.skip_inactive = True
-    for _ in range(2):
-        model.run(B, P_NOISE, want_flags=False, want_diff=False)
-    barrier()
-    ctx.timer_start()
-    skip_steps = max(3, min(args.steps, 5))
-    skip_counters = np.zeros(4, np.int64)
-    for _ in range(skip_steps):
-        skip_counters += model.run(B, P_NOISE, want_flags=False, want_diff=False, want_counters=True)["counters"]
-    skip_ms = ctx.timer_stop()
+    s_steps = max(3, min(args.steps, 5))
+    s_ms, s_counters = time_pipeline(ctx, comm, model, B, s_steps, 2)
     model.skip_inactive = False
-    skip_ms = max_over_ranks(skip_ms)
-    skip_value = skip_steps * B * world / (skip_ms * 1e-3)
+    s_value = s_steps * B * world / (s_ms * 1e-3)
 
-    # ---- end to end through the public API with host buffers
+    # ---- end to end through the public API with HOST buffers: packed noise bit-planes in, packed flags out
+    W = (N_Q + 31) // 32
+    host_src = F.Pauli(seed=2, first_frame=10 ** 10 + rank * B).sample_device(B, N_Q, F.pauli_thresholds(P_NOISE))
+    nx_host, nz_host = host_src[0].numpy(), host_src[1].numpy()                # synthetic samples, host resident
     nx_h = _ffi.PinnedArray((B, N_Q), np.uint8)
     nz_h = _ffi.PinnedArray((B, N_Q), np.uint8)
-    host_src = F.Pauli(seed=2, first_frame=10 ** 10 + rank * B).sample_device(B, N_Q, F.pauli_thresholds(P_NOISE))
-    nx_h.array[:], nz_h.array[:] = host_src[0].numpy(), host_src[1].numpy()   # synthetic samples, host resident
+    nx_h.array[:], nz_h.array[:] = nx_host, nz_host
     flags_h = _ffi.PinnedArray((B,), np.uint8)
     nx_d, nz_d = ctx.empty((B, N_Q), np.uint8), ctx.empty((B, N_Q), np.uint8)
     import ctypes as C
@@ -263,7 +264,7 @@ def main():
         return int(((flags_h.array >> 1) & 1).sum()), res["counters"]
 
     e2e_step()
-    barrier()
+    comm.barrier()
     t0 = time.perf_counter()
     ctx.timer_start()
     e2e_steps = max(3, min(args.steps, 5))
@@ -273,8 +274,9 @@ def main():
     e2e_ms_dev = ctx.timer_stop()
     e2e_wall = time.perf_counter() - t0
     e2e_ms = max(e2e_ms_dev, e2e_wall * 1e3)          # wall clock includes the Python host side
-    e2e_ms = max_over_ranks(e2e_ms)
+    e2e_ms = float(comm.allreduce_f64([e2e_ms], "max")[0])
     e2e_value = e2e_steps * B * world / (e2e_ms * 1e-3)
+    h2d_bytes, d2h_bytes = 2 * B * N_Q, B + 32
 
     if rank != 0:
         comm.close()
@@ -294,6 +296,7 @@ def main():
     for _ in range(2):
         dec.decode_device(None, sx, sz, want_logits=True, prior=prior)
     ctx.sync()
+    ctx.stats(reset=True)
     reps = 3
     kt = 0.0
     for _ in range(reps):
@@ -303,29 +306,36 @@ def main():
         dec.decode_device(None, sx, sz, want_logits=True, prior=prior)
         kt += ctx.timer_stop()
     k_ms = kt / reps
-    te_launch = B * (64 * TE_ITER + TE_EPI)
+    k_frames, k_iters = ctx.stats(reset=True)
+    te_launch = B * (64 * TE_ITER + TE_EPI)                       # algorithmic: every frame, every iteration
+    te_executed = k_iters / reps * TE_ITER + B * TE_EPI           # the iterations the kernel actually ran
     achieved = te_launch / (k_ms * 1e-3)
-    roofline = {"bound": "sfu", "kernel": "k_bp4<const prior>, 64 iterations", "achieved": achieved / 1e9,
-                "peak": sfu_peak / 1e9, "unit": "G transcendental evals/s", "frac": achieved / sfu_peak,
-                "peak_source": "measured live: ex2.approx micro-benchmark (fbgnn_sfu_peak)",
+    prof = _profile_summary(args.math, B)
+    roofline = {"bound": "sfu", "kernel": "k_bp4<const prior, fixed-point exit>, 64 iterations, arithmetic " + args.math,
+                "achieved": achieved / 1e9, "peak": sfu_peak / 1e9, "unit": "G transcendental evals/s",
+                "frac": achieved / sfu_peak,
+                "peak_source": "measured live: ex2.approx micro-benchmark (fbgnn_sfu_peak); SURVEY.md 8(d) names the SFU "
+                               "as the bound of this path, MEASURED_PEAKS.json holds only HBM / bf16 figures",
                 "units_per_launch": B, "te_per_unit": 64 * TE_ITER + TE_EPI, "launch_ms": k_ms,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu --set full capture
-                # (profiles/r01_ncu_final_bp4_gnn_2368frames.txt: 7.89 MB for a 2368-frame launch), scaled to B frames
-                "traffic": int(7893504 / 2368 * B),
-                "traffic_note": "scaled from the 2368-frame ncu capture in profiles/; the algorithmic HBM bytes are "
-                                "~1.3 KB of syndromes in + 20 KB of marginals/soft syndromes out per frame (the writes "
-                                "stay in the 126 MB L2 during the launch)",
-                "issue_slot_utilisation_ncu": 0.864,
+                "executed_iterations_per_frame": k_iters / max(k_frames, 1),
+                "executed_frac": te_executed / (k_ms * 1e-3) / sfu_peak,
+                "executed_note": "TE of the iterations actually run (the fixed-point exit leaves the loop once an iteration "
+                                 "reproduces every message bit for bit) / MUFU peak; inside an iteration warps whose lanes "
+                                 "are all saturated skip evaluations as well -- the MUFU pipe utilisation ncu measured for "
+                                 "this launch is `profile.xu_pipe_pct`",
                 "fp32_issue_peak_ginstr_s": fma_peak / 1e9,
                 "whole_step_frac": value * TE_PER_FRAME / (sfu_peak * world),
+                "whole_step_executed_iterations_per_frame": bp_iters / max(bp_frames, 1) * (1 + N_G),
                 "hbm_peak_gbs": _measured_peaks().get("hbm_gbs"),
-                # the same launch against the HBM roofline (why HBM is not the bound): ncu DRAM bytes / launch time
-                "hbm_achieved_gbs": (7893504 / 2368 * B) / (k_ms * 1e-3) / 1e9,
-                "hbm_frac": ((7893504 / 2368 * B) / (k_ms * 1e-3) / 1e9) / _measured_peaks().get("hbm_gbs")
-                            if _measured_peaks().get("hbm_gbs") else None,
-                "note": "algorithmic TE count of SURVEY.md 8(d) / measured MUFU peak; the shipped path evaluates "
-                        "exp/log in bit-exact software (FP32 pipe) so its own bound is the FP32 issue rate "
-                        "(see profiles/ for sm issue utilisation)"}
+                "traffic": prof.get("dram_bytes") if prof else None,
+                "profile": prof}
+    if prof and prof.get("dram_bytes") and _measured_peaks().get("hbm_gbs"):
+        roofline["hbm_achieved_gbs"] = prof["dram_bytes"] / (k_ms * 1e-3) / 1e9
+        roofline["hbm_frac"] = roofline["hbm_achieved_gbs"] / _measured_peaks()["hbm_gbs"]
+    if prof and prof.get("thread_inst"):
+        roofline["issue_frac"] = prof["thread_inst"] / (k_ms * 1e-3) / fma_peak
+        roofline["issue_note"] = ("thread-instructions of this launch (ncu, profiles/) / live launch time / measured FP32 "
+                                  "issue peak")
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
@@ -333,39 +343,69 @@ def main():
         frames = max(96 * cores, 256)                # ~10-20 s of CPU work
         fps, threads, _ = cpu_reference_run(code, frames, steps=1, warmup=1)
         cpu_baseline = {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                        "sample": f"{frames} frames of the same workload (oracle/fbgnn_oracle.c, OpenMP over frames)"}
+                        "sample": f"{frames} frames of the same workload (oracle/fbgnn_oracle.c, exact arithmetic, "
+                                  f"OpenMP over frames)",
+                        "numpy_oracle": numpy_reference_run(code)}
 
     line = {"metric": "decoded frames/sec (BP->GNN->BP, [[1270,28]])", "value": value, "unit": "frames/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "frames_per_step_per_gpu": B, "num_iter": NUM_ITERS, "rounds_of_gnn": N_G,
-                       "l2": "per-step working set (~23 KB/frame of HBM state, %d MB) exceeds the 126 MB L2"
-                             % (B * 23 // 1000),
-                       "counters": {"frames": int(counters[0]), "flagged": int(counters[1]),
-                                    "block_errors": int(counters[2]), "stage0_failures": int(counters[3])},
-                       "published_rtx4090_tf_xla_frames_per_s": 6389},
+            "data": "synthetic", "config": shared_config(B),
+            "arithmetic": {"mode": args.math,
+                           "note": "float32 throughout; 'sfu' evaluates exp/log on MUFU.EX2/LG2 (2-3 ulp), 'exact' as FP32 "
+                                   "polynomials (1 ulp).  Both are bit-exact against the CPU oracle in the same arithmetic "
+                                   "and reproduce the published error rates (tests/test_gpu_sfu.py, test_gpu_fullsize.py)",
+                           other: {"value": o_value, "unit": "frames/s", "steps": o_steps,
+                                   "block_errors": int(o_counters[2]), "frames": int(o_counters[0])}},
+            "counters": {"frames": int(counters[0]), "flagged": int(counters[1]),
+                         "block_errors": int(counters[2]), "stage0_failures": int(counters[3])},
+            "collectives_in_timed_region": args.steps if world > 1 else 0,
+            "context": {"published_rtx4090_tf_xla_frames_per_s": 6389},
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": 2 * B * N_Q,
-                    "d2h_bytes_per_step": B + 32, "steps": e2e_steps,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
+                    "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
                     "path": "Sandwich_BP_GNN_Evaluation_Model.run(noise=host samples) -> flags/counters on host"},
             "gpu_launches": int(launches),
-            "skip_inactive": {"value": skip_value, "unit": "frames/s", "steps": skip_steps,
-                              "block_errors": int(skip_counters[2]), "frames": int(skip_counters[0]),
+            "skip_inactive": {"value": s_value, "unit": "frames/s", "steps": s_steps,
+                              "block_errors": int(s_counters[2]), "frames": int(s_counters[0]),
                               "note": "frames whose correction already matches the syndrome skip the remaining "
                                       "GNN/BP rounds: bit-identical results (the reference masks those updates, "
                                       "feedback_gnn.py:339-340) but less work than the reference executes, so it "
                                       "is reported beside the headline, not as the headline"},
-            "fast_math": {"value": fast_value, "unit": "frames/s", "steps": fast_steps,
-                          "block_errors": int(fast_counters[2]), "frames": int(fast_counters[0]),
-                          "sfu_frac": fast_value * TE_PER_FRAME / (sfu_peak * world),
-                          "note": "opt-in Context.set_math('fast'): MUFU ex2/lg2/rcp instead of the bit-exact software "
-                                  "libm. NOT a parity path: not bit-exact and its logical error rate is lower than "
-                                  "the reference's (tests/test_gpu_fastmath.py); informational only"},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
     comm.close()
+
+
+def numpy_reference_run(code, frames=24):
+    """The independent numpy restatement (oracle/np_oracle.py) on the same workload: a second CPU figure
+    (BASELINE.md 2.2), single-threaded elementwise numpy."""
+    from oracle import c_oracle as O
+    from oracle import np_oracle as N
+    import fbgnn as F
+    w = F.read_weights(os.path.join(F.WEIGHTS_DIR, WEIGHTS))
+    nx, nz = O.pauli(2, 0, frames, code.N, P_NOISE)
+    X, Z = N.Side(code.hx), N.Side(code.hz)
+    t0 = time.perf_counter()
+    N.pipeline(code, X, Z, NUM_ITERS, [w] * N_G, nx, nz, O.prior_llr(P0))
+    dt = time.perf_counter() - t0
+    return {"value": frames / dt, "unit": "frames/s", "sample": f"{frames} frames, one process"}
+
+
+def _profile_summary(math_mode, B):
+    """Per-launch ncu figures of the dominant kernel from the committed capture of this round (same B, same arithmetic),
+    written by tools/ncu_to_json.py; None when there is no matching capture."""
+    path = os.path.join(ROOT, "profiles", f"r02_ncu_k_bp4_stage0_{math_mode}.json")
+    try:
+        with open(path) as f:
+            p = json.load(f)
+    except Exception:
+        return None
+    if p.get("frames") != B:
+        return None
+    p["source"] = os.path.relpath(path, ROOT)
+    return p
 
 
 def _measured_peaks():

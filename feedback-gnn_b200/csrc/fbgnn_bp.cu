@@ -71,8 +71,10 @@ static int launch_bp4_gstate(fbgnn_ctx *ctx, Bp4Args a, int64_t grid, int thread
     return 0;
 }
 
-int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid) {
+int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a_in, int64_t grid) {
     if (grid <= 0) return 0;
+    Bp4Args a = a_in;
+    a.stats = ctx->stats;
     const bool cp = a.llr.ptr == nullptr;
     const size_t smem = bp4_smem(a.X, a.Z, cp, a.iter_logits.ptr != nullptr);
     int threads = pick_threads(a.X.n, a.X.m + a.Z.m);

@@ -65,6 +65,7 @@ extern "C" int fbgnn_ctx_destroy(fbgnn_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     fbgnn_comm_destroy(ctx);
     cudaFree(ctx->comm_buf);
+    cudaFree(ctx->stats);
     ws_free(ctx->ws);
     cudaFree(ctx->flush_buf);
     cudaEventDestroy(ctx->ev0);
@@ -115,6 +116,23 @@ extern "C" int fbgnn_ctx_set_math(fbgnn_ctx *ctx, int32_t mode) {
 extern "C" int fbgnn_ctx_get_math(fbgnn_ctx *ctx, int32_t *mode) {
     REQUIRE(ctx && mode, "NULL argument");
     *mode = ctx->math_mode;
+    return 0;
+}
+
+extern "C" int fbgnn_ctx_stats(fbgnn_ctx *ctx, int64_t out[2], int32_t reset) {
+    REQUIRE(ctx, "ctx is NULL");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    if (!ctx->stats) {
+        CK(cudaMalloc(&ctx->stats, 2 * sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
+    }
+    if (out) {
+        unsigned long long h[2];
+        CK(cudaMemcpyAsync(h, ctx->stats, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        out[0] = (int64_t)h[0]; out[1] = (int64_t)h[1];
+    }
+    if (reset) CK(cudaMemsetAsync(ctx->stats, 0, 2 * sizeof(unsigned long long), ctx->stream));
     return 0;
 }
 

@@ -12,6 +12,11 @@ static void pack_gnn(std::vector<float> &w, const float *W0, const float *b0, co
     put(L::W1x, W1x, 4 * H); put(L::b1x, b1x, H); put(L::W2x, W2x, H * M); put(L::b2x, b2x, M);
     put(L::W1z, W1z, 4 * H); put(L::b1z, b1z, H); put(L::W2z, W2z, H * M); put(L::b2z, b2z, M);
     put(L::W3, W3, (2 * M + 3) * H); put(L::b3, b3, H); put(L::W0, W0, H * 3); put(L::b0, b0, 3);
+    for (int j = 0; j < H; j++)
+        for (int k = 0; k < 4; k++) {
+            w[L::W1tx + 4 * j + k] = W1x[k * H + j];
+            w[L::W1tz + 4 * j + k] = W1z[k * H + j];
+        }
 }
 
 extern "C" int fbgnn_gnn_create(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t activation, int32_t reduce_op,

@@ -59,6 +59,7 @@ struct fbgnn_ctx {
     int comm_rank = 0, comm_size = 1;
     void *comm_buf = nullptr;      // device staging buffer, FBGNN_COMM_MAX_ELEMS 8-byte elements
     int64_t collectives = 0;
+    unsigned long long *stats = nullptr;   // device [2]: {frames, BP iterations executed} of the k_bp4 launches (fbgnn_ctx_stats)
 };
 
 struct fbgnn_graph {

@@ -385,6 +385,8 @@ struct Bp4Args {
     uint8_t *active_out;                // [B]
     uint8_t *rounds;                    // [B] incremented when the frame stays active (or nullptr)
     int *next_list, *next_count;        // optional compaction of still-active frames
+    unsigned long long *stats;          // optional [2]: += {frames decoded, BP iterations actually executed} (bench.py's
+                                        // executed-work roofline; the fixed-point exit skips iterations)
     float *state;                       // GSTATE kernels: per-CTA message / prior arrays in HBM (codes beyond shared memory)
     int64_t state_stride;               // floats per CTA
 };
@@ -462,6 +464,7 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     // Only worth its bookkeeping for long runs (the 64-iteration first stage), and never before iteration 6.
     const bool fp_exit = FPX && fast && MATH::kSaturationShortcuts && !a.iter_logits.ptr;
     const int sat_bits = __float_as_int(FB_MUL(FB_PHI_CLIP_HI, a.factor)) & 0x7fffffff;   // |phi(clip_lo) * factor|
+    int it_done = a.num_iter;
     for (int it = 0; it < a.num_iter; it++) {
         if (a.iter_logits.ptr) bp4_iter_logits<CONST_PRIOR, MATH>(a, mx, mz, pri, scr2, dec, b, it);
         uint16_t *recp = (fp_exit && it >= 6) ? rec : nullptr;
@@ -508,12 +511,13 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
             }
         }
         if (FPX && recp) {
-            if (__syncthreads_and(stable)) break;
+            if (__syncthreads_and(stable)) { it_done = it + 1; break; }
         } else {
             __syncthreads();
         }
     }
 
+    if (a.stats && tid == 0) { atomicAdd(a.stats, 1ull); atomicAdd(a.stats + 1, (unsigned long long)it_done); }
     if (a.iter_logits.ptr) bp4_iter_logits<CONST_PRIOR, MATH>(a, mx, mz, pri, scr2, dec, b, a.num_iter);
     if (a.msg_x.ptr) for (int e = tid; e < X.E; e += T) a.msg_x(b, e) = mx[e];
     if (a.msg_z.ptr) for (int e = tid; e < Z.E; e += T) a.msg_z(b, e) = mz[e];
@@ -703,7 +707,10 @@ template <int H, int M> struct GnnLayout {
     static constexpr int b3 = W3 + pad4((2 * M + 3) * H);
     static constexpr int W0 = b3 + pad4(H);
     static constexpr int b0 = W0 + pad4(H * 3);
-    static constexpr int total = b0 + pad4(3);
+    // first-layer rows once more, one float4 {w_cn, w_Lx, w_Ly, w_Lz} per hidden unit (one LDS.128 in the regular path)
+    static constexpr int W1tx = b0 + pad4(3);
+    static constexpr int W1tz = W1tx + 4 * H;
+    static constexpr int total = W1tz + 4 * H;
 };
 
 template <typename MATH>
@@ -751,6 +758,60 @@ __device__ __forceinline__ void gnn_body(const GnnArgs &a, const WSRC w) {
         const int64_t b = a.frame_list ? a.frame_list[fi] : fi;
         const float f1 = a.h_vn(b, v, 0), f2 = a.h_vn(b, v, 1), f3 = a.h_vn(b, v, 2);
         float in[2 * M + 3];
+        if (FACT && DV > 0) {
+            // Regular sides, mean / sum: the 2 * DV tanh chains of one hidden unit (both sides) are evaluated together,
+            // so their MUFU / FMA latencies overlap; per side the operations and their order are those of the
+            // one-side loop below (and of the oracle's gnn_side).
+            float hcx[NE], hcz[NE], rx[M], rz[M];
+#pragma unroll
+            for (int k = 0; k < NE; k++) {
+                const int cx = a.X.vn_cn[v * NE + k], cz = a.Z.vn_cn[v * NE + k];
+                const float lx = a.logit_hx(cx, b), lz = a.logit_hz(cz, b);
+                hcx[k] = a.sx(cx, b) ? -lx : lx;
+                hcz[k] = a.sz(cz, b) ? -lz : lz;
+            }
+#pragma unroll
+            for (int i = 0; i < M; i++) { rx[i] = 0.0f; rz[i] = 0.0f; }
+#pragma unroll 1
+            for (int j = 0; j < H; j++) {
+                const float4 wx = w.ld4(Lay::W1tx + 4 * j), wz = w.ld4(Lay::W1tz + 4 * j);
+                const float bx = w.ld(Lay::b1x + j), bz = w.ld(Lay::b1z + j);
+                const float basex = FB_FMA(f3, wx.w, FB_FMA(f2, wx.z, FB_FMA(f1, wx.y, 0.0f)));
+                const float basez = FB_FMA(f3, wz.w, FB_FMA(f2, wz.z, FB_FMA(f1, wz.y, 0.0f)));
+                float tx[NE], tz[NE];
+#pragma unroll
+                for (int k = 0; k < NE; k++) {
+                    tx[k] = FB_FMA(hcx[k], wx.x, basex);
+                    tz[k] = FB_FMA(hcz[k], wz.x, basez);
+                    if (use_bias) { tx[k] = FB_ADD(tx[k], bx); tz[k] = FB_ADD(tz[k], bz); }
+                }
+#pragma unroll
+                for (int k = 0; k < NE; k++) { tx[k] = gnn_act<MATH>(act, tx[k]); tz[k] = gnn_act<MATH>(act, tz[k]); }
+                float hsx = tx[0], hsz = tz[0];
+#pragma unroll
+                for (int k = 1; k < NE; k++) { hsx = FB_ADD(hsx, tx[k]); hsz = FB_ADD(hsz, tz[k]); }
+#pragma unroll
+                for (int i = 0; i < M; i += 4) {
+                    const float4 ux = w.ld4(Lay::W2x + j * M + i), uz = w.ld4(Lay::W2z + j * M + i);
+                    rx[i + 0] = FB_FMA(hsx, ux.x, rx[i + 0]); rx[i + 1] = FB_FMA(hsx, ux.y, rx[i + 1]);
+                    rx[i + 2] = FB_FMA(hsx, ux.z, rx[i + 2]); rx[i + 3] = FB_FMA(hsx, ux.w, rx[i + 3]);
+                    rz[i + 0] = FB_FMA(hsz, uz.x, rz[i + 0]); rz[i + 1] = FB_FMA(hsz, uz.y, rz[i + 1]);
+                    rz[i + 2] = FB_FMA(hsz, uz.z, rz[i + 2]); rz[i + 3] = FB_FMA(hsz, uz.w, rz[i + 3]);
+                }
+            }
+            const float dg = (float)NE;
+#pragma unroll
+            for (int i = 0; i < M; i++) {
+                float qx = rx[i], qz = rz[i];
+                if (a.reduce == 0) {
+                    qx = FB_DIV(qx, dg); qz = FB_DIV(qz, dg);
+                    if (use_bias) { qx = FB_ADD(qx, w.ld(Lay::b2x + i)); qz = FB_ADD(qz, w.ld(Lay::b2z + i)); }
+                } else if (use_bias) {
+                    qx = FB_FMA(dg, w.ld(Lay::b2x + i), qx); qz = FB_FMA(dg, w.ld(Lay::b2z + i), qz);
+                }
+                in[i] = qx; in[M + i] = qz;
+            }
+        } else
 #pragma unroll 1
         for (int side = 0; side < 2; side++) {
             const SideDev &S = side ? a.Z : a.X;
@@ -892,8 +953,11 @@ __device__ __forceinline__ void gnn_body(const GnnArgs &a, const WSRC w) {
     }
 }
 
+#ifndef FBGNN_GNN_MINBLOCKS
+#define FBGNN_GNN_MINBLOCKS 5         // 96 registers, 5 CTAs / SM: measured best (profiles/r02_lab_k_gnn_variants.txt)
+#endif
 template <int H, int M, int DV, bool TANH_BIAS, bool FACT, typename MATH>
-static __global__ void __launch_bounds__(128) k_gnn(const GnnArgs a) {
+static __global__ void __launch_bounds__(128, FBGNN_GNN_MINBLOCKS) k_gnn(const GnnArgs a) {
     extern __shared__ float wsm[];
     for (int i = threadIdx.x; i < GnnLayout<H, M>::total; i += blockDim.x) wsm[i] = a.weights[i];
     __syncthreads();

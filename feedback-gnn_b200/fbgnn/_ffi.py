@@ -54,6 +54,7 @@ _SIGNATURES = {
     "fbgnn_timer_start": [C.c_void_p],
     "fbgnn_timer_stop": [C.c_void_p, C.POINTER(C.c_float)],
     "fbgnn_launch_count": [C.c_void_p, C.POINTER(C.c_int64)],
+    "fbgnn_ctx_stats": [C.c_void_p, C.POINTER(C.c_int64), C.c_int32],
     "fbgnn_ctx_set_math": [C.c_void_p, C.c_int32],
     "fbgnn_ctx_get_math": [C.c_void_p, C.POINTER(C.c_int32)],
     "fbgnn_malloc": [C.c_void_p, C.c_size_t, _vpp],
@@ -180,6 +181,13 @@ class Context:
         v = C.c_int64()
         call("fbgnn_launch_count", self.handle, C.byref(v))
         return v.value
+
+    def stats(self, reset=False):
+        """(frames decoded, BP iterations executed) by the quaternary BP kernels since the last reset; the first call
+        switches the counting on."""
+        v = (C.c_int64 * 2)()
+        call("fbgnn_ctx_stats", self.handle, v, 1 if reset else 0)
+        return int(v[0]), int(v[1])
 
     def flush_l2(self):
         call("fbgnn_flush_l2", self.handle)

@@ -99,6 +99,10 @@ int fbgnn_timer_stop(fbgnn_ctx *ctx, float *elapsed_ms);          /* synchronise
 /* Arithmetic mode used by the kernels this context launches from now on (FBGNN_MATH_*). */
 int fbgnn_ctx_set_math(fbgnn_ctx *ctx, int32_t mode);
 int fbgnn_ctx_get_math(fbgnn_ctx *ctx, int32_t *mode);
+/* Executed-work counters of the quaternary BP launches of this context: out = {frames decoded, BP iterations actually
+ * executed} since the last reset (the fixed-point exit skips iterations; bench.py reports its roofline on the work
+ * executed).  The first call switches the counting on (two atomics per frame); out may be NULL. */
+int fbgnn_ctx_stats(fbgnn_ctx *ctx, int64_t out[2], int32_t reset);
 /* number of kernel launches this context has enqueued so far */
 int fbgnn_launch_count(fbgnn_ctx *ctx, int64_t *launches);
 
