@@ -111,7 +111,22 @@ def load():
     decoding_q = _load("sionna.fec.ldpc.decoding_q", "sionna/fec/ldpc/decoding_q.py")
     feedback_gnn = _load("sionna.fec.ldpc.feedback_gnn", "sionna/fec/ldpc/feedback_gnn.py")
 
-    ns = types.SimpleNamespace(tf=tf, codes_q=codes_q, fec_utils=fec_utils, pauli=pauli, gnn=gnn, decoding_q=decoding_q,
+    # The binary decoder assumes scipy.sparse.find returns the entries column-major (true up to scipy 1.10;
+    # decoding_q.py carries an argsort "fix for scipy>=1.11", decoding.py does not -- SURVEY.md F8).  It is run here in
+    # the scipy environment it was written for: its module-level `sp` sees a find() with the old ordering.
+    import numpy as np
+    import scipy as real_sp
+    decoding = _load("sionna.fec.ldpc.decoding", "sionna/fec/ldpc/decoding.py")
+
+    def find_column_major(a):
+        i, j, v = real_sp.sparse.find(a)
+        order = np.lexsort((i, j))
+        return i[order], j[order], v[order]
+    sparse_proxy = types.SimpleNamespace(**{k: getattr(real_sp.sparse, k) for k in ("csr_matrix", "issparse", "csc_matrix")},
+                                         find=find_column_major)
+    decoding.sp = types.SimpleNamespace(sparse=sparse_proxy)
+
+    ns = types.SimpleNamespace(tf=tf, codes_q=codes_q, decoding=decoding, LDPCBPDecoder=decoding.LDPCBPDecoder, fec_utils=fec_utils, pauli=pauli, gnn=gnn, decoding_q=decoding_q,
                                feedback_gnn=feedback_gnn, metrics=metrics,
                                QLDPCBPDecoder=decoding_q.QLDPCBPDecoder, Feedback_GNN=feedback_gnn.Feedback_GNN,
                                Sandwich_BP_GNN_Evaluation_Model=feedback_gnn.Sandwich_BP_GNN_Evaluation_Model,

@@ -32,6 +32,10 @@ class T(np.ndarray):
     def numpy(self):
         return np.asarray(self)
 
+    def get_shape(self):
+        shape = tuple(self.shape)
+        return type("TensorShape", (tuple,), {"as_list": lambda s: list(s)})(shape)
+
     def __bool__(self):
         return bool(np.asarray(self))
 
@@ -380,6 +384,21 @@ def _map_fn(fn, elems, **kw):
     return _t(np.stack([_np(fn(e)) for e in _np(elems)]))
 
 
+def _while_loop(cond, body, loop_vars, maximum_iterations=None, **kw):
+    vars_ = tuple(loop_vars)
+    n = 0
+    while bool(np.asarray(cond(*vars_))) and (maximum_iterations is None or n < int(np.asarray(maximum_iterations))):
+        vars_ = tuple(body(*vars_))
+        n += 1
+    return vars_
+
+
+def _tensor_scatter_nd_add(tensor, indices, updates):
+    out = np.array(_np(tensor), copy=True)
+    np.add.at(out, tuple(_np(indices).T), _np(updates))
+    return _t(out)
+
+
 class TensorArray:
     def __init__(self, dtype, size=0, **kw):
         self.items = [None] * int(size)
@@ -662,6 +681,9 @@ def build_modules():
     tf.ensure_shape = lambda x, shape=None, **k: x
     tf.print = lambda *a, **k: None
     tf.map_fn = _map_fn
+    tf.while_loop = _while_loop
+    tf.tensor_scatter_nd_add = _tensor_scatter_nd_add
+    tf.slice = lambda x, begin, size: _t(_np(x)[tuple(slice(int(b), None if int(n) < 0 else int(b) + int(n)) for b, n in zip(begin, size))])
     tf.numpy_function = lambda f, inp, Tout=None: _t(f(*inp))
     tf.top_k = None
     tf.complex = lambda re, im: _t(_np(re) + 1j * _np(im))
@@ -669,7 +691,8 @@ def build_modules():
     tf.math = _module("tensorflow.math", softplus=_unary(_softplus), reduce_logsumexp=_reduce_logsumexp,
                       log=_unary(np.log), exp=_unary(np.exp), sigmoid=_unary(lambda x: 1 / (1 + np.exp(-x))),
                       multiply=tf.multiply, reduce_sum=tf.reduce_sum, reduce_min=tf.reduce_min, argmin=tf.argmin,
-                      mod=lambda a, b: _t(np.mod(_np(a), _np(b))), abs=tf.abs, tanh=tf.tanh, atanh=tf.atanh,
+                      mod=lambda a, b: _t(np.mod(_np(a), _np(b))), abs=tf.abs,
+                      pow=lambda a, b: _t(np.power(_np(a), _np(b))), tanh=tf.tanh, atanh=tf.atanh,
                       sign=tf.sign, logical_xor=lambda a, b: _t(np.logical_xor(_np(a), _np(b))),
                       logical_and=lambda a, b: _t(np.logical_and(_np(a), _np(b))),
                       logical_or=lambda a, b: _t(np.logical_or(_np(a), _np(b))),

@@ -126,9 +126,29 @@ def main():
             bp["c882.stage_two.llr_hat"] = np.asarray(llr_hat)
     np.savez_compressed(os.path.join(HERE, "ref_bp4.npz"), **bp)
 
+    # ---------------------------------------------------------------- 2b. LDPCBPDecoder.call, is_syndrome (decoding.py:875-1048)
+    from oracle import c_oracle as O
+    b2 = {}
+    for cname, B in (("c882", 12), ("rsurf3", 24), ("c1270", 6)):
+        code = built[cname]
+        noise = O.bsc(5, 0, B, code.N, 0.04)
+        synd = (code.hx @ noise.T.astype(np.int64)) & 1
+        rng = np.random.default_rng(0)
+        llr = (-np.log((1 - 0.1) / 0.1) + rng.normal(0, 0.2, (B, code.N))).astype(np.float32)
+        llr[0, :3] = [30.0, -30.0, 0.0]                                      # exercises the +-20 clip
+        b2[f"{cname}.llr"], b2[f"{cname}.synd"] = llr, synd.astype(np.uint8)
+        for cn_type in ("boxplus-phi", "minsum", "boxplus"):
+            for it in (1, 2, 5):
+                dec = ns.LDPCBPDecoder(code.hx, is_syndrome=True, num_iter=it, normalization_factor=0.9, cn_type=cn_type,
+                                       hard_out=False)
+                b2[f"{cname}.{cn_type}.{it}.soft"] = np.asarray(dec((tf.constant(llr), tf.constant(synd))))
+                hard = ns.LDPCBPDecoder(code.hx, is_syndrome=True, num_iter=it, normalization_factor=0.9, cn_type=cn_type)
+                b2[f"{cname}.{cn_type}.{it}.hard"] = np.asarray(hard((tf.constant(llr), tf.constant(synd)))).astype(np.uint8)
+        print("bp2", cname)
+    np.savez_compressed(os.path.join(HERE, "ref_bp2.npz"), **b2)
+
     # ---------------------------------------------------------------- 3. Feedback_GNN.call with the shipped weights
     gn = {}
-    from oracle import c_oracle as O
     for cname, wfile, B in (("c882", W882, 8), ("c1270", W1270, 4)):
         code = built[cname]
         bs, n = tf.constant(B), tf.constant(code.N)

@@ -10,6 +10,8 @@ for the CUDA path through the C ABI:
     iteration and 2e-3 after two (phi = softplus(x) - log(exp(x) - 1) cancels catastrophically, SURVEY.md H2, so the
     float32 noise of any two libms grows by ~10x per iteration; from iteration 3 on only robust statistics are asserted);
     soft syndromes within the float32 noise model of phi(sum phi(|.|)) (error ~ 4e-6 exp|logit|, saturating in steps of ln 2);
+  * LDPCBPDecoder.call (binary, is_syndrome): hard decisions identical, soft outputs within 5e-6 after one iteration,
+    5e-3 after five; min-sum bit-identical;
   * Feedback_GNN.call with the shipped weights loaded by the reference's load_weights: 1e-6 absolute, all four reduce ops;
   * Sandwich_BP_GNN_Evaluation_Model.call on the same uniforms: per-frame flagged / block-error indicators and the dense
     s_hat rows, identical on >= 97 % of the frames at p = 0.06 (>= 85 % in the chaotic regime p >= 0.08, F6 noise floor).
@@ -27,7 +29,7 @@ LN2 = 0.6931472
 
 @pytest.fixture(scope="module")
 def ref():
-    return {k: np.load(os.path.join(GOLDEN, f"ref_{k}.npz")) for k in ("codes", "bp4", "gnn", "sandwich")}
+    return {k: np.load(os.path.join(GOLDEN, f"ref_{k}.npz")) for k in ("codes", "bp4", "bp2", "gnn", "sandwich")}
 
 
 @pytest.fixture(scope="module")
@@ -117,6 +119,38 @@ def test_oracle_bp4_matches_the_reference_code(ref, allcodes, oracle, arith):
         assert np.all(np.abs(got - r) <= 6 * (2e-5 * a + 1e-5 + np.minimum(4e-6 * np.exp(np.minimum(a, 20.0)), 4 * LN2)))
 
 
+def _check_bp2(Z, key, soft, hard, what):
+    """LDPCBPDecoder (decoding.py, run with the column-major scipy.sparse.find it was written for)."""
+    it = int(key.rsplit(".", 1)[1])
+    r = Z[f"{key}.soft"]
+    err = np.abs(soft - r)
+    assert np.array_equal(hard, Z[f"{key}.hard"]), (what, key)
+    if ".minsum." in key:
+        assert err.max() == 0.0, (what, key)                  # no transcendental: bit-identical to the reference's code
+    elif ".boxplus." in key:
+        # tanh variant: |llr| = 20 (the clip) drives tanh(10) into saturation, where implementations differ in the last
+        # float32 step (numpy: exactly 1; Eigen's rational form as restated in fb_math.h: 1 - 2.4e-7) and atanh amplifies
+        # it -- a handful of saturated entries may differ by < 0.7, everything else agrees to rounding
+        bad = int(np.count_nonzero(err > (5e-6 if it == 1 else 2e-3)))
+        assert bad <= max(3, err.size // 1000) and err.max() <= 0.7, (what, key, bad, float(err.max()))
+    else:
+        assert err.max() <= (5e-6 if it == 1 else 1e-4 if it == 2 else 5e-3), (what, key, float(err.max()))
+
+
+def _bp2_cases(Z):
+    return sorted({k.rsplit(".", 1)[0] for k in Z.files if k.endswith(".soft")})
+
+
+@pytest.mark.parametrize("arith", ["exact", "sfu"])
+def test_oracle_bp2_matches_the_reference_code(ref, allcodes, oracle, arith):
+    Z = ref["bp2"]
+    with oracle.math(arith):
+        for key in _bp2_cases(Z):
+            cname, cn_type, it = key.split(".")
+            soft, hard = oracle.bp2(allcodes[cname].hx, Z[f"{cname}.llr"], Z[f"{cname}.synd"], int(it), 0.9, cn_type)
+            _check_bp2(Z, key, soft, hard, f"oracle[{arith}]")
+
+
 @pytest.mark.parametrize("arith", ["exact", "sfu"])
 def test_oracle_gnn_matches_the_reference_code(ref, allcodes, oracle, weights, arith):
     Z = ref["gnn"]
@@ -188,6 +222,13 @@ def test_cuda_bp4_and_gnn_match_the_reference_code(ref, allcodes, weights, arith
         got["x_hat"], got["z_hat"] = got["x_hat"].astype(np.uint8), got["z_hat"].astype(np.uint8)
         assert [o.dtype for o in out] == [np.dtype(d) for d in Z[f"{key}.dtypes"]]           # the reference's output dtypes
         _check_bp4(Z, key, got, f"cuda[{arith_gpu}]")
+    Zb = ref["bp2"]
+    for key in _bp2_cases(Zb):
+        cname, cn_type, it = key.split(".")
+        kw = dict(is_syndrome=True, num_iter=int(it), normalization_factor=0.9, cn_type=cn_type)
+        soft = F.LDPCBPDecoder(allcodes[cname].hx, hard_out=False, **kw)((Zb[f"{cname}.llr"], Zb[f"{cname}.synd"]))
+        hard = F.LDPCBPDecoder(allcodes[cname].hx, **kw)((Zb[f"{cname}.llr"], Zb[f"{cname}.synd"]))
+        _check_bp2(Zb, key, soft, hard.astype(np.uint8), f"cuda[{arith_gpu}]")
     Zg = ref["gnn"]
     for cname in ("c882", "c1270"):
         for red in ("mean", "sum", "max", "min"):
