@@ -92,11 +92,43 @@ int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a_in, int64_t grid) {
 }
 
 // ------------------------------------------------------------------ decoders ------------
-extern "C" int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
-                                fbgnn_tensor3 llr, float prior, fbgnn_tensor2 synd_x, fbgnn_tensor2 synd_z,
-                                fbgnn_tensor2 Lx, fbgnn_tensor2 Ly, fbgnn_tensor2 Lz, fbgnn_tensor2 x_hat,
-                                fbgnn_tensor2 z_hat, fbgnn_tensor2 x_logit, fbgnn_tensor2 z_logit,
-                                fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z, fbgnn_tensor3 iter_logits) {
+extern "C" int fbgnn_rows_create(fbgnn_ctx *ctx, int32_t n, int32_t m, const int32_t *indptr, const int32_t *indices,
+                                 fbgnn_rows **out) {
+    REQUIRE(ctx && out && indptr, "NULL argument");
+    REQUIRE(n > 0 && n <= 65535 && m >= 0, "bad shape (%d x %d; at most 65535 columns)", m, n);
+    REQUIRE(indptr[0] == 0, "indptr[0] != 0");
+    for (int r = 0; r < m; r++) {
+        REQUIRE(indptr[r + 1] >= indptr[r], "indptr not monotone at row %d", r);
+        for (int k = indptr[r]; k < indptr[r + 1]; k++)
+            REQUIRE(indices[k] >= 0 && indices[k] < n, "column index out of range in row %d", r);
+    }
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    fbgnn_rows *R = new fbgnn_rows();
+    R->ctx = ctx; R->n = n; R->m = m;
+    std::vector<idx_t> col(std::max(indptr[m], 1));
+    for (int k = 0; k < indptr[m]; k++) col[k] = (idx_t)indices[k];
+    CK(cudaMalloc(&R->ptr, sizeof(int) * (size_t)(m + 1)));
+    CK(cudaMemcpy(R->ptr, indptr, sizeof(int) * (size_t)(m + 1), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&R->col, sizeof(idx_t) * col.size()));
+    CK(cudaMemcpy(R->col, col.data(), sizeof(idx_t) * col.size(), cudaMemcpyHostToDevice));
+    *out = R;
+    return 0;
+}
+
+extern "C" int fbgnn_rows_destroy(fbgnn_rows *R) {
+    if (!R) return 0;
+    cudaSetDevice(R->ctx->device);
+    cudaFree(R->ptr); cudaFree(R->col);
+    delete R;
+    return 0;
+}
+
+extern "C" int fbgnn_bp4_decode_ex(fbgnn_code *code, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                                   fbgnn_tensor3 llr, float prior, fbgnn_tensor2 synd_x, fbgnn_tensor2 synd_z,
+                                   fbgnn_tensor2 Lx, fbgnn_tensor2 Ly, fbgnn_tensor2 Lz, fbgnn_tensor2 x_hat,
+                                   fbgnn_tensor2 z_hat, fbgnn_tensor2 x_logit, fbgnn_tensor2 z_logit,
+                                   fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z, fbgnn_tensor3 iter_logits,
+                                   const fbgnn_bp4_opts *opts) {
     REQUIRE(code, "code is NULL");
     REQUIRE(cn_type >= 0 && cn_type <= 2, "unknown cn_type %d", cn_type);
     REQUIRE(num_iter >= 0 && B >= 0, "num_iter and B must be non-negative");
@@ -113,7 +145,27 @@ extern "C" int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_i
     a.xl = v2<float>(x_logit); a.zl = v2<float>(z_logit);
     a.msg_x = v2<float>(msg_x); a.msg_z = v2<float>(msg_z);
     a.iter_logits = v3<float>(iter_logits);
+    if (opts) {
+        REQUIRE(!opts->iters_out || num_iter <= 255, "early stop reports iteration counts as uint8 (num_iter <= 255)");
+        REQUIRE(!opts->iters_out || !iter_logits.ptr, "early stop and per-iteration soft syndromes exclude each other");
+        REQUIRE((opts->rows_x == nullptr) == (opts->rows_z == nullptr), "give both rows_x and rows_z or neither");
+        a.iters_out = opts->iters_out;
+        if (opts->rows_x) {
+            REQUIRE(opts->rows_x->n == a.X.n && opts->rows_z->n == a.X.n, "row sets must have n = %d columns", a.X.n);
+            a.rows_x_ptr = opts->rows_x->ptr; a.rows_x_col = opts->rows_x->col; a.rows_x_m = opts->rows_x->m;
+            a.rows_z_ptr = opts->rows_z->ptr; a.rows_z_col = opts->rows_z->col; a.rows_z_m = opts->rows_z->m;
+        }
+    }
     return launch_bp4(ctx, a, B);
+}
+
+extern "C" int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                                fbgnn_tensor3 llr, float prior, fbgnn_tensor2 synd_x, fbgnn_tensor2 synd_z,
+                                fbgnn_tensor2 Lx, fbgnn_tensor2 Ly, fbgnn_tensor2 Lz, fbgnn_tensor2 x_hat,
+                                fbgnn_tensor2 z_hat, fbgnn_tensor2 x_logit, fbgnn_tensor2 z_logit,
+                                fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z, fbgnn_tensor3 iter_logits) {
+    return fbgnn_bp4_decode_ex(code, cn_type, num_iter, factor, B, llr, prior, synd_x, synd_z, Lx, Ly, Lz, x_hat, z_hat,
+                               x_logit, z_logit, msg_x, msg_z, iter_logits, nullptr);
 }
 
 static size_t bp2_smem(const SideDev &S) { return sizeof(float) * ((size_t)S.E + S.n) + S.m + S.n + 16; }

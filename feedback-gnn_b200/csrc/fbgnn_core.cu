@@ -54,7 +54,7 @@ extern "C" int fbgnn_ctx_create(int device, fbgnn_ctx **out) {
 
 void ws_free(Workspace &w) {
     cudaFree(w.vbits); cudaFree(w.sbits); cudaFree(w.active[0]); cudaFree(w.active[1]);
-    cudaFree(w.rounds); cudaFree(w.L); cudaFree(w.P); cudaFree(w.logit); cudaFree(w.list[0]);
+    cudaFree(w.rounds); cudaFree(w.iters); cudaFree(w.L); cudaFree(w.P); cudaFree(w.logit); cudaFree(w.list[0]);
     cudaFree(w.list[1]); cudaFree(w.list_count); cudaFree(w.counters);
     w = Workspace();
 }

@@ -35,7 +35,7 @@ int fbgnn_fail(int code, const char *fmt, ...);      // sets the thread-local me
 struct Workspace {                 // per-context scratch of the fused pipelines
     int64_t cap_frames = 0;
     int n = 0, m = 0;
-    uint8_t *vbits = nullptr, *sbits = nullptr, *active[2] = {nullptr, nullptr}, *rounds = nullptr;
+    uint8_t *vbits = nullptr, *sbits = nullptr, *active[2] = {nullptr, nullptr}, *rounds = nullptr, *iters = nullptr;
     float *L = nullptr, *P = nullptr, *logit = nullptr;
     int *list[2] = {nullptr, nullptr};
     int *list_count = nullptr;     // [2]
@@ -82,6 +82,13 @@ struct fbgnn_code {
     idx_t *lx_col = nullptr, *lz_col = nullptr;
     fbgnn_graph *basis_x = nullptr, *basis_z = nullptr;      // hx[pivot_hx], hz[pivot_hz]
     idx_t *pivot_x = nullptr, *pivot_z = nullptr;            // device [rank]
+};
+
+struct fbgnn_rows {
+    fbgnn_ctx *ctx;
+    int n = 0, m = 0;
+    int *ptr = nullptr;            // device [m+1]
+    idx_t *col = nullptr;          // device [nnz]
 };
 
 struct fbgnn_gnn {

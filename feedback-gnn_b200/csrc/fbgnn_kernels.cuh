@@ -385,6 +385,14 @@ struct Bp4Args {
     uint8_t *active_out;                // [B]
     uint8_t *rounds;                    // [B] incremented when the frame stays active (or nullptr)
     int *next_list, *next_count;        // optional compaction of still-active frames
+    uint8_t *iters_out;                 // optional [B]: OPT-IN early stop (not what the reference does) -- a
+                                        // frame leaves the loop once its hard decision reproduces the syndrome (warp-ballot
+                                        // check after every iteration); iters_out[b] = iterations executed
+    // optional row sets of the soft syndromes (CSR, int ptr / u16 col): the dense hx_perp / hz_perp rows of the reference's
+    // trainable mode (decoding_q.py:32-37, 93-94); default = rows of hz (x_logit) and hx (z_logit)
+    const int *rows_x_ptr, *rows_z_ptr;
+    const idx_t *rows_x_col, *rows_z_col;
+    int rows_x_m, rows_z_m;
     unsigned long long *stats;          // optional [2]: += {frames decoded, BP iterations actually executed} (bench.py's
                                         // executed-work roofline; the fixed-point exit skips iterations)
     float *state;                       // GSTATE kernels: per-CTA message / prior arrays in HBM (codes beyond shared memory)
@@ -416,6 +424,27 @@ __device__ void bp4_iter_logits(const Bp4Args &a, const float *mx, const float *
         scr[n + v] = MATH::phi4(fabsf(llr_zp));
     }
     __syncthreads();
+    if (a.rows_x_ptr) {                                 // custom row sets (dense hx_perp / hz_perp of the trainable mode)
+        for (int c = tid; c < a.rows_x_m + a.rows_z_m; c += T) {
+            const bool isz = c >= a.rows_x_m;           // rows_z -> z_logit (from llr_z'), rows_x -> x_logit
+            const int cc = isz ? c - a.rows_x_m : c;
+            const int *ptr = isz ? a.rows_z_ptr : a.rows_x_ptr;
+            const idx_t *col = isz ? a.rows_z_col : a.rows_x_col;
+            const float *sc = isz ? scr + n : scr;
+            int par = 0;
+            float Tsum = 0.0f;
+            for (int k = ptr[cc]; k < ptr[cc + 1]; k++) {
+                const int v = col[k];
+                par ^= (sgn[v] >> (isz ? 1 : 0)) & 1;
+                Tsum = FB_ADD(Tsum, sc[v]);
+            }
+            float val = MATH::phi4(Tsum);
+            val = par ? -val : val;
+            a.iter_logits(2 * slot + (isz ? 1 : 0), cc, b) = val;
+        }
+        __syncthreads();
+        return;
+    }
     for (int c = tid; c < X.m + Z.m; c += T) {
         const bool isx = c < X.m;                       // hx row -> z_logit (from llr_z'), hz row -> x_logit
         const SideDev &S = isx ? X : Z;
@@ -515,9 +544,43 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         } else {
             __syncthreads();
         }
+        if (a.iters_out) {
+            // opt-in early stop: hard decision of the current messages, then the syndrome of that decision
+            for (int v = tid; v < n; v += T) {
+                float Sx = 0.0f, Sz = 0.0f;
+                for (int e = X.vn_ptr[v]; e < X.vn_ptr[v + 1]; e++) Sx = FB_ADD(Sx, mx[e]);
+                for (int e = Z.vn_ptr[v]; e < Z.vn_ptr[v + 1]; e++) Sz = FB_ADD(Sz, mz[e]);
+                const float px = CONST_PRIOR ? a.prior : pri[v];
+                const float py = CONST_PRIOR ? a.prior : pri[n + v];
+                const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
+                const float ly = FB_ADD(FB_ADD(Sz, Sx), py), lx = FB_ADD(Sz, px), lz = FB_ADD(Sx, pz);
+                int d = 0;
+                float best = 0.0f;
+                if (lx < best) { best = lx; d = 1; }
+                if (lz < best) { best = lz; d = 2; }
+                if (ly < best) { best = ly; d = 3; }
+                dec[v] = (uint8_t)d;
+            }
+            __syncthreads();
+            bool bad = false;
+            const int mt = X.m + Z.m, mround = (mt + 31) & ~31;
+            for (int c = tid; c < mround; c += T) {
+                int par = 0;
+                if (c < mt) {
+                    const bool isx = c < X.m;                   // hx rows check z_hat (bit 1), hz rows check x_hat (bit 0)
+                    const SideDev &S = isx ? X : Z;
+                    const int cc = isx ? c : c - X.m;
+                    par = isx ? sbx[cc] : sbz[cc];
+                    for (int k = S.cn_ptr[cc]; k < S.cn_ptr[cc + 1]; k++) par ^= (dec[S.cn_vn[k]] >> (isx ? 1 : 0)) & 1;
+                }
+                bad |= __ballot_sync(0xffffffffu, par) != 0u;   // one vote per 32 checks
+            }
+            if (!__syncthreads_or(bad)) { it_done = it + 1; break; }
+        }
     }
 
     if (a.stats && tid == 0) { atomicAdd(a.stats, 1ull); atomicAdd(a.stats + 1, (unsigned long long)it_done); }
+    if (a.iters_out && tid == 0) a.iters_out[b] = (uint8_t)it_done;
     if (a.iter_logits.ptr) bp4_iter_logits<CONST_PRIOR, MATH>(a, mx, mz, pri, scr2, dec, b, a.num_iter);
     if (a.msg_x.ptr) for (int e = tid; e < X.E; e += T) a.msg_x(b, e) = mx[e];
     if (a.msg_z.ptr) for (int e = tid; e < Z.E; e += T) a.msg_z(b, e) = mz[e];
@@ -572,10 +635,30 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
             if (want_logits) Tsum = FB_ADD(Tsum, scr[v]);
         }
         mismatch |= dpar ^ (isx ? sbx[cc] : sbz[cc]);
-        if (want_logits) {
+        if (want_logits && !a.rows_x_ptr) {
             float val = MATH::phi4(Tsum);
             val = par ? -val : val;
             if (isx) { if (a.zl.ptr) a.zl(cc, b) = val; }
+            else     { if (a.xl.ptr) a.xl(cc, b) = val; }
+        }
+    }
+    if (want_logits && a.rows_x_ptr) {
+        for (int c = tid; c < a.rows_x_m + a.rows_z_m; c += T) {
+            const bool isz = c >= a.rows_x_m;
+            const int cc = isz ? c - a.rows_x_m : c;
+            const int *ptr = isz ? a.rows_z_ptr : a.rows_x_ptr;
+            const idx_t *col = isz ? a.rows_z_col : a.rows_x_col;
+            const float *scr = isz ? pri + n : pri;
+            int par = 0;
+            float Tsum = 0.0f;
+            for (int k = ptr[cc]; k < ptr[cc + 1]; k++) {
+                const int v = col[k];
+                par ^= (dec[v] >> (isz ? 3 : 2)) & 1;
+                Tsum = FB_ADD(Tsum, scr[v]);
+            }
+            float val = MATH::phi4(Tsum);
+            val = par ? -val : val;
+            if (isz) { if (a.zl.ptr) a.zl(cc, b) = val; }
             else     { if (a.xl.ptr) a.xl(cc, b) = val; }
         }
     }

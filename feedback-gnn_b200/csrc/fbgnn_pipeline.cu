@@ -43,6 +43,7 @@ static int ws_reserve(fbgnn_ctx *ctx, int64_t B, int n, int m) {
     CK(cudaMalloc(&w.active[0], b));
     CK(cudaMalloc(&w.active[1], b));
     CK(cudaMalloc(&w.rounds, b));
+    CK(cudaMalloc(&w.iters, b));
     CK(cudaMalloc(&w.L, b * 3 * n * sizeof(float)));
     CK(cudaMalloc(&w.P, b * 3 * n * sizeof(float)));
     CK(cudaMalloc(&w.logit, b * std::max(m, 1) * sizeof(float)));
@@ -67,6 +68,7 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
     for (int s = 0; s < cfg->num_stages; s++) {
         REQUIRE(cfg->cn_type[s] >= 0 && cfg->cn_type[s] <= 2, "unknown cn_type in stage %d", s);
         REQUIRE(cfg->num_iter[s] >= 0, "negative num_iter in stage %d", s);
+        REQUIRE(!cfg->early_stop || cfg->num_iter[s] <= 255, "early stop needs num_iter <= 255 (stage %d)", s);
         REQUIRE(s == 0 || cfg->gnn[s - 1], "feedback GNN %d is NULL", s - 1);
     }
     fbgnn_ctx *ctx = code->ctx;
@@ -129,6 +131,7 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
             }
         }
         a.vbits = w.vbits;
+        a.iters_out = cfg->early_stop ? w.iters : nullptr;
         a.active_in = (s == 0) ? nullptr : w.active[(s - 1) & 1];
         a.active_out = w.active[s & 1];
         a.rounds = last ? nullptr : w.rounds;

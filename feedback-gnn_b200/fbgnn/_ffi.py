@@ -34,7 +34,12 @@ class PipelineCfg(C.Structure):
     _fields_ = [("num_stages", C.c_int32), ("num_iter", C.POINTER(C.c_int32)),
                 ("factor", C.POINTER(C.c_float)), ("cn_type", C.POINTER(C.c_int32)),
                 ("gnn", C.POINTER(C.c_void_p)), ("prior", C.c_float), ("thr", C.c_float * 3),
-                ("fixed_weight", C.c_int32), ("osd0", C.c_int32), ("skip_inactive", C.c_int32)]
+                ("fixed_weight", C.c_int32), ("osd0", C.c_int32), ("skip_inactive", C.c_int32),
+                ("early_stop", C.c_int32)]
+
+
+class Bp4Opts(C.Structure):
+    _fields_ = [("iters_out", C.c_void_p), ("rows_x", C.c_void_p), ("rows_z", C.c_void_p)]
 
 
 NULL2 = Tensor2(None, 0, 0)
@@ -80,6 +85,11 @@ _SIGNATURES = {
     "fbgnn_bp4_decode": [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int64, Tensor3, C.c_float,
                          Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2,
                          Tensor2, Tensor2, Tensor3],
+    "fbgnn_bp4_decode_ex": [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int64, Tensor3, C.c_float,
+                            Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2, Tensor2,
+                            Tensor2, Tensor2, Tensor3, C.POINTER(Bp4Opts)],
+    "fbgnn_rows_create": [C.c_void_p, C.c_int32, C.c_int32, _i32p, _i32p, _vpp],
+    "fbgnn_rows_destroy": [C.c_void_p],
     "fbgnn_bp2_decode": [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_int64, Tensor2, Tensor2, Tensor2,
                          Tensor2],
     "fbgnn_osd0_decode": [C.c_void_p, C.c_int64, Tensor2, Tensor2, Tensor2],
@@ -505,13 +515,30 @@ class Graph:
             pass
 
 
+class Rows:
+    """Device-side CSR rows of a binary matrix (fbgnn_rows): a row set for soft syndromes."""
+
+    def __init__(self, mat, ctx=None):
+        self.ctx = ctx or default_context()
+        self.m, self.n, indptr, indices = _csr(mat)
+        self.handle = C.c_void_p()
+        call("fbgnn_rows_create", self.ctx.handle, self.n, self.m, _ip(indptr), _ip(indices), C.byref(self.handle))
+
+    def __del__(self):
+        try:
+            if self.handle:
+                lib().fbgnn_rows_destroy(self.handle)
+        except Exception:
+            pass
+
+
 class Code:
     """Device-side CSS code (fbgnn_code): graphs of hx and hz plus bit-packed logicals."""
 
     def __init__(self, code, ctx=None):
         self.ctx = ctx or default_context()
-        mx, n, hxp, hxi = _csr(code.hx)
-        mz, n2, hzp, hzi = _csr(code.hz)
+        # css_code objects of fbgnn.codes_q carry their CSR; anything else with hx / hz matrices works too
+        (mx, n, hxp, hxi), (mz, n2, hzp, hzi) = _csr(code.hx), _csr(code.hz)
         assert n == n2
         lx = np.asarray(code.lx) if np.asarray(code.lx).size else np.zeros((0, n), int)
         lz = np.asarray(code.lz) if np.asarray(code.lz).size else np.zeros((0, n), int)

@@ -41,17 +41,20 @@ class QLDPCBPDecoder:
                  stage_one=False,
                  stage_two=False,
                  ctx=None,
+                 early_stop=False,
                  **kwargs):
         if cn_type not in CN_TYPES:
             raise ValueError('Unknown node type.')
-        if trainable and not (stage_one or stage_two):
-            # In the reference `trainable` creates no variables (every weight is commented out, decoding_q.py:
-            # 114-135, 240-242, 748-749); it only switches the per-iteration soft syndromes on (:743, :794), over the
-            # rows of hx_perp / hz_perp unless stage_one / stage_two select hz / hx (:35-37).  The notebook that
-            # uses it passes stage_two=True as well (Feedback_GNN.ipynb cell 8); that combination is supported, and
-            # with stage_one=True the flag has no effect at all (the stage_one return comes first, :792-793).
-            raise NotImplementedError("trainable=True without stage_one / stage_two (soft syndromes over the dense "
-                                      "hx_perp / hz_perp rows) is not provided; pass stage_two=True")
+        # In the reference `trainable` creates no variables (every weight is commented out, decoding_q.py:114-135,
+        # 240-242, 748-749); it only switches the per-iteration soft syndromes on (:743, :794).  Their rows are those of
+        # hx_perp / hz_perp -- dense kernel bases -- unless stage_one / stage_two select hz / hx (:32-37); with
+        # stage_one=True the flag has no effect at all (the stage_one return comes first, :792-793).
+        self._perp_rows = bool(trainable) and not (stage_one or stage_two)
+        if self._perp_rows and np.asarray(code.hx_perp).shape[0] != np.asarray(code.hz_perp).shape[0]:
+            raise ValueError("trainable mode stacks x and z soft syndromes: hx_perp and hz_perp need equal row counts")
+        # extension (not in the reference): leave a frame's iteration loop once its decision reproduces the
+        # syndrome; the call then also returns the iterations used per frame
+        self._early_stop = bool(early_stop)
         self._code = code
         self._cn_type = cn_type
         self._hard_out = hard_out
@@ -109,7 +112,7 @@ class QLDPCBPDecoder:
         sz = ctx.asarray(_to_u8(syndrome_z), np.uint8)
         if sx.shape != (mx, B) or sz.shape != (mz, B):
             raise ValueError(f"syndromes must have shapes [{mx},{B}] and [{mz},{B}]")
-        if self._stage_two and not self._stage_one:
+        if (self._stage_two or self._trainable) and not self._stage_one:
             # (llr_hat [2*num_iter+2, m, B], x_hat, z_hat): decoding_q.py:794-795
             out = self.decode_device(llr, sx, sz, want_logits=False, want_iter_logits=True)
             xh, zh, llr_hat = out[3], out[4], out[-1]
@@ -117,7 +120,8 @@ class QLDPCBPDecoder:
                 return llr_hat, xh, zh
             return llr_hat.numpy(), xh.numpy().astype(np.int64), zh.numpy().astype(np.float64)
         out = self.decode_device(llr, sx, sz, want_logits=self._stage_one)
-        Lx, Ly, Lz, xh, zh, xl, zl = out
+        Lx, Ly, Lz, xh, zh, xl, zl = out[:7]
+        self.last_iterations = out[-1].numpy() if self._early_stop else None
         if self._stage_one:
             if on_device:
                 return Lx, Ly, Lz, xh, zh, xl, zl
@@ -140,6 +144,10 @@ class QLDPCBPDecoder:
         Lx, Ly, Lz = (ctx.empty((B, n), np.float32) for _ in range(3))
         xh, zh = ctx.empty((B, n), np.uint8), ctx.empty((B, n), np.uint8)
         xl = zl = None
+        rows = None
+        if self._perp_rows:
+            rows = self._device_rows()
+            mz, mx = rows[0].m, rows[1].m                # x_logit over hx_perp rows, z_logit over hz_perp rows
         if want_logits:
             # frame-major storage, exposed in the reference's [m, B] orientation
             xl = ctx.empty((B, mz), np.float32).T
@@ -150,16 +158,27 @@ class QLDPCBPDecoder:
         il = ()
         if want_iter_logits:
             if mx != mz:
-                raise ValueError("per-iteration soft syndromes need hx and hz with the same number of rows")
+                raise ValueError("per-iteration soft syndromes need x and z row sets with the same number of rows")
             il = (ctx.empty((2 * self._num_iter + 2, B, mx), np.float32).transpose((0, 2, 1)),)
         t2 = lambda a: a.t2() if a is not None else _ffi.NULL2
-        _ffi.call("fbgnn_bp4_decode", dev.handle, CN_TYPES[self._cn_type], self._num_iter,
+        iters = (ctx.empty((B,), np.uint8),) if self._early_stop else ()
+        opts = _ffi.Bp4Opts(iters[0].ptr if iters else None, rows[0].handle if rows else None,
+                            rows[1].handle if rows else None)
+        import ctypes as C
+        _ffi.call("fbgnn_bp4_decode_ex", dev.handle, CN_TYPES[self._cn_type], self._num_iter,
                   self._normalization_factor, B,
                   llr.t3() if llr is not None else _ffi.NULL3, float(prior or 0.0),
                   sx.t2(), sz.t2(), Lx.t2(), Ly.t2(), Lz.t2(), xh.t2(), zh.t2(), t2(xl), t2(zl),
                   msgs[0].t2() if want_msgs else _ffi.NULL2, msgs[1].t2() if want_msgs else _ffi.NULL2,
-                  il[0].t3() if want_iter_logits else _ffi.NULL3)
-        return (Lx, Ly, Lz, xh, zh, xl, zl) + msgs + il
+                  il[0].t3() if want_iter_logits else _ffi.NULL3, C.byref(opts))
+        return (Lx, Ly, Lz, xh, zh, xl, zl) + msgs + il + iters
+
+    def _device_rows(self):
+        """(rows of hx_perp, rows of hz_perp) on the device, one copy per decoder."""
+        if getattr(self, "_rows", None) is None:
+            ctx = self._device().ctx
+            self._rows = (_ffi.Rows(self._code.hx_perp, ctx), _ffi.Rows(self._code.hz_perp, ctx))
+        return self._rows
 
 
 def _to_u8(s):

@@ -205,10 +205,13 @@ class Sandwich_BP_GNN_Evaluation_Model:
                       so shards of one Monte-Carlo run can be given disjoint id ranges
       skip_inactive   stop frames once their correction matches the syndrome (result-identical
                       to the reference, which masks the later updates: feedback_gnn.py:339-340)
+      early_stop      opt-in: every BP stage leaves a frame's iteration loop at the first iteration whose decision
+                      reproduces the syndrome.  NOT what the reference computes -- it always runs
+                      num_iter iterations -- so it is off by default and excluded from parity claims
     """
 
     def __init__(self, code, decoders, feedbacks, num_layers=4, wt=False, p0=0.05, seed=0, first_frame=0,
-                 skip_inactive=False, osd0=False, ctx=None):
+                 skip_inactive=False, osd0=False, ctx=None, early_stop=False):
         self.k, self.n = code.K, code.N
         self.code = code
         self.hx, self.hz, self.lx, self.lz = code.hx, code.hz, code.lx, code.lz
@@ -235,6 +238,7 @@ class Sandwich_BP_GNN_Evaluation_Model:
         self.next_frame = int(first_frame)
         self.skip_inactive = bool(skip_inactive)
         self.osd0 = bool(osd0)          # OSD-0 on the frames the last BP stage leaves mismatching (bp_osd.py)
+        self.early_stop = bool(early_stop)   # opt-in: BP stages stop per frame at the first syndrome match (not the reference)
         self._ctx = ctx
         self.last_counters = None
 
@@ -258,7 +262,7 @@ class Sandwich_BP_GNN_Evaluation_Model:
         thr = pauli_thresholds(0.0 if self.wt else float(p))
         cfg = _ffi.PipelineCfg(S, ni, fa, ct, gh, float(self.prior(p)), (C.c_float * 3)(*thr),
                                int(round(float(p))) if self.wt else 0, 1 if self.osd0 else 0,
-                               1 if self.skip_inactive else 0)
+                               1 if self.skip_inactive else 0, 1 if self.early_stop else 0)
         nx = nz = _ffi.NULL2
         keep = None
         if noise is not None:

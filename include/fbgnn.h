@@ -45,7 +45,7 @@
 extern "C" {
 #endif
 
-#define FBGNN_VERSION 100            /* 0.1.0 */
+#define FBGNN_VERSION 200            /* 0.2.0 */
 
 #define FBGNN_OK            0
 #define FBGNN_E_INVALID    -1        /* bad argument */
@@ -80,6 +80,7 @@ typedef struct fbgnn_graph fbgnn_graph;   /* Tanner graph of one parity-check ma
 typedef struct fbgnn_code  fbgnn_code;    /* CSS code: graphs of hx, hz + logicals lx,lz */
 typedef struct fbgnn_gnn   fbgnn_gnn;     /* one Feedback_GNN weight set                 */
 typedef struct fbgnn_gbp   fbgnn_gbp;     /* one GNN_BP4 weight set                      */
+typedef struct fbgnn_rows  fbgnn_rows;    /* sparse rows of a binary matrix (soft-syndrome row sets) */
 
 /* strided views (strides in ELEMENTS; ptr == NULL means "absent") */
 typedef struct { void *ptr; int64_t s0, s1; } fbgnn_tensor2;
@@ -177,6 +178,35 @@ int fbgnn_bp4_decode(fbgnn_code *code, int32_t cn_type, int32_t num_iter, float 
                      fbgnn_tensor2 x_logit, fbgnn_tensor2 z_logit,
                      fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z, fbgnn_tensor3 iter_logits);
 
+/* Rows of a binary matrix as CSR on the device (any density; at most 65535 columns): the row sets over which
+ * fbgnn_bp4_decode_ex forms soft syndromes. */
+int fbgnn_rows_create(fbgnn_ctx *ctx, int32_t n, int32_t m, const int32_t *indptr, const int32_t *indices,
+                      fbgnn_rows **rows);
+int fbgnn_rows_destroy(fbgnn_rows *rows);
+
+/* Options of fbgnn_bp4_decode_ex (zero-initialise; every field optional). */
+typedef struct {
+    /* OPT-IN early stop.  The reference always runs num_iter iterations (decoding_q.py:732).  With
+     * iters_out != NULL a frame leaves the loop as soon as the hard decision of its current messages reproduces the
+     * syndrome (checked after every iteration by a warp ballot over the checks); iters_out[b] (device uint8 [B],
+     * num_iter <= 255) receives the iterations executed, and the frame's outputs are exactly those of a decoder
+     * configured with num_iter = iters_out[b]. */
+    uint8_t *iters_out;
+    /* Row sets of the soft syndromes: x_logit over rows_x (from llr_x'), z_logit over rows_z (from llr_z').  NULL =
+     * the rows of hz / hx (the stage_one / stage_two choice, decoding_q.py:35-37); the reference's trainable mode
+     * without those flags uses the dense hx_perp / hz_perp (decoding_q.py:32-33, 93-94). */
+    fbgnn_rows *rows_x, *rows_z;
+} fbgnn_bp4_opts;
+
+/* fbgnn_bp4_decode with options; x_logit / z_logit / iter_logits are then indexed by the rows of opts->rows_x / rows_z. */
+int fbgnn_bp4_decode_ex(fbgnn_code *code, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                        fbgnn_tensor3 llr, float prior, fbgnn_tensor2 synd_x, fbgnn_tensor2 synd_z,
+                        fbgnn_tensor2 Lx, fbgnn_tensor2 Ly, fbgnn_tensor2 Lz,
+                        fbgnn_tensor2 x_hat, fbgnn_tensor2 z_hat,
+                        fbgnn_tensor2 x_logit, fbgnn_tensor2 z_logit,
+                        fbgnn_tensor2 msg_x, fbgnn_tensor2 msg_z, fbgnn_tensor3 iter_logits,
+                        const fbgnn_bp4_opts *opts);
+
 /* LDPCBPDecoder.call with is_syndrome.  llr: float32 logits (b,v); synd: uint8 (c,b) or
  * NULL ptr (no syndrome); soft: float32 (b,v) output logits; hard: uint8 (b,v) or NULL. */
 int fbgnn_bp2_decode(fbgnn_graph *graph, int32_t cn_type, int32_t num_iter, float factor,
@@ -259,6 +289,8 @@ typedef struct {
     int32_t skip_inactive;     /* 0: all frames run all rounds (reference-equivalent work)   */
                                /* 1: frames whose decision matches the syndrome stop early   */
                                /*    (result-identical; the reference masks the scatter)     */
+    int32_t early_stop;        /* 1: OPT-IN early stop inside every BP stage (see fbgnn_bp4_opts; NOT result-identical */
+                               /*    to the reference in general -- a converged frame keeps its first converged state)  */
 } fbgnn_pipeline_cfg;
 
 /* Sandwich_BP_GNN_Evaluation_Model.call on global frames [first_frame, first_frame+B).

@@ -58,7 +58,7 @@ class _PipeCfg(C.Structure):
                 ("cn_type", C.c_void_p), ("gnn", C.c_void_p), ("prior", C.c_float),
                 ("fixed_weight", C.c_int32), ("osd0", C.c_int32), ("basis_x", C.c_void_p),
                 ("pivot_x", C.c_void_p), ("basis_z", C.c_void_p), ("pivot_z", C.c_void_p),
-                ("skip_inactive", C.c_int32)]
+                ("early_stop", C.c_int32), ("skip_inactive", C.c_int32)]
 
 
 def lib():
@@ -221,7 +221,7 @@ def bsc(seed, first_frame, B, n, p):
 
 
 def bp4(g, llr, syndrome_x, syndrome_z, num_iter, factor=1.0, cn_type="boxplus-phi",
-        rows_x=None, rows_z=None, want_msgs=False, want_iter_logits=False):
+        rows_x=None, rows_z=None, want_msgs=False, want_iter_logits=False, early_stop=False):
     """llr [B,3,n] f32 (or a float: constant prior); syndromes [m,B] 0/1.
     rows_x / rows_z: matrices whose rows define x_logit / z_logit (default: hz / hx, the
     stage_one choice of decoding_q.py:35-37).  Returns a dict."""
@@ -245,11 +245,15 @@ def bp4(g, llr, syndrome_x, syndrome_z, num_iter, factor=1.0, cn_type="boxplus-p
     if want_iter_logits:                # stage_two / trainable output, decoding_q.py:730,743-746,779-781
         assert rx.m == rz.m
         out["llr_hat"] = np.empty((2 * num_iter + 2, rx.m, B), np.float32)
+    if early_stop:                      # opt-in: stop a frame once its decision reproduces the syndrome (not the reference)
+        assert num_iter <= 255
+        out["iters"] = np.empty(B, np.uint8)
     lib().orc_bp4(C.byref(g.X.c), C.byref(g.Z.c), C.byref(rx.c), C.byref(rz.c),
                   C.c_int(CN_TYPES[cn_type]), C.c_int(num_iter), C.c_float(factor), C.c_int64(B),
                   _p(llr_arr), C.c_float(prior), _p(sx), _p(sz), _p(out["Lx"]), _p(out["Ly"]),
                   _p(out["Lz"]), _p(out["x_hat"]), _p(out["z_hat"]), _p(out["x_logit"]),
-                  _p(out["z_logit"]), _p(out.get("msg_x")), _p(out.get("msg_z")), _p(out.get("llr_hat")))
+                  _p(out["z_logit"]), _p(out.get("msg_x")), _p(out.get("msg_z")), _p(out.get("llr_hat")),
+                  _p(out.get("iters")))
     return out
 
 
@@ -278,7 +282,7 @@ def gnn(g, G, h_vn, logit_hx, logit_hz, syndrome_x, syndrome_z):
 
 
 def pipeline(g, num_iters, gnns, p, p0=0.05, factors=None, cn_types=None, seed=0, first_frame=0,
-             B=1, noise=None, skip_inactive=False, want_diff=False, wt=0, osd0=False):
+             B=1, noise=None, skip_inactive=False, want_diff=False, wt=0, osd0=False, early_stop=False):
     """Sandwich model: decoders[i] has num_iters[i] iterations; gnns[i] is feedbacks[i].
     Returns dict(flags [B] u8, counters [4] i64, x_diff, z_diff)."""
     S = len(num_iters)
@@ -293,7 +297,7 @@ def pipeline(g, num_iters, gnns, p, p0=0.05, factors=None, cn_types=None, seed=0
     cfg = _PipeCfg(S, _p(ni), _p(fa), _p(ct), C.cast(garr, C.c_void_p),
                    C.c_float(prior_llr(p if p0 is None else p0)), int(wt), int(osd0),
                    C.cast(C.pointer(bx.c), C.c_void_p), _p(pvx), C.cast(C.pointer(bz.c), C.c_void_p), _p(pvz),
-                   int(skip_inactive))
+                   int(early_stop), int(skip_inactive))
     thr = pauli_thresholds(p)
     flags = np.empty(B, np.uint8)
     counters = np.zeros(4, np.int64)

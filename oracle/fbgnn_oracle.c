@@ -334,10 +334,11 @@ static void bp4_frame_il(const orc_side_t *X, const orc_side_t *Z, int cn_type, 
                          float factor, const float *llrx, const float *llry, const float *llrz,
                          const uint8_t *sx, const uint8_t *sz, float *mx, float *mz,
                          float *Lx, float *Ly, float *Lz, uint8_t *xh, uint8_t *zh, float *work,
-                         const orc_iterlog_t *il, float *xl, float *zl) {
+                         const orc_iterlog_t *il, float *xl, float *zl, int *iters_used) {
     const int n = X->n;
     memset(mx, 0, sizeof(float) * (size_t)X->E);
     memset(mz, 0, sizeof(float) * (size_t)Z->E);
+    if (iters_used) *iters_used = num_iter;
     for (int it = 0; it < num_iter; it++) {
         if (il) {              /* marginals the VN update of this iteration is about to compute */
             bp4_marginals(X, Z, mx, mz, llrx, llry, llrz, Lx, Ly, Lz);
@@ -364,6 +365,33 @@ static void bp4_frame_il(const orc_side_t *X, const orc_side_t *Z, int cn_type, 
         }
         cn_update(X, cn_type, 1, factor, sx, mx, work);
         cn_update(Z, cn_type, 1, factor, sz, mz, work);
+        if (iters_used) {
+            /* opt-in early stop (NOT what the reference does, which always runs num_iter iterations):
+             * leave the loop as soon as the hard decision of the current messages reproduces the syndrome.  The frame's
+             * outputs are then exactly those of a decoder configured with num_iter = *iters_used. */
+            bp4_marginals(X, Z, mx, mz, llrx, llry, llrz, Lx, Ly, Lz);
+            for (int v = 0; v < n; v++) {
+                int d = 0;
+                float best = 0.0f;
+                if (Lx[v] < best) { best = Lx[v]; d = 1; }
+                if (Lz[v] < best) { best = Lz[v]; d = 2; }
+                if (Ly[v] < best) { best = Ly[v]; d = 3; }
+                xh[v] = (uint8_t)(d & 1);
+                zh[v] = (uint8_t)(d >> 1);
+            }
+            int bad = 0;
+            for (int c = 0; c < X->m && !bad; c++) {
+                int par = sx[c];
+                for (int k = X->cn_ptr[c]; k < X->cn_ptr[c + 1]; k++) par ^= zh[X->cn_vn[k]];
+                bad |= par;
+            }
+            for (int c = 0; c < Z->m && !bad; c++) {
+                int par = sz[c];
+                for (int k = Z->cn_ptr[c]; k < Z->cn_ptr[c + 1]; k++) par ^= xh[Z->cn_vn[k]];
+                bad |= par;
+            }
+            if (!bad) { *iters_used = it + 1; num_iter = it + 1; break; }
+        }
     }
     bp4_marginals(X, Z, mx, mz, llrx, llry, llrz, Lx, Ly, Lz);
     if (il) iterlog_write(il, n, num_iter, Lx, Ly, Lz, xl, zl);
@@ -379,12 +407,15 @@ static void bp4_frame_il(const orc_side_t *X, const orc_side_t *Z, int cn_type, 
     }
 }
 
+static int g_pipeline_early_stop = 0;      /* set per orc_pipeline call (read-only inside the parallel region) */
+
 static void bp4_frame(const orc_side_t *X, const orc_side_t *Z, int cn_type, int num_iter,
                       float factor, const float *llrx, const float *llry, const float *llrz,
                       const uint8_t *sx, const uint8_t *sz, float *mx, float *mz,
                       float *Lx, float *Ly, float *Lz, uint8_t *xh, uint8_t *zh, float *work) {
+    int used;
     bp4_frame_il(X, Z, cn_type, num_iter, factor, llrx, llry, llrz, sx, sz, mx, mz, Lx, Ly, Lz, xh, zh,
-                 work, NULL, NULL, NULL);
+                 work, NULL, NULL, NULL, g_pipeline_early_stop ? &used : NULL);
 }
 
 /* Batched QLDPCBPDecoder.call with the reference's tensor layouts:
@@ -396,7 +427,8 @@ void orc_bp4(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *rows_x,
              const orc_rows_t *rows_z, int cn_type, int num_iter, float factor, int64_t B,
              const float *llr, float prior, const uint8_t *synd_x, const uint8_t *synd_z,
              float *Lx, float *Ly, float *Lz, uint8_t *x_hat, uint8_t *z_hat,
-             float *x_logit, float *z_logit, float *msg_x, float *msg_z, float *llr_hat) {
+             float *x_logit, float *z_logit, float *msg_x, float *msg_z, float *llr_hat, uint8_t *iters_out) {
+    /* iters_out != NULL: opt-in early stop, iters_out[b] = iterations executed for frame b */
     const int n = X->n, mxn = X->m, mzn = Z->m;
     int wd = max_cn_degree(X), wz = max_cn_degree(Z);
     if (wz > wd) wd = wz;
@@ -416,9 +448,11 @@ void orc_bp4(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *rows_x,
             for (int c = 0; c < mxn; c++) sx[c] = synd_x[(int64_t)c * B + b];
             for (int c = 0; c < mzn; c++) sz[c] = synd_z[(int64_t)c * B + b];
             orc_iterlog_t il = { rows_x, rows_z, llr_hat, B, b, rows_x ? rows_x->m : 0, wa };
+            int used = num_iter;
             bp4_frame_il(X, Z, cn_type, num_iter, factor, pri, pri + n, pri + 2 * n, sx, sz, mx, mz,
                          Lx + b * n, Ly + b * n, Lz + b * n, x_hat + b * n, z_hat + b * n, work,
-                         llr_hat ? &il : NULL, xl, zl);
+                         llr_hat ? &il : NULL, xl, zl, iters_out ? &used : NULL);
+            if (iters_out) iters_out[b] = (uint8_t)used;
             if (x_logit || z_logit) {
                 bp4_logits(n, x_logit ? rows_x : NULL, z_logit ? rows_z : NULL, Lx + b * n,
                            Ly + b * n, Lz + b * n, xl, zl, wa, wa + n);
@@ -695,6 +729,7 @@ typedef struct {
     const int32_t *pivot_x;      /* [rank_x] rows of hx forming the basis */
     const orc_rows_t *basis_z;
     const int32_t *pivot_z;
+    int32_t early_stop;          /* 1: opt-in early stop inside every BP stage (not the reference) */
     int32_t skip_inactive;       /* 0: every frame runs every round (reference behaviour);     */
                                  /* 1: stop a frame once its decision matches the syndrome     */
                                  /*    (result-identical, the scatter is masked: 339-340)      */
@@ -797,6 +832,7 @@ void orc_pipeline(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *lx
                   uint8_t *z_diff) {
     const int n = X->n;
     int64_t c_flag = 0, c_blk = 0, c_s1 = 0;
+    g_pipeline_early_stop = cfg->early_stop;
 #pragma omp parallel reduction(+ : c_flag, c_blk, c_s1)
     {
         float *fw = (float *)malloc(sizeof(float) * pipe_float_work(X, Z, cfg));

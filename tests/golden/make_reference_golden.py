@@ -124,6 +124,11 @@ def main():
                                     cn_type="boxplus-phi", trainable=False, stage_two=True)
             llr_hat, xh, zh = dec((tf.constant(llr), tf.constant(sx), tf.constant(sz)))
             bp["c882.stage_two.llr_hat"] = np.asarray(llr_hat)
+            # trainable=True without stage flags: the same output over the DENSE hx_perp / hz_perp rows (decoding_q.py:32-33)
+            dec = ns.QLDPCBPDecoder(code=code, num_iter=tf.constant(2), normalization_factor=tf.constant(1.0),
+                                    cn_type="boxplus-phi", trainable=True)
+            llr_hat, xh, zh = dec((tf.constant(llr[:4]), tf.constant(sx[:, :4]), tf.constant(sz[:, :4])))
+            bp["c882.trainable.llr_hat"] = np.asarray(llr_hat)
     np.savez_compressed(os.path.join(HERE, "ref_bp4.npz"), **bp)
 
     # ---------------------------------------------------------------- 2b. LDPCBPDecoder.call, is_syndrome (decoding.py:875-1048)

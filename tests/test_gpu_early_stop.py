@@ -1,0 +1,77 @@
+"""Opt-in early stop (north_star: "early-stop syndrome checks use a warp ballot", "early-stop iteration
+counts ... bit-exact").  The reference has NO early stopping (decoding_q.py:732 runs num_iter iterations for every
+frame), so this mode is off by default and outside every parity claim with the reference; what is tested is its own
+contract: a frame leaves the loop at the first iteration whose hard decision reproduces the syndrome, iters[b] says which,
+and the frame's outputs are bit for bit those of a decoder configured with num_iter = iters[b] -- and the CUDA path
+agrees with the oracle's implementation of the same rule, iteration counts included."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _synd(oracle, code, B, p, seed):
+    nx, nz = oracle.pauli(seed, 0, B, code.N, p)
+    return (((code.hx @ nz.T.astype(np.int64)) & 1).astype(np.uint8), ((code.hz @ nx.T.astype(np.int64)) & 1).astype(np.uint8))
+
+
+@pytest.mark.parametrize("name,p,arith", [("c882", 0.05, "exact"), ("c1270", 0.08, "exact"), ("rsurf3", 0.08, "exact"),
+                                          ("c882", 0.05, "sfu"), ("c1270", 0.08, "sfu")])
+def test_early_stop_layer(codes, c1270, oracle, name, p, arith):
+    import fbgnn as F
+    code = c1270 if name == "c1270" else codes[name]
+    B = 160
+    sx, sz = _synd(oracle, code, B, p, 3)
+    prior = oracle.prior_llr(0.05)
+    llr = np.full((B, 3, code.N), prior, np.float32)
+    ctx = F.default_context()
+    ctx.set_math(arith)
+    try:
+        with oracle.math(arith):
+            dec = F.QLDPCBPDecoder(code, num_iter=64, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True,
+                                   early_stop=True)
+            out = dec((llr, sx, sz))
+            iters = dec.last_iterations
+            ref = oracle.bp4(oracle.CodeGraph(code), llr, sx, sz, 64, 1.0, "boxplus-phi", early_stop=True)
+            assert np.array_equal(iters, ref["iters"])                       # integer output: bit-exact
+            for k, o in zip(("Lx", "Ly", "Lz", "x_hat", "z_hat", "x_logit", "z_logit"), out):
+                a, b = np.asarray(o, dtype=ref[k].dtype), ref[k]
+                assert np.array_equal(a.view(np.uint32) if a.dtype == np.float32 else a,
+                                      b.view(np.uint32) if b.dtype == np.float32 else b), k
+            # contract: frame b == plain decoder with num_iter = iters[b]
+            assert iters.min() >= 1 and iters.max() <= 64 and np.median(iters) < 20
+            for k_it in np.unique(iters)[:4]:
+                sel = iters == k_it
+                plain = F.QLDPCBPDecoder(code, num_iter=int(k_it), normalization_factor=1.0, cn_type="boxplus-phi",
+                                         stage_one=True)((llr[sel], sx[:, sel], sz[:, sel]))
+                assert np.array_equal(plain[0].view(np.uint32), out[0][sel].view(np.uint32))
+                assert np.array_equal(plain[3], out[3][sel]) and np.array_equal(plain[5].view(np.uint32), out[5][:, sel].view(np.uint32))
+            # every frame that stopped early reproduces its syndrome
+            early = iters < 64
+            zs = (code.hx @ out[4][early].T.astype(np.int64)) & 1
+            assert np.array_equal(zs, sx[:, early])
+    finally:
+        ctx.set_math("exact")
+
+
+def test_early_stop_pipeline_matches_oracle_and_is_much_cheaper(codes, oracle, weights):
+    import fbgnn as F
+    code = codes["c882"]
+    G = F.Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, use_bias=True)
+    G.set_weights(weights["c882"])
+    d1 = F.QLDPCBPDecoder(code, num_iter=64, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+    d2 = F.QLDPCBPDecoder(code, num_iter=16, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+    B, p = 256, 0.1
+    model = F.Sandwich_BP_GNN_Evaluation_Model(code, [d1, d2, d2], [G, G], num_layers=3, seed=4, early_stop=True)
+    ctx = F.default_context()
+    ctx.stats(reset=True)
+    res = model.run(B, p, want_counters=True)
+    frames, iters = ctx.stats(reset=True)
+    ref = oracle.pipeline(oracle.CodeGraph(code), [64, 16, 16], [oracle.Gnn(weights["c882"])] * 2, p, seed=4, B=B,
+                          early_stop=True, want_diff=True)
+    assert np.array_equal(res["flags"].numpy(), ref["flags"]) and res["counters"].tolist() == ref["counters"].tolist()
+    assert np.array_equal(res["x_diff"].numpy(), ref["x_diff"])
+    assert frames == 3 * B and iters < 0.5 * B * (64 + 32)          # most frames stop long before the last iteration
+    # same logical error count as the fixed-iteration pipeline, up to frames whose first converged state differs
+    full = F.Sandwich_BP_GNN_Evaluation_Model(code, [d1, d2, d2], [G, G], num_layers=3, seed=4).run(B, p, want_counters=True)
+    assert abs(int(full["counters"][2]) - int(res["counters"][2])) <= 4

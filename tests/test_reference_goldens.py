@@ -151,6 +151,38 @@ def test_oracle_bp2_matches_the_reference_code(ref, allcodes, oracle, arith):
             _check_bp2(Z, key, soft, hard, f"oracle[{arith}]")
 
 
+def _logit_tol(r, g):
+    a = np.maximum(np.abs(r), np.abs(g))
+    return 6 * (2e-5 * a + 1e-5 + np.minimum(4e-6 * np.exp(np.minimum(a, 20.0)), 4 * LN2))
+
+
+def test_oracle_trainable_mode_matches_the_reference_code(ref, allcodes, oracle):
+    """trainable=True without stage_one / stage_two: llr_hat over the dense hx_perp / hz_perp rows (decoding_q.py:32-37)."""
+    Z = ref["bp4"]
+    code = allcodes["c882"]
+    r = Z["c882.trainable.llr_hat"]
+    got = oracle.bp4(oracle.CodeGraph(code), Z["c882.llr"][:4], Z["c882.sx"][:, :4], Z["c882.sz"][:, :4], 2, 1.0,
+                     "boxplus-phi", rows_x=code.hx_perp, rows_z=code.hz_perp, want_iter_logits=True)["llr_hat"]
+    assert got.shape == r.shape == (6, code.hx_perp.shape[0], 4)
+    assert np.all(np.abs(got - r) <= _logit_tol(r, got))
+
+
+@pytest.mark.gpu
+def test_cuda_trainable_mode_matches_oracle_and_reference(ref, allcodes, oracle):
+    import fbgnn as F
+    Z = ref["bp4"]
+    code = allcodes["c882"]
+    llr, sx, sz = Z["c882.llr"][:4], Z["c882.sx"][:, :4], Z["c882.sz"][:, :4]
+    dec = F.QLDPCBPDecoder(code, num_iter=2, normalization_factor=1.0, cn_type="boxplus-phi", trainable=True)
+    llr_hat, xh, zh = dec((llr, sx, sz))
+    want = oracle.bp4(oracle.CodeGraph(code), llr, sx, sz, 2, 1.0, "boxplus-phi", rows_x=code.hx_perp, rows_z=code.hz_perp,
+                      want_iter_logits=True)
+    assert np.array_equal(llr_hat.view(np.uint32), want["llr_hat"].view(np.uint32))          # bit-exact vs the oracle
+    assert np.array_equal(xh.astype(np.uint8), want["x_hat"]) and np.array_equal(zh.astype(np.uint8), want["z_hat"])
+    r = Z["c882.trainable.llr_hat"]
+    assert np.all(np.abs(llr_hat - r) <= _logit_tol(r, llr_hat))                             # float32 noise vs the reference's code
+
+
 @pytest.mark.parametrize("arith", ["exact", "sfu"])
 def test_oracle_gnn_matches_the_reference_code(ref, allcodes, oracle, weights, arith):
     Z = ref["gnn"]
