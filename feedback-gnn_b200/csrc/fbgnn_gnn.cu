@@ -46,6 +46,34 @@ extern "C" int fbgnn_gnn_create(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t ac
     return 0;
 }
 
+extern "C" int fbgnn_gnn_create_deep(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t num_mlp_layers, int32_t activation,
+                                     int32_t reduce_op, int32_t use_bias, const float *packed, int64_t count,
+                                     fbgnn_gnn **out) {
+    REQUIRE(ctx && out && packed, "NULL argument");
+    REQUIRE(H >= 1 && H <= GNND_MAX && M >= 1 && M <= GNND_MAX, "hidden / message dims must be in [1, %d]", GNND_MAX);
+    REQUIRE(num_mlp_layers >= 1 && num_mlp_layers <= 8, "num_mlp_layers must be in [1, 8]");
+    REQUIRE(activation >= 0 && activation <= 2 && reduce_op >= 0 && reduce_op <= 3, "bad activation / reduce_op");
+    const int L = num_mlp_layers;
+    int64_t want = (int64_t)(L == 1 ? 2 * M + 3 : H) * 3 + 3;
+    {
+        int kin = 4;
+        int64_t side = 0;
+        for (int l = 0; l < L; l++) { const int kout = (l == L - 1) ? M : H; side += (int64_t)kin * kout + kout; kin = kout; }
+        want += 2 * side;
+        kin = 2 * M + 3;
+        for (int l = 0; l < L - 1; l++) { want += (int64_t)kin * H + H; kin = H; }
+    }
+    REQUIRE(count == want, "packed weights hold %lld floats, the layer sequence needs %lld", (long long)count, (long long)want);
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    fbgnn_gnn *g = new fbgnn_gnn();
+    g->ctx = ctx; g->H = H; g->M = M; g->act = activation; g->reduce = reduce_op; g->use_bias = use_bias ? 1 : 0;
+    g->layers = L; g->total = (int)count;
+    CK(cudaMalloc(&g->weights, (size_t)count * sizeof(float)));
+    CK(cudaMemcpy(g->weights, packed, (size_t)count * sizeof(float), cudaMemcpyHostToDevice));
+    *out = g;
+    return 0;
+}
+
 extern "C" int fbgnn_gnn_destroy(fbgnn_gnn *g) {
     if (!g) return 0;
     cudaSetDevice(g->ctx->device);
@@ -77,6 +105,16 @@ static int launch_gnn_m(fbgnn_ctx *ctx, const GnnArgs &a) {
 int launch_gnn(fbgnn_ctx *ctx, const fbgnn_gnn *g, GnnArgs &a) {
     if (a.num_frames <= 0) return 0;
     a.weights = g->weights; a.act = g->act; a.reduce = g->reduce; a.use_bias = g->use_bias;
+    if (g->layers != 2) {                      // general depth: k_gnn_deep
+        GnnDeepArgs d{a, g->H, g->M, g->layers};
+        const int64_t items = a.num_frames * a.X.n;
+        const unsigned blocks = (unsigned)std::min<int64_t>((items + 127) / 128, (int64_t)ctx->num_sms * 16);
+        if (ctx->math_mode == FBGNN_MATH_SFU) k_gnn_deep<MathSfu><<<blocks, 128, 0, ctx->stream>>>(d);
+        else k_gnn_deep<MathExact><<<blocks, 128, 0, ctx->stream>>>(d);
+        CK(cudaGetLastError());
+        ctx->launches++;
+        return 0;
+    }
     const bool reg3 = a.X.reg_dv == 3 && a.Z.reg_dv == 3;      // the (3,6)-regular GHP / bivariate codes
     const bool tb = g->act == FBGNN_ACT_TANH && g->use_bias;   // the shipped configuration
     const bool fact = g->reduce <= 1;                          // mean / sum: output layer after the reduction

@@ -94,8 +94,9 @@ struct fbgnn_rows {
 struct fbgnn_gnn {
     fbgnn_ctx *ctx;
     int H, M, act, reduce, use_bias;
-    float *weights = nullptr;      // packed GnnLayout<H,M>
+    float *weights = nullptr;      // packed GnnLayout<H,M> (layers == 2) or the layer sequence of k_gnn_deep
     int total = 0;
+    int layers = 2;                // num_mlp_layers
 };
 
 

@@ -1047,6 +1047,96 @@ static __global__ void __launch_bounds__(128, FBGNN_GNN_MINBLOCKS) k_gnn(const G
     gnn_body<H, M, DV, TANH_BIAS, FACT, MATH, WSmem>(a, WSmem{wsm});
 }
 
+// ---- feedback GNN with MLPs of any depth (num_mlp_layers != 2; feedback_gnn.py:110-127) ----------------------------
+// General form: every edge's MLP evaluated in full, messages reduced in edge order; arithmetic and packed weight layout
+// are those of oracle/fbgnn_oracle.c (gnnd_vn).  One thread per (frame, variable node); the layer vectors live in local
+// memory and the weights are read through the read-only cache -- this is the path for configurations outside the shipped
+// one, not a tuned kernel.
+constexpr int GNND_MAX = 128;
+
+struct GnnDeepArgs {
+    GnnArgs g;                          // graph tables, views, frame list (weights / act / reduce / use_bias of g are used)
+    int H, M, L;
+};
+
+template <typename MATH>
+__device__ __forceinline__ const float *gnnd_dense(const float *__restrict__ w, int kin, int kout, bool use_bias, int act,
+                                                   const float *in, float *out) {
+    for (int j = 0; j < kout; j++) {
+        float a = 0.0f;
+        for (int k = 0; k < kin; k++) a = FB_FMA(in[k], __ldg(w + k * kout + j), a);
+        if (use_bias) a = FB_ADD(a, __ldg(w + kin * kout + j));
+        out[j] = gnn_act<MATH>(act, a);
+    }
+    return w + kin * kout + kout;
+}
+
+template <typename MATH>
+static __global__ void __launch_bounds__(128) k_gnn_deep(const GnnDeepArgs d) {
+    const GnnArgs &a = d.g;
+    const int n = a.X.n, H = d.H, M = d.M, L = d.L;
+    const bool use_bias = a.use_bias != 0;
+    const int64_t items = a.num_frames * n;
+    for (int64_t it = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; it < items; it += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t fi = it / n;
+        const int v = (int)(it - fi * n);
+        const int64_t b = a.frame_list ? a.frame_list[fi] : fi;
+        const float f3[3] = {a.h_vn(b, v, 0), a.h_vn(b, v, 1), a.h_vn(b, v, 2)};
+        float in[2 * GNND_MAX + 3], va[GNND_MAX], vc[GNND_MAX];
+        const float *w_inv = a.weights;
+        const float *w = w_inv + ((L == 1 ? 2 * M + 3 : H) * 3 + 3);
+        for (int side = 0; side < 2; side++) {
+            const SideDev &S = side ? a.Z : a.X;
+            const View2<const float> &logit = side ? a.logit_hz : a.logit_hx;
+            const View2<const uint8_t> &synd = side ? a.sz : a.sx;
+            float *red = in + side * M;
+            const int e0 = S.vn_ptr[v], e1 = S.vn_ptr[v + 1];
+            const float *wend = w;
+            for (int i = 0; i < M; i++) red[i] = 0.0f;
+            for (int e = e0; e < e1; e++) {
+                const int c = S.vn_cn[e];
+                va[0] = FB_MUL(logit(c, b), synd(c, b) ? -1.0f : 1.0f);
+                va[1] = f3[0]; va[2] = f3[1]; va[3] = f3[2];
+                const float *wl = w;
+                int kin = 4;
+                float *src = va, *dst = vc;
+                for (int l = 0; l < L; l++) {
+                    const int kout = (l == L - 1) ? M : H;
+                    wl = gnnd_dense<MATH>(wl, kin, kout, use_bias, (l == L - 1) ? 2 : a.act, src, dst);
+                    float *t = src; src = dst; dst = t;
+                    kin = kout;
+                }
+                wend = wl;
+                for (int i = 0; i < M; i++) {
+                    if (e == e0) red[i] = src[i];
+                    else if (a.reduce <= 1) red[i] = FB_ADD(red[i], src[i]);
+                    else if (a.reduce == 2) red[i] = (src[i] > red[i]) ? src[i] : red[i];
+                    else red[i] = (src[i] < red[i]) ? src[i] : red[i];
+                }
+            }
+            if (e1 == e0) {
+                int kin = 4;
+                for (int l = 0; l < L; l++) { const int kout = (l == L - 1) ? M : H; wend += kin * kout + kout; kin = kout; }
+            } else if (a.reduce == 0) {
+                const float deg = (float)(e1 - e0);
+                for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], deg);
+            }
+            w = wend;
+        }
+        in[2 * M] = f3[0]; in[2 * M + 1] = f3[1]; in[2 * M + 2] = f3[2];
+        float *src = in, *dst = va;
+        int kin = 2 * M + 3;
+        for (int l = 0; l < L - 1; l++) {
+            w = gnnd_dense<MATH>(w, kin, H, use_bias, a.act, src, dst);
+            src = dst; dst = (dst == va) ? vc : va;
+            kin = H;
+        }
+        float o[3];
+        gnnd_dense<MATH>(w_inv, kin, 3, use_bias, 2, src, o);
+        a.out(b, v, 0) = o[0]; a.out(b, v, 1) = o[1]; a.out(b, v, 2) = o[2];
+    }
+}
+
 // ------------------------------------------------------------------ GNN_BP4 -----------
 // The full GNN message-passing decoder of gnn.py:71-751 (BASELINE configs[4]); arithmetic and
 // summation orders are those of oracle/fbgnn_oracle.c (gbp_*).  Embeddings live in HBM

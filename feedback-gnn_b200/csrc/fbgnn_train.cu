@@ -22,7 +22,7 @@ extern "C" int fbgnn_second_stage_grad(fbgnn_code *code, fbgnn_gnn *gnn, int32_t
     REQUIRE(h_vn.ptr && logit_hx.ptr && logit_hz.ptr && synd_x.ptr && synd_z.ptr, "NULL tensor");
     REQUIRE(B > 0 && num_iter >= 1 && loss_from >= 0 && loss_from <= num_iter, "bad B / num_iter / loss_from");
     REQUIRE(!want_grad || grads, "grads buffer missing");
-    if (!(gnn->H == 40 && gnn->M == 20 && gnn->act == FBGNN_ACT_TANH && gnn->use_bias && gnn->reduce <= 1))
+    if (!(gnn->layers == 2 && gnn->H == 40 && gnn->M == 20 && gnn->act == FBGNN_ACT_TANH && gnn->use_bias && gnn->reduce <= 1))
         return fail(FBGNN_E_UNSUPPORTED, "gradients are provided for the 40 / 20 tanh GNN with bias and reduce mean / sum");
     fbgnn_ctx *ctx = code->ctx;
     if (set_device(ctx)) return FBGNN_E_CUDA;

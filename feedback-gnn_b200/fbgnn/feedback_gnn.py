@@ -50,9 +50,10 @@ class Feedback_GNN:
         self._num_msg_dims = int(num_msg_dims)
         self._num_hidden_units = int(num_hidden_units)
         self._num_mlp_layers = int(num_mlp_layers)
-        if self._num_mlp_layers != 2:
-            raise NotImplementedError("this build provides the 2-layer MLPs of the shipped weights "
-                                      "(num_mlp_layers=2)")
+        if not 1 <= self._num_mlp_layers <= 8:
+            raise ValueError("num_mlp_layers must be in [1, 8]")
+        if self._num_mlp_layers != 2 and max(self._num_hidden_units, self._num_msg_dims) > 128:
+            raise ValueError("hidden / message dims above 128 are supported for 2-layer MLPs only")
         if reduce_op not in REDUCE:
             raise ValueError("unknown reduce operation")
         if activation not in ACTS:
@@ -72,13 +73,22 @@ class Feedback_GNN:
         if self._is_built:
             return
         self._is_built = True
-        H, M = self._num_hidden_units, self._num_msg_dims
+        H, M, L = self._num_hidden_units, self._num_msg_dims, self._num_mlp_layers
         rng = np.random.default_rng(0)
         ones = lambda k: np.ones(k, np.float32)
-        w = [np.zeros((H, 3), np.float32), ones(3)]
+
+        def mlp(k_in, units):                 # gnn.py:46-58: Dense layers, Glorot-uniform kernels, biases of ones
+            out = []
+            for k_out in units:
+                out += [_glorot_uniform(rng, k_in, k_out), ones(k_out)]
+                k_in = k_out
+            return out
+        # _llr_inv_embed acts on the embedding MLP's output -- for L = 1 that MLP is empty and it sees the concatenated
+        # input itself; edge MLPs: L-1 hidden layers + a linear output of M; embedding MLP: L-1 hidden layers
+        w = [np.zeros((H if L > 1 else 2 * M + 3, 3), np.float32), ones(3)]
         for _ in range(2):
-            w += [_glorot_uniform(rng, 4, H), ones(H), _glorot_uniform(rng, H, M), ones(M)]
-        w += [_glorot_uniform(rng, 2 * M + 3, H), ones(H)]
+            w += mlp(4, [H] * (L - 1) + [M])
+        w += mlp(2 * M + 3, [H] * (L - 1))
         if not self._use_bias:
             w = w[0::2]
         self._weights = w
@@ -120,6 +130,20 @@ class Feedback_GNN:
         self.build()
         ctx = ctx or self._ctx or _ffi.default_context()
         ent = self._handles.get(id(ctx))          # one device copy of the weights per context (GPU)
+        if (ent is None or ent[0] is not ctx) and self._num_mlp_layers != 2:
+            import ctypes as C
+            packed = []
+            step = 2 if self._use_bias else 1
+            for i in range(0, len(self._weights), step):
+                W = self._weights[i]
+                packed += [W.reshape(-1), self._weights[i + 1] if self._use_bias else np.zeros(W.shape[1], np.float32)]
+            packed = np.ascontiguousarray(np.concatenate(packed), np.float32)
+            h = C.c_void_p()
+            _ffi.call("fbgnn_gnn_create_deep", ctx.handle, self._num_hidden_units, self._num_msg_dims,
+                      self._num_mlp_layers, ACTS[self._activation], REDUCE[self._reduce_op], int(self._use_bias),
+                      packed.ctypes.data_as(C.POINTER(C.c_float)), packed.size, C.byref(h))
+            self._handles[id(ctx)] = (ctx, h)
+            ent = self._handles[id(ctx)]
         if ent is None or ent[0] is not ctx:
             import ctypes as C
             if self._use_bias:

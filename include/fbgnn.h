@@ -223,12 +223,18 @@ int fbgnn_osd0_decode(fbgnn_graph *basis, int64_t B, fbgnn_tensor2 llr, fbgnn_te
 /* ---- feedback GNN --------------------------------------------------------------------- */
 /* Weights in Keras get_weights() order, host float32 pointers (copied); bias pointers may
  * be NULL when use_bias is False.  Shapes: W0[H,3] b0[3] W1x[4,H] b1x[H] W2x[H,M] b2x[M]
- * W1z[4,H] b1z[H] W2z[H,M] b2z[M] W3[2M+3,H] b3[H].  This build supports 2-layer MLPs. */
+ * W1z[4,H] b1z[H] W2z[H,M] b2z[M] W3[2M+3,H] b3[H]: the 2-layer MLPs of the shipped weights (tuned kernel). */
 int fbgnn_gnn_create(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t activation, int32_t reduce_op,
                      const float *W0, const float *b0, const float *W1x, const float *b1x,
                      const float *W2x, const float *b2x, const float *W1z, const float *b1z,
                      const float *W2z, const float *b2z, const float *W3, const float *b3,
                      fbgnn_gnn **gnn);
+/* Feedback_GNN with num_mlp_layers != 2 (feedback_gnn.py:110-127), any hidden / message dims up to 128.  `packed`:
+ * the dense layers one after the other, each [K_in x K_out] row-major followed by K_out biases (zeros without bias):
+ * _llr_inv_embed ((L == 1 ? 2M+3 : H) -> 3), vn_msg_mlp_x (4 -> H ... -> M, L layers), vn_msg_mlp_z, vn_embed_mlp
+ * (2M+3 -> H ... -> H, L-1 layers) -- the Keras get_weights() order.  Runs through fbgnn_gnn_forward / the pipelines. */
+int fbgnn_gnn_create_deep(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t num_mlp_layers, int32_t activation,
+                          int32_t reduce_op, int32_t use_bias, const float *packed, int64_t count, fbgnn_gnn **gnn);
 int fbgnn_gnn_destroy(fbgnn_gnn *gnn);
 /* Feedback_GNN.call.  h_vn float32 (b, v, k); logit_hx (row of hx, b), logit_hz (row of hz, b);
  * synd_x/z uint8 (c, b); out float32 (b, v, k). */

@@ -172,6 +172,44 @@ class Gnn:
         self.c = _Gnn(H, M, ACTS[activation], REDUCE[reduce_op], *[_p(a) for a in self.keep])
 
 
+class _GnnD(C.Structure):
+    _fields_ = [("H", C.c_int32), ("M", C.c_int32), ("L", C.c_int32), ("act", C.c_int32), ("reduce", C.c_int32),
+                ("use_bias", C.c_int32), ("w", C.c_void_p)]
+
+
+def pack_deep_gnn(weights, H, M, L, use_bias=True):
+    """Keras get_weights() order of Feedback_GNN with L-layer MLPs -> the packed layer sequence of orc_gnn_deep /
+    fbgnn_gnn_create_deep: [W row-major, bias (zeros if absent)] for _llr_inv_embed, msg_x (L), msg_z (L), embed (L-1)."""
+    ws = [np.asarray(w, np.float32) for w in weights]
+    step = 2 if use_bias else 1
+    n_layers = 1 + 2 * L + (L - 1)
+    assert len(ws) == n_layers * step, (len(ws), n_layers, step)
+    out = []
+    for i in range(n_layers):
+        W = ws[i * step]
+        out.append(W.reshape(-1))
+        out.append(ws[i * step + 1].reshape(-1) if use_bias else np.zeros(W.shape[1], np.float32))
+    return np.ascontiguousarray(np.concatenate(out), np.float32)
+
+
+class GnnDeep:
+    def __init__(self, weights, H, M, L, activation="tanh", reduce_op="mean", use_bias=True):
+        assert max(H, M) <= 128
+        self.w = pack_deep_gnn(weights, H, M, L, use_bias)
+        self.c = _GnnD(H, M, L, ACTS[activation], REDUCE[reduce_op], int(use_bias), _p(self.w))
+
+
+def gnn_deep(g, G, h_vn, logit_hx, logit_hz, syndrome_x, syndrome_z):
+    h_vn = _f32(h_vn)
+    B = h_vn.shape[0]
+    lhx, lhz = _f32(logit_hx), _f32(logit_hz)
+    sx, sz = _u8(syndrome_x), _u8(syndrome_z)
+    out = np.empty((B, g.n, 3), np.float32)
+    lib().orc_gnn_deep(C.byref(g.X.c), C.byref(g.Z.c), C.byref(G.c), C.c_int64(B), _p(h_vn), _p(lhx), _p(lhz), _p(sx),
+                       _p(sz), _p(out))
+    return out
+
+
 def pauli_thresholds(p):
     """float32 thresholds of Pauli.call as called by the model (feedback_gnn.py:298, pauli.py:100-107)."""
     px, py, pz = np.float32(2 * p / 3), np.float32(p / 3), np.float32(2 * p / 3)

@@ -648,6 +648,100 @@ void orc_gnn(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t *G, int64
     }
 }
 
+
+/* ---------------------------------------------------------------- feedback GNN, any MLP depth ------- */
+/* Feedback_GNN with num_mlp_layers = L != 2 (feedback_gnn.py:110-127: the edge MLPs have L-1 hidden layers of H units
+ * and a linear output of M, the embedding MLP has L-1 hidden layers, _llr_inv_embed maps its output -- or, for L = 1,
+ * the concatenated input itself -- to 3).  The two-layer case keeps its own (factored) arithmetic above; this general
+ * form evaluates every edge's MLP in full and reduces the messages in edge order.
+ * Packed weights: dense layers one after the other, each [K_in x K_out] row-major followed by K_out biases (zeros when
+ * use_bias is off): _llr_inv_embed, vn_msg_mlp_x (L layers), vn_msg_mlp_z (L layers), vn_embed_mlp (L-1 layers). */
+typedef struct {
+    int32_t H, M, L, act, reduce, use_bias;
+    const float *w;
+} orc_gnnd_t;
+
+#define GNND_MAX 128
+static const float *gnnd_dense(const float *w, int kin, int kout, int use_bias, int act, const float *in, float *out) {
+    for (int j = 0; j < kout; j++) {
+        float a = 0.0f;
+        for (int k = 0; k < kin; k++) a = FB_FMA(in[k], w[k * kout + j], a);
+        if (use_bias) a = FB_ADD(a, w[kin * kout + j]);
+        out[j] = gnn_act(act, a);
+    }
+    return w + kin * kout + kout;
+}
+
+static void gnnd_vn(const orc_side_t *X, const orc_side_t *Z, const orc_gnnd_t *G, const float *hcx, const float *hcz,
+                    int v, const float f3[3], float out[3]) {
+    const int H = G->H, M = G->M, L = G->L;
+    float in[2 * GNND_MAX + 3], a[GNND_MAX], c[GNND_MAX];
+    const float *w_inv = G->w;
+    const float *w = w_inv + ((L == 1 ? 2 * M + 3 : H) * 3 + 3);
+    for (int side = 0; side < 2; side++) {
+        const orc_side_t *S = side ? Z : X;
+        const float *hc = side ? hcz : hcx;
+        float *red = in + side * M;
+        const int e0 = S->vn_ptr[v], e1 = S->vn_ptr[v + 1];
+        const float *wend = w;
+        for (int i = 0; i < M; i++) red[i] = 0.0f;
+        for (int e = e0; e < e1; e++) {
+            a[0] = hc[S->vn_cn[e]]; a[1] = f3[0]; a[2] = f3[1]; a[3] = f3[2];
+            const float *wl = w;
+            int kin = 4;
+            float *src = a, *dst = c;
+            for (int l = 0; l < L; l++) {
+                const int kout = (l == L - 1) ? M : H;
+                wl = gnnd_dense(wl, kin, kout, G->use_bias, (l == L - 1) ? 2 : G->act, src, dst);
+                float *t = src; src = dst; dst = t;
+                kin = kout;
+            }
+            wend = wl;
+            for (int i = 0; i < M; i++) {
+                if (e == e0) red[i] = src[i];
+                else if (G->reduce <= 1) red[i] = FB_ADD(red[i], src[i]);
+                else if (G->reduce == 2) red[i] = (src[i] > red[i]) ? src[i] : red[i];
+                else red[i] = (src[i] < red[i]) ? src[i] : red[i];
+            }
+        }
+        if (e1 == e0) {                  /* skip over this side's layers */
+            int kin = 4;
+            for (int l = 0; l < L; l++) { const int kout = (l == L - 1) ? M : H; wend += kin * kout + kout; kin = kout; }
+        } else if (G->reduce == 0) {
+            const float deg = (float)(e1 - e0);
+            for (int i = 0; i < M; i++) red[i] = FB_DIV(red[i], deg);
+        }
+        w = wend;
+    }
+    in[2 * M] = f3[0]; in[2 * M + 1] = f3[1]; in[2 * M + 2] = f3[2];
+    float *src = in, *dst = a;
+    int kin = 2 * M + 3;
+    for (int l = 0; l < L - 1; l++) {
+        w = gnnd_dense(w, kin, H, G->use_bias, G->act, src, dst);
+        src = dst; dst = (dst == a) ? c : a;
+        kin = H;
+    }
+    gnnd_dense(w_inv, kin, 3, G->use_bias, 2, src, out);
+}
+
+void orc_gnn_deep(const orc_side_t *X, const orc_side_t *Z, const orc_gnnd_t *G, int64_t B,
+                  const float *h_vn, const float *logit_hx, const float *logit_hz,
+                  const uint8_t *synd_x, const uint8_t *synd_z, float *out) {
+    const int n = X->n;
+#pragma omp parallel
+    {
+        float *hc = (float *)malloc(sizeof(float) * (size_t)(X->m + Z->m + 2));
+#pragma omp for schedule(dynamic, 4)
+        for (int64_t b = 0; b < B; b++) {
+            for (int c = 0; c < X->m; c++) hc[c] = FB_MUL(logit_hx[(int64_t)c * B + b], synd_x[(int64_t)c * B + b] ? -1.0f : 1.0f);
+            for (int c = 0; c < Z->m; c++) hc[X->m + c] = FB_MUL(logit_hz[(int64_t)c * B + b], synd_z[(int64_t)c * B + b] ? -1.0f : 1.0f);
+            for (int v = 0; v < n; v++)
+                gnnd_vn(X, Z, G, hc, hc + X->m, v, h_vn + (b * n + v) * 3, out + (b * n + v) * 3);
+        }
+        free(hc);
+    }
+}
+
 /* ---------------------------------------------------------------- OSD-0 ------------ */
 /* OSD0_Decoder.call + find_mrb (bp_osd.py:8-77).  `rows`: the full-rank basis of the pcm (rank rows),
  * llr [n] reliabilities (small = likely in error), s [rank] reduced syndrome.  Columns are visited

@@ -71,7 +71,7 @@ def test_early_stop_pipeline_matches_oracle_and_is_much_cheaper(codes, oracle, w
                           early_stop=True, want_diff=True)
     assert np.array_equal(res["flags"].numpy(), ref["flags"]) and res["counters"].tolist() == ref["counters"].tolist()
     assert np.array_equal(res["x_diff"].numpy(), ref["x_diff"])
-    assert frames == 3 * B and iters < 0.5 * B * (64 + 32)          # most frames stop long before the last iteration
+    assert frames == 3 * B and iters < 0.6 * B * (64 + 32)          # most frames stop long before the last iteration
     # same logical error count as the fixed-iteration pipeline, up to frames whose first converged state differs
     full = F.Sandwich_BP_GNN_Evaluation_Model(code, [d1, d2, d2], [G, G], num_layers=3, seed=4).run(B, p, want_counters=True)
     assert abs(int(full["counters"][2]) - int(res["counters"][2])) <= 4

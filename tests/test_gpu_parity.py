@@ -154,6 +154,27 @@ def test_gnn_irregular_code_and_relu(codes, oracle):
         assert_bitexact(out, ref, f"gnn rsurf3 {act}")
 
 
+@pytest.mark.parametrize("L,reduce_op,bias", [(1, "mean", True), (3, "mean", True), (3, "max", False), (4, "sum", True)])
+def test_gnn_any_mlp_depth_bitexact(codes, oracle, L, reduce_op, bias):
+    """Feedback_GNN(num_mlp_layers != 2) (feedback_gnn.py:110-127): layer and a 2-stage pipeline vs the oracle."""
+    import fbgnn as F
+    code = codes["gb48"]
+    B = 50
+    nx, nz, sx, sz = _noise_and_syndromes(oracle, code, B, 0.08, seed=9)
+    g = oracle.CodeGraph(code)
+    r = oracle.bp4(g, float(oracle.prior_llr(0.05)), sx, sz, 6)
+    h_vn = np.stack([r["Lx"], r["Ly"], r["Lz"]], -1)
+    G = F.Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=L, reduce_op=reduce_op,
+                       activation="tanh", use_bias=bias)
+    rng = np.random.default_rng(L)
+    w = [(a + rng.normal(0, 0.25, a.shape)).astype(np.float32) for a in G.get_weights()]
+    G.set_weights(w)
+    out = G((h_vn, r["z_logit"], r["x_logit"], sx, sz))
+    ref = oracle.gnn_deep(g, oracle.GnnDeep(w, 40, 20, L, "tanh", reduce_op, use_bias=bias), h_vn, r["z_logit"],
+                          r["x_logit"], sx, sz)
+    assert_bitexact(out, ref, f"deep gnn L={L} {reduce_op}")
+
+
 def test_pauli_and_syndrome_bitexact(codes, oracle):
     import fbgnn as F
     from fbgnn import _ffi

@@ -37,8 +37,11 @@ def test_save_load_weights_roundtrip(tmp_path, codes, weights):
         G2.set_weights(weights["c882"][:5])
     G3 = F.Feedback_GNN(code=codes["steane"], num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, use_bias=False)
     assert len(G3.get_weights()) == 6
-    with pytest.raises(NotImplementedError):
-        F.Feedback_GNN(code=codes["steane"], num_msg_dims=20, num_hidden_units=40, num_mlp_layers=3)
+    G4 = F.Feedback_GNN(code=codes["steane"], num_msg_dims=20, num_hidden_units=40, num_mlp_layers=3, use_bias=True)
+    assert [w.shape for w in G4.get_weights()] == [(40, 3), (3,)] + [(4, 40), (40,), (40, 40), (40,), (40, 20), (20,)] * 2 + \
+        [(43, 40), (40,), (40, 40), (40,)]
+    assert [w.shape for w in F.Feedback_GNN(codes["steane"], 20, 40, 1, use_bias=True).get_weights()] == \
+        [(43, 3), (3,), (4, 20), (20,), (4, 20), (20,)]
 
 
 def test_c_abi_library_exports_every_declared_symbol():
