@@ -194,8 +194,9 @@ int launch_bp2(fbgnn_ctx *ctx, const Bp2Args &a, int64_t B) {
     return launch_bp2_m<0, 0>(ctx, a, B, smem);
 }
 
-extern "C" int fbgnn_bp2_decode(fbgnn_graph *g, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
-                                fbgnn_tensor2 llr, fbgnn_tensor2 synd, fbgnn_tensor2 soft, fbgnn_tensor2 hard) {
+extern "C" int fbgnn_bp2_decode_ex(fbgnn_graph *g, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                                   fbgnn_tensor2 llr, fbgnn_tensor2 synd, fbgnn_tensor2 soft, fbgnn_tensor2 hard,
+                                   const float *edge_weights, fbgnn_tensor2 msg_in, fbgnn_tensor2 msg_out) {
     REQUIRE(g, "graph is NULL");
     REQUIRE(cn_type >= 0 && cn_type <= 2, "unknown cn_type %d", cn_type);
     REQUIRE(num_iter >= 0 && B >= 0, "num_iter and B must be non-negative");
@@ -208,6 +209,13 @@ extern "C" int fbgnn_bp2_decode(fbgnn_graph *g, int32_t cn_type, int32_t num_ite
     a.S = g->dev; a.cn_type = cn_type; a.num_iter = num_iter; a.factor = factor;
     a.llr = v2<const float>(llr); a.synd = v2<const uint8_t>(synd);
     a.soft = v2<float>(soft); a.hard = v2<uint8_t>(hard);
+    a.edge_w = edge_weights;
+    a.msg_in = v2<const float>(msg_in); a.msg_out = v2<float>(msg_out);
     return launch_bp2(ctx, a, B);
 }
 
+extern "C" int fbgnn_bp2_decode(fbgnn_graph *g, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                                fbgnn_tensor2 llr, fbgnn_tensor2 synd, fbgnn_tensor2 soft, fbgnn_tensor2 hard) {
+    const fbgnn_tensor2 none = {nullptr, 0, 0};
+    return fbgnn_bp2_decode_ex(g, cn_type, num_iter, factor, B, llr, synd, soft, hard, nullptr, none, none);
+}

@@ -692,6 +692,10 @@ struct Bp2Args {
     View2<uint8_t> hard;                // (b, v) optional
     uint8_t *vbits;                     // optional [B][n]: the hard decision goes to bit 2 (pipeline mode)
     int *next_list, *next_count;        // optional: frames whose decision misses the syndrome (for OSD-0)
+    const float *edge_w;                // optional [E], VN order: per-edge weights on the v2c messages (trainable decoder,
+                                        // decoding.py:981-983)
+    View2<const float> msg_in;          // optional (b, e): initial c2v messages (stateful decoder, decoding.py:947-953)
+    View2<float> msg_out;               // optional (b, e): final c2v messages
 };
 
 // smem: float msg[E], llr[n]; u8 sb[m], dec[n].  (DV, DC) > 0: regular graph, unrolled (boxplus-phi only).
@@ -703,7 +707,7 @@ static __global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
     const int64_t b = blockIdx.x;
     float *msg = smem, *llr = msg + S.E;
     uint8_t *sb = (uint8_t *)(llr + n), *dec = sb + S.m;
-    for (int e = tid; e < S.E; e += T) msg[e] = 0.0f;
+    for (int e = tid; e < S.E; e += T) msg[e] = a.msg_in.ptr ? a.msg_in(b, e) : 0.0f;
     for (int v = tid; v < n; v += T) {
         float l = a.llr.ptr ? a.llr(b, v) : a.llr_const;
         l = FB_FMIN(FB_FMAX(l, -FB_LLR_MAX), FB_LLR_MAX);
@@ -724,14 +728,22 @@ static __global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
                 for (int k = 0; k < D; k++) s = FB_ADD(s, m[k]);
                 s = FB_ADD(s, llr[v]);
 #pragma unroll
-                for (int k = 0; k < D; k++) msg[v * D + k] = FB_SUB(s, m[k]);
+                for (int k = 0; k < D; k++) {
+                    float o = FB_SUB(s, m[k]);
+                    if (a.edge_w) o = FB_MUL(o, a.edge_w[v * D + k]);
+                    msg[v * D + k] = o;
+                }
                 continue;
             }
             const int e0 = S.vn_ptr[v], e1 = S.vn_ptr[v + 1];
             float s = 0.0f;
             for (int e = e0; e < e1; e++) s = FB_ADD(s, msg[e]);
             s = FB_ADD(s, llr[v]);
-            for (int e = e0; e < e1; e++) msg[e] = FB_SUB(s, msg[e]);
+            for (int e = e0; e < e1; e++) {
+                float o = FB_SUB(s, msg[e]);
+                if (a.edge_w) o = FB_MUL(o, a.edge_w[e]);
+                msg[e] = o;
+            }
         }
         __syncthreads();
         for (int c = tid; c < S.m; c += T) {
@@ -740,6 +752,7 @@ static __global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
         }
         __syncthreads();
     }
+    if (a.msg_out.ptr) for (int e = tid; e < S.E; e += T) a.msg_out(b, e) = msg[e];
     for (int v = tid; v < n; v += T) {
         float s = 0.0f;
         for (int e = S.vn_ptr[v]; e < S.vn_ptr[v + 1]; e++) s = FB_ADD(s, msg[e]);

@@ -42,9 +42,14 @@ class LDPCBPDecoder:
         assert isinstance(stateful, bool), 'stateful must be bool.'
         if cn_type not in CN_TYPES:
             raise ValueError('Unknown node type.')
-        if trainable or stateful or track_exit:
-            raise NotImplementedError("trainable / stateful / track_exit are outside the quantum hot path "
-                                      "of this build")
+        if track_exit:
+            raise NotImplementedError("track_exit (EXIT-chart bookkeeping, decoding.py:958-961) is not provided")
+        if stateful and is_syndrome:
+            raise ValueError("the reference takes either (llr, msg_vn) or (llr, syndrome), decoding.py:901-909")
+        self._stateful = stateful
+        self._has_weights = trainable
+        self._edge_weights = None         # ones(num_edges) once the graph exists (decoding.py:361-366)
+        self._edge_weights_dev = None
         if not (isinstance(pcm, np.ndarray) or hasattr(pcm, "toarray")):
             raise TypeError("Unsupported dtype of pcm.")
         self._pcm = pcm
@@ -79,9 +84,38 @@ class LDPCBPDecoder:
             self._graph = _ffi.Graph(self._pcm, self._ctx)
         return self._graph
 
+    # -- trainable=True: one weight per edge on the variable-to-check messages, initialised to one -----------------
+    @property
+    def has_weights(self):
+        return self._has_weights
+
+    @property
+    def edge_weights(self):
+        """[num_edges] float32, edges sorted by (variable, check) -- the order of the reference's message vector."""
+        if not self._has_weights:
+            return []
+        if self._edge_weights is None:
+            self._edge_weights = np.ones(self.graph().E, np.float32)
+        return self._edge_weights
+
+    def get_weights(self):
+        return [self.edge_weights.copy()] if self._has_weights else []
+
+    def set_weights(self, weights):
+        if not self._has_weights:
+            if len(weights):
+                raise ValueError("the decoder has no weights (trainable=False)")
+            return
+        w = np.ascontiguousarray(np.asarray(weights[0]), np.float32)
+        if w.shape != (self.graph().E,):
+            raise ValueError(f"Layer weight shape {(self.graph().E,)} not compatible with provided weight shape {w.shape}")
+        self._edge_weights, self._edge_weights_dev = w, None
+
     def __call__(self, inputs):
-        syndrome = None
-        if self._is_syndrome:
+        syndrome = msg_vn = None
+        if self._stateful:
+            llr_ch, msg_vn = inputs
+        elif self._is_syndrome:
             llr_ch, syndrome = inputs
         else:
             llr_ch = inputs
@@ -109,12 +143,28 @@ class LDPCBPDecoder:
                 raise ValueError(f"syndrome must have shape [{g.m},{B}]")
         soft = ctx.empty((B, g.n), np.float32)
         hard = ctx.empty((B, g.n), np.uint8)
-        _ffi.call("fbgnn_bp2_decode", g.handle, CN_TYPES[self._cn_type], self._num_iter,
+        ew = None
+        if self._has_weights:
+            if self._edge_weights_dev is None:
+                self._edge_weights_dev = ctx.asarray(self.edge_weights, np.float32)
+            ew = self._edge_weights_dev.ptr
+        # stateful: the message state is the flat [num_edges, B] tensor of the reference's ragged msg_vn
+        m_in = m_out = None
+        if self._stateful:
+            m_out = ctx.empty((B, g.E), np.float32).T
+            if msg_vn is not None:
+                m_in = ctx.asarray(msg_vn, np.float32)
+                if m_in.shape != (g.E, B):
+                    raise ValueError(f"msg_vn must have shape [{g.E},{B}]")
+        _ffi.call("fbgnn_bp2_decode_ex", g.handle, CN_TYPES[self._cn_type], self._num_iter,
                   self._normalization_factor, B, llr.t2(), synd.t2() if synd is not None else _ffi.NULL2,
-                  soft.t2(), hard.t2())
+                  soft.t2(), hard.t2(), ew,
+                  m_in.T.t2() if m_in is not None else _ffi.NULL2, m_out.T.t2() if m_out is not None else _ffi.NULL2)
         if on_device:
-            return hard if self._hard_out else soft
+            res = hard if self._hard_out else soft
+            return (res, m_out) if self._stateful else res
         out = hard.numpy().astype(self._output_dtype) if self._hard_out else soft.numpy().astype(self._output_dtype)
-        return out.reshape(lead_shape + (g.n,))
+        out = out.reshape(lead_shape + (g.n,))
+        return (out, m_out.numpy()) if self._stateful else out
 
     call = __call__

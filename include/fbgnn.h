@@ -213,6 +213,14 @@ int fbgnn_bp2_decode(fbgnn_graph *graph, int32_t cn_type, int32_t num_iter, floa
                      int64_t B, fbgnn_tensor2 llr, fbgnn_tensor2 synd, fbgnn_tensor2 soft,
                      fbgnn_tensor2 hard);
 
+/* The same with the reference's optional decoder features: edge_weights (device float32 [E], edges sorted by
+ * (variable, check); NULL = none) multiply the variable-to-check messages (trainable=True, decoding.py:361-366,
+ * 981-983); msg_in / msg_out (float32 views (b, edge), NULL ptr = absent) carry the check-to-variable messages into
+ * and out of the call (stateful=True, decoding.py:947-953, 1045-1048). */
+int fbgnn_bp2_decode_ex(fbgnn_graph *graph, int32_t cn_type, int32_t num_iter, float factor, int64_t B,
+                        fbgnn_tensor2 llr, fbgnn_tensor2 synd, fbgnn_tensor2 soft, fbgnn_tensor2 hard,
+                        const float *edge_weights, fbgnn_tensor2 msg_in, fbgnn_tensor2 msg_out);
+
 /* OSD0_Decoder.call (bp_osd.py:51-77): ordered-statistics post-processing of order 0.  `basis` is the
  * graph of a FULL-RANK row basis of the parity-check matrix (rank rows); llr float32 (b, v) are the
  * reliabilities BP produced (small = likely in error; ties are broken by index); synd uint8 (row, b) is

@@ -295,17 +295,23 @@ def bp4(g, llr, syndrome_x, syndrome_z, num_iter, factor=1.0, cn_type="boxplus-p
     return out
 
 
-def bp2(pcm_or_side, llr, syndrome, num_iter, factor=1.0, cn_type="boxplus-phi"):
-    """llr [B,n] logits; syndrome [m,B] or None.  Returns (soft [B,n], hard [B,n] u8)."""
+def bp2(pcm_or_side, llr, syndrome, num_iter, factor=1.0, cn_type="boxplus-phi", edge_weights=None, msg_in=None,
+        want_msgs=False):
+    """llr [B,n] logits; syndrome [m,B] or None.  Returns (soft [B,n], hard [B,n] u8) (+ final c2v messages [B,E], VN
+    order, with want_msgs).  edge_weights [E] (VN order): the trainable decoder's weights on the v2c messages;
+    msg_in [B,E]: the stateful decoder's incoming message state."""
     S = pcm_or_side if isinstance(pcm_or_side, Side) else Side(pcm_or_side)
     llr = _f32(llr)
     B = llr.shape[0]
     s = None if syndrome is None else _u8(syndrome)
     soft = np.empty((B, S.n), np.float32)
     hard = np.empty((B, S.n), np.uint8)
+    ew = None if edge_weights is None else _f32(edge_weights)
+    mi = None if msg_in is None else _f32(msg_in)
+    mo = np.empty((B, S.E), np.float32) if want_msgs else None
     lib().orc_bp2(C.byref(S.c), C.c_int(CN_TYPES[cn_type]), C.c_int(num_iter), C.c_float(factor),
-                  C.c_int64(B), _p(llr), _p(s), _p(soft), _p(hard))
-    return soft, hard
+                  C.c_int64(B), _p(llr), _p(s), _p(soft), _p(hard), _p(ew), _p(mi), _p(mo))
+    return (soft, hard, mo) if want_msgs else (soft, hard)
 
 
 def gnn(g, G, h_vn, logit_hx, logit_hz, syndrome_x, syndrome_z):

@@ -470,24 +470,32 @@ void orc_bp4(const orc_side_t *X, const orc_side_t *Z, const orc_rows_t *rows_x,
 /* One frame of LDPCBPDecoder.call with is_syndrome (decoding.py:905-1034).  `logit` is the
  * layer input (log p1/p0); returns the soft output (logits) in `soft` and the hard decision
  * (1 if logit > 0) in `hard`. */
-static void bp2_frame(const orc_side_t *S, int cn_type, int num_iter, float factor,
-                      const float *logit, const uint8_t *synd, float *msg, float *soft,
-                      uint8_t *hard, float *work, float *llr) {
+/* edge_w (optional): the trainable decoder's per-edge weights on the v2c messages, VN order (decoding.py:981-983);
+ * msg_in / msg_out (optional): the stateful decoder's c2v messages before / after the call (decoding.py:947-953). */
+static void bp2_frame_ex(const orc_side_t *S, int cn_type, int num_iter, float factor,
+                         const float *logit, const uint8_t *synd, float *msg, float *soft,
+                         uint8_t *hard, float *work, float *llr, const float *edge_w, const float *msg_in,
+                         float *msg_out) {
     const int n = S->n;
     for (int v = 0; v < n; v++) {
         float l = FB_FMIN(FB_FMAX(logit[v], -FB_LLR_MAX), FB_LLR_MAX);   /* decoding.py:918-920 */
         llr[v] = -l;                                                   /* decoding.py:940 */
     }
-    memset(msg, 0, sizeof(float) * (size_t)S->E);
+    if (msg_in) memcpy(msg, msg_in, sizeof(float) * (size_t)S->E);
+    else memset(msg, 0, sizeof(float) * (size_t)S->E);
     for (int it = 0; it < num_iter; it++) {
         for (int v = 0; v < n; v++) {                                  /* decoding.py:511-535 */
             float s = 0.0f;
             for (int e = S->vn_ptr[v]; e < S->vn_ptr[v + 1]; e++) s = FB_ADD(s, msg[e]);
             s = FB_ADD(s, llr[v]);
-            for (int e = S->vn_ptr[v]; e < S->vn_ptr[v + 1]; e++) msg[e] = FB_SUB(s, msg[e]);
+            for (int e = S->vn_ptr[v]; e < S->vn_ptr[v + 1]; e++) {
+                msg[e] = FB_SUB(s, msg[e]);
+                if (edge_w) msg[e] = FB_MUL(msg[e], edge_w[e]);
+            }
         }
         cn_update(S, cn_type, 0, factor, synd, msg, work);
     }
+    if (msg_out) memcpy(msg_out, msg, sizeof(float) * (size_t)S->E);
     for (int v = 0; v < n; v++) {                                      /* decoding.py:1026-1034 */
         float s = 0.0f;
         for (int e = S->vn_ptr[v]; e < S->vn_ptr[v + 1]; e++) s = FB_ADD(s, msg[e]);
@@ -498,8 +506,15 @@ static void bp2_frame(const orc_side_t *S, int cn_type, int num_iter, float fact
 }
 
 /* llr [B,n] logits, synd [m,B] or NULL, soft [B,n], hard [B,n] */
+static void bp2_frame(const orc_side_t *S, int cn_type, int num_iter, float factor,
+                      const float *logit, const uint8_t *synd, float *msg, float *soft,
+                      uint8_t *hard, float *work, float *llr) {
+    bp2_frame_ex(S, cn_type, num_iter, factor, logit, synd, msg, soft, hard, work, llr, NULL, NULL, NULL);
+}
+
 void orc_bp2(const orc_side_t *S, int cn_type, int num_iter, float factor, int64_t B,
-             const float *llr, const uint8_t *synd, float *soft, uint8_t *hard) {
+             const float *llr, const uint8_t *synd, float *soft, uint8_t *hard, const float *edge_w,
+             const float *msg_in, float *msg_out) {
     const int n = S->n, m = S->m;
     int wd = max_cn_degree(S);
 #pragma omp parallel
@@ -511,8 +526,9 @@ void orc_bp2(const orc_side_t *S, int cn_type, int num_iter, float factor, int64
 #pragma omp for schedule(dynamic, 4)
         for (int64_t b = 0; b < B; b++) {
             if (synd) for (int c = 0; c < m; c++) s[c] = synd[(int64_t)c * B + b];
-            bp2_frame(S, cn_type, num_iter, factor, llr + b * n, synd ? s : NULL, msg,
-                      soft + b * n, hard + b * n, work, l);
+            bp2_frame_ex(S, cn_type, num_iter, factor, llr + b * n, synd ? s : NULL, msg,
+                         soft + b * n, hard + b * n, work, l, edge_w, msg_in ? msg_in + b * S->E : NULL,
+                         msg_out ? msg_out + b * S->E : NULL);
         }
         free(msg); free(work); free(l); free(s);
     }

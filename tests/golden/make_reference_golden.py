@@ -149,6 +149,20 @@ def main():
                 b2[f"{cname}.{cn_type}.{it}.soft"] = np.asarray(dec((tf.constant(llr), tf.constant(synd))))
                 hard = ns.LDPCBPDecoder(code.hx, is_syndrome=True, num_iter=it, normalization_factor=0.9, cn_type=cn_type)
                 b2[f"{cname}.{cn_type}.{it}.hard"] = np.asarray(hard((tf.constant(llr), tf.constant(synd)))).astype(np.uint8)
+        if cname == "c882":
+            # trainable=True: per-edge weights on the v2c messages (decoding.py:361-366, 981-983), here set to random values
+            dec = ns.LDPCBPDecoder(code.hx, trainable=True, is_syndrome=True, num_iter=3, normalization_factor=0.9,
+                                   cn_type="boxplus-phi", hard_out=False)
+            ew = (1.0 + 0.2 * np.random.default_rng(9).standard_normal(int(code.hx.sum()))).astype(np.float32)
+            dec._edge_weights.assign(ew)
+            b2["c882.trainable.edge_weights"] = ew
+            b2["c882.trainable.soft"] = np.asarray(dec((tf.constant(llr), tf.constant(synd))))
+            # stateful=True: (llr, msg_vn) -> (x, msg_vn); two calls of 2 iterations == one call of 4 (decoding.py:947-953)
+            dec = ns.LDPCBPDecoder(code.hx, stateful=True, num_iter=2, normalization_factor=0.9, cn_type="minsum", hard_out=False)
+            x1, m1 = dec((tf.constant(llr), None))
+            x2, m2 = dec((tf.constant(llr), m1))
+            b2["c882.stateful.x1"], b2["c882.stateful.x2"] = np.asarray(x1), np.asarray(x2)
+            b2["c882.stateful.m1"], b2["c882.stateful.m2"] = np.asarray(m1.flat_values), np.asarray(m2.flat_values)
         print("bp2", cname)
     np.savez_compressed(os.path.join(HERE, "ref_bp2.npz"), **b2)
 

@@ -138,7 +138,7 @@ def _check_bp2(Z, key, soft, hard, what):
 
 
 def _bp2_cases(Z):
-    return sorted({k.rsplit(".", 1)[0] for k in Z.files if k.endswith(".soft")})
+    return sorted({k.rsplit(".", 1)[0] for k in Z.files if k.endswith(".soft") and k.split(".")[-2].isdigit()})
 
 
 @pytest.mark.parametrize("arith", ["exact", "sfu"])
@@ -181,6 +181,44 @@ def test_cuda_trainable_mode_matches_oracle_and_reference(ref, allcodes, oracle)
     assert np.array_equal(xh.astype(np.uint8), want["x_hat"]) and np.array_equal(zh.astype(np.uint8), want["z_hat"])
     r = Z["c882.trainable.llr_hat"]
     assert np.all(np.abs(llr_hat - r) <= _logit_tol(r, llr_hat))                             # float32 noise vs the reference's code
+
+
+def test_oracle_bp2_trainable_and_stateful_match_the_reference_code(ref, allcodes, oracle):
+    Z = ref["bp2"]
+    hx = allcodes["c882"].hx
+    soft, _ = oracle.bp2(hx, Z["c882.llr"], Z["c882.synd"], 3, 0.9, "boxplus-phi", edge_weights=Z["c882.trainable.edge_weights"])
+    assert np.abs(soft - Z["c882.trainable.soft"]).max() <= 2e-4
+    x1, _, m1 = oracle.bp2(hx, Z["c882.llr"], None, 2, 0.9, "minsum", want_msgs=True)
+    x2, _, m2 = oracle.bp2(hx, Z["c882.llr"], None, 2, 0.9, "minsum", msg_in=m1, want_msgs=True)
+    for got, key in ((x1, "x1"), (x2, "x2"), (m1.T, "m1"), (m2.T, "m2")):
+        assert np.array_equal(got, Z[f"c882.stateful.{key}"]), key           # min-sum: bit-identical to the reference's code
+    x4, _ = oracle.bp2(hx, Z["c882.llr"], None, 4, 0.9, "minsum")
+    assert np.array_equal(x4, x2)
+
+
+@pytest.mark.gpu
+def test_cuda_bp2_trainable_and_stateful(ref, allcodes, oracle):
+    import fbgnn as F
+    Z = ref["bp2"]
+    hx = allcodes["c882"].hx
+    llr, synd, ew = Z["c882.llr"], Z["c882.synd"], Z["c882.trainable.edge_weights"]
+    dec = F.LDPCBPDecoder(hx, trainable=True, is_syndrome=True, num_iter=3, normalization_factor=0.9, cn_type="boxplus-phi",
+                          hard_out=False)
+    assert dec.has_weights and np.all(dec.edge_weights == 1.0) and len(dec.get_weights()) == 1
+    plain = F.LDPCBPDecoder(hx, is_syndrome=True, num_iter=3, normalization_factor=0.9, cn_type="boxplus-phi", hard_out=False)
+    assert np.array_equal(dec((llr, synd)), plain((llr, synd)))                 # unit weights change nothing
+    dec.set_weights([ew])
+    got = dec((llr, synd))
+    want, _ = oracle.bp2(hx, llr, synd, 3, 0.9, "boxplus-phi", edge_weights=ew)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    assert np.abs(got - Z["c882.trainable.soft"]).max() <= 2e-4
+    st = F.LDPCBPDecoder(hx, stateful=True, num_iter=2, normalization_factor=0.9, cn_type="minsum", hard_out=False)
+    x1, m1 = st((llr, None))
+    x2, m2 = st((llr, m1))
+    for got, key in ((x1, "x1"), (x2, "x2"), (m1, "m1"), (m2, "m2")):
+        assert np.array_equal(got, Z[f"c882.stateful.{key}"]), key
+    with pytest.raises(NotImplementedError):
+        F.LDPCBPDecoder(hx, track_exit=True)
 
 
 @pytest.mark.parametrize("arith", ["exact", "sfu"])
