@@ -1,5 +1,6 @@
 // fbgnn_bp.cu -- launch configuration of the BP kernels and the decoder entry points of the C ABI.
 #include "fbgnn_internal.h"
+#include "fbgnn_cluster.cuh"
 
 // ------------------------------------------------------------------ launch helpers ------
 // Threads per CTA for the one-frame-per-CTA kernels: the multiple of 32 in [128, 512] that
@@ -71,6 +72,64 @@ static int launch_bp4_gstate(fbgnn_ctx *ctx, Bp4Args a, int64_t grid, int thread
     return 0;
 }
 
+// Codes beyond one SM's shared memory, fast path: a thread-block cluster of 2 / 4 / 8 CTAs per frame with the messages in
+// distributed shared memory (fbgnn_cluster.cuh).  Returns 1 if the configuration is not served (caller falls back).
+template <bool CP, typename MATH, int DCMAX>
+static int launch_bp4_cluster_t(fbgnn_ctx *ctx, const Bp4Args &a, int64_t frames, const ClusterPart &P, size_t smem) {
+    auto kernel = k_bp4_cluster<CP, MATH, DCMAX>;
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(frames * P.C), 1, 1);
+    cfg.blockDim = dim3(512, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)P.C; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CK(cudaLaunchKernelEx(&cfg, kernel, a, P));
+    ctx->launches++;
+    return 0;
+}
+
+template <bool CP, typename MATH>
+static int launch_bp4_cluster_d(fbgnn_ctx *ctx, const Bp4Args &a, int64_t frames, const ClusterPart &P, size_t smem, int max_dc) {
+    return max_dc <= 8 ? launch_bp4_cluster_t<CP, MATH, 8>(ctx, a, frames, P, smem)
+                       : launch_bp4_cluster_t<CP, MATH, 64>(ctx, a, frames, P, smem);
+}
+
+static int launch_bp4_cluster(fbgnn_ctx *ctx, const Bp4Args &a, int64_t frames, bool cp, int max_dc) {
+    const SideDev &X = a.X, &Z = a.Z;
+    if (!X.h_vn_ptr || !Z.h_vn_ptr || a.iter_logits.ptr || a.iters_out || a.rows_x_ptr) return 1;
+    const int n = X.n, mt = X.m + Z.m;
+    // Smallest cluster whose CTAs fit; FBGNN_BP4_CLUSTER=<C> (lab knob) starts the search at C.  Measured on the
+    // [[7688,50]] code (profiles/r02_cluster_vs_gstate.txt).
+    int c_first = 4;                   // 4 CTAs per frame measured best (2: too few warps per SM; 8: barrier cost)
+    if (const char *e = getenv("FBGNN_BP4_CLUSTER")) c_first = std::max(2, std::min(CL_MAX, atoi(e)));
+    for (int C = c_first; C <= CL_MAX; C *= 2) {
+        ClusterPart P{};
+        P.C = C;
+        for (int r = 0; r <= C; r++) {
+            P.v0[r] = (int)((int64_t)n * r / C);
+            P.ex0[r] = X.h_vn_ptr[P.v0[r]];
+            P.ez0[r] = Z.h_vn_ptr[P.v0[r]];
+            P.c0[r] = (int)((int64_t)mt * r / C);
+        }
+        for (int r = 0; r < C; r++) {
+            P.nv_max = std::max(P.nv_max, P.v0[r + 1] - P.v0[r]);
+            P.ex_max = std::max(P.ex_max, P.ex0[r + 1] - P.ex0[r]);
+            P.ez_max = std::max(P.ez_max, P.ez0[r + 1] - P.ez0[r]);
+        }
+        const size_t smem = sizeof(float) * ((size_t)P.ex_max + P.ez_max + (cp ? 2 : 3) * (size_t)P.nv_max) +
+                            (((size_t)P.nv_max + 3) & ~(size_t)3) + sizeof(int) * CL_MAX;
+        if (smem > ctx->smem_optin) continue;
+        if (ctx->math_mode == FBGNN_MATH_SFU)
+            return cp ? launch_bp4_cluster_d<true, MathSfu>(ctx, a, frames, P, smem, max_dc) : launch_bp4_cluster_d<false, MathSfu>(ctx, a, frames, P, smem, max_dc);
+        return cp ? launch_bp4_cluster_d<true, MathExact>(ctx, a, frames, P, smem, max_dc) : launch_bp4_cluster_d<false, MathExact>(ctx, a, frames, P, smem, max_dc);
+    }
+    return 1;
+}
+
 int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a_in, int64_t grid) {
     if (grid <= 0) return 0;
     Bp4Args a = a_in;
@@ -79,9 +138,21 @@ int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a_in, int64_t grid) {
     const size_t smem = bp4_smem(a.X, a.Z, cp, a.iter_logits.ptr != nullptr);
     int threads = pick_threads(a.X.n, a.X.m + a.Z.m);
     if (const char *t = getenv("FBGNN_BP4_THREADS")) threads = std::max(32, std::min(512, atoi(t) / 32 * 32));   // lab knob
-    if (smem > ctx->smem_optin)
+    if (smem > ctx->smem_optin) {
+        // Larger than one SM: a thread-block cluster with the messages in distributed shared memory, or the kernel whose
+        // state lives in HBM / L2.  Measured on the [[7688,50]] code (profiles/r02_cluster_vs_gstate.txt): the cluster of
+        // 4 wins by 7 % in exact arithmetic, the L2-state kernel by 17 % in SFU arithmetic (its state stays L2-resident
+        // and it keeps more warps per SM) -- the default follows the measurement, FBGNN_BP4_LARGE=cluster|gstate overrides.
+        const char *force = getenv("FBGNN_BP4_LARGE");
+        const bool want_cluster = force ? !strcmp(force, "cluster") : ctx->math_mode != FBGNN_MATH_SFU;
+        if (want_cluster) {
+            const int max_dc = (a.X.reg_dc && a.Z.reg_dc) ? std::max(a.X.reg_dc, a.Z.reg_dc) : 64;
+            const int rc = launch_bp4_cluster(ctx, a, grid, cp, max_dc);
+            if (rc <= 0) return rc;
+        }
         return ctx->math_mode == FBGNN_MATH_SFU ? launch_bp4_gstate<MathSfu>(ctx, a, grid, threads, cp)
                                                  : launch_bp4_gstate<MathExact>(ctx, a, grid, threads, cp);
+    }
     // both sides regular with the same degrees -> unrolled instantiation
     int dv = 0, dc = 0;
     if (a.X.reg_dv && a.X.reg_dv == a.Z.reg_dv && a.X.reg_dc && a.X.reg_dc == a.Z.reg_dc) { dv = a.X.reg_dv; dc = a.X.reg_dc; }

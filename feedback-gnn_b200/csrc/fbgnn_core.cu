@@ -291,6 +291,8 @@ extern "C" int fbgnn_graph_create(fbgnn_ctx *ctx, int32_t n, int32_t m, const in
     d.n = n; d.m = m; d.E = E;
     d.reg_dc = (m > 0 && max_dc == min_dc) ? max_dc : 0;
     d.reg_dv = (max_dv == min_dv) ? max_dv : 0;
+    g->h_vn_ptr.assign(vn_ptr.begin(), vn_ptr.end());
+    d.h_vn_ptr = g->h_vn_ptr.empty() ? nullptr : g->h_vn_ptr.data();
     int rc = 0;
     rc |= upload(g, vn_ptr, &d.vn_ptr); rc |= upload(g, vn_cn, &d.vn_cn);
     rc |= upload(g, cn_ptr, &d.cn_ptr); rc |= upload(g, cn_edge, &d.cn_edge);

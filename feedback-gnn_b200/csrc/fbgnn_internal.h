@@ -69,6 +69,7 @@ struct fbgnn_graph {
     bool decodable = true;         // false: only the bit-packed rows exist (dense logical matrices)
     std::string why_not;
     std::vector<void *> allocs;
+    std::vector<int> h_vn_ptr;     // host copy of the per-variable edge ranges
 };
 
 struct fbgnn_code {

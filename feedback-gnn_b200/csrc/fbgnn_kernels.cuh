@@ -32,6 +32,7 @@ struct SideDev {
     const idx_t *cn_edge;      // [E]   VN-order position of each edge, listed in CN order
     const idx_t *cn_vn;        // [E]   variable of each edge, listed in CN order
     const uint32_t *bitrows;   // [m][W] rows bit-packed, W = ceil(n/32)
+    const int *h_vn_ptr;       // HOST copy of vn_ptr (launch-time partitioning of the cluster kernel; never read on the device)
 };
 
 template <typename T> struct View2 { T *ptr; int64_t s0, s1;

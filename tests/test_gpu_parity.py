@@ -347,11 +347,14 @@ def test_dlpack_roundtrip():
     assert np.array_equal(e.numpy(), a.transpose(1, 0, 2))
 
 
-def test_code_larger_than_shared_memory_uses_hbm_state(oracle, weights):
+@pytest.mark.parametrize("large", ["cluster", "gstate"])
+def test_code_larger_than_shared_memory(oracle, weights, large, monkeypatch):
     """[[7688,50]] hypergraph-product code: 36 bytes of decoder state per qubit = 277 KB per frame, more than an SM's
-    227 KB of shared memory -- the decoder switches to the kernel variant whose message arrays live in HBM.
-    Same arithmetic: layer outputs and pipeline flags stay bit-exact with the oracle."""
+    227 KB of shared memory.  Default: a thread-block cluster decodes the frame with the messages in distributed shared
+    memory (csrc/fbgnn_cluster.cuh); FBGNN_BP4_LARGE=gstate selects the fallback whose message arrays live in HBM / L2.
+    Same arithmetic either way: layer outputs (incl. the final messages) and pipeline flags bit-exact with the oracle."""
     import fbgnn as F
+    monkeypatch.setenv("FBGNN_BP4_LARGE", large)
     h = F.create_circulant_matrix(62, [0, 2, 5])
     code = F.hypergraph_product(h, h)
     assert (code.N, code.K) == (7688, 50)
@@ -367,6 +370,17 @@ def test_code_larger_than_shared_memory_uses_hbm_state(oracle, weights):
         ref = oracle.bp4(g, llr, sx, sz, it, 0.9, cn_type)
         for k, o in zip(("Lx", "Ly", "Lz", "x_hat", "z_hat", "x_logit", "z_logit"), out):
             assert_bitexact(np.asarray(o, dtype=ref[k].dtype), ref[k], f"large code {cn_type} {k}")
+        dev = dec._device()
+        d = dec.decode_device(dev.ctx.asarray(llr), dev.ctx.asarray(sx), dev.ctx.asarray(sz), want_msgs=True)
+        refm = oracle.bp4(g, llr, sx, sz, it, 0.9, cn_type, want_msgs=True)
+        assert_bitexact(d[7].numpy(), refm["msg_x"], f"large code {cn_type} msg_x")
+        assert_bitexact(d[8].numpy(), refm["msg_z"], f"large code {cn_type} msg_z")
+    # constant prior (stage 0 of a pipeline) through the same path
+    d1c = F.QLDPCBPDecoder(code, num_iter=5, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+    outc = d1c.decode_device(None, d1c._device().ctx.asarray(sx), d1c._device().ctx.asarray(sz), prior=float(prior))
+    refc = oracle.bp4(g, float(prior), sx, sz, 5, 1.0, "boxplus-phi")
+    for k, o in zip(("Lx", "Ly", "Lz", "x_hat", "z_hat", "x_logit", "z_logit"), outc):
+        assert_bitexact(o.numpy(), refc[k], f"large code const prior {k}")
     G = F.Feedback_GNN(code, 20, 40, 2, "mean", "tanh", True)
     G.set_weights(weights["c882"])
     d1 = F.QLDPCBPDecoder(code, num_iter=8, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
