@@ -245,23 +245,26 @@ def main():
     model.skip_inactive = False
     s_value = s_steps * B * world / (s_ms * 1e-3)
 
-    # ---- end to end through the public API with HOST buffers: packed noise bit-planes in, packed flags out
-    W = (N_Q + 31) // 32
+    # ---- end to end through the public API with HOST buffers: packed noise bit-planes in, packed indicator planes out
+    # (32 qubits / 32 frames per word: 10.5 MB in, 12 KB out per step instead of 83 MB / 33 KB as byte arrays)
     host_src = F.Pauli(seed=2, first_frame=10 ** 10 + rank * B).sample_device(B, N_Q, F.pauli_thresholds(P_NOISE))
     nx_host, nz_host = host_src[0].numpy(), host_src[1].numpy()                # synthetic samples, host resident
-    nx_h = _ffi.PinnedArray((B, N_Q), np.uint8)
-    nz_h = _ffi.PinnedArray((B, N_Q), np.uint8)
-    nx_h.array[:], nz_h.array[:] = nx_host, nz_host
-    flags_h = _ffi.PinnedArray((B,), np.uint8)
-    nx_d, nz_d = ctx.empty((B, N_Q), np.uint8), ctx.empty((B, N_Q), np.uint8)
+    wq, fw = F.packed_words(N_Q), (B + 31) // 32
+    nx_h = _ffi.PinnedArray((B, wq), np.uint32)
+    nz_h = _ffi.PinnedArray((B, wq), np.uint32)
+    nx_h.array[:], nz_h.array[:] = F.pack_bits(nx_host), F.pack_bits(nz_host)
+    planes_h = _ffi.PinnedArray((3, fw), np.uint32)
+    nxb_d, nzb_d = ctx.empty((B, wq), np.uint32), ctx.empty((B, wq), np.uint32)
+    nx_d, nz_d = ctx.asarray(nx_host), ctx.asarray(nz_host)                    # byte form, for the roofline probe below
     import ctypes as C
 
     def e2e_step():
-        _ffi.copy_h2d_async(ctx, nx_d, nx_h.array)
-        _ffi.copy_h2d_async(ctx, nz_d, nz_h.array)
-        res = model.run(B, P_NOISE, noise=(nx_d, nz_d), want_flags=True, want_diff=False, want_counters=True)
-        _ffi.call("fbgnn_memcpy_d2h", ctx.handle, flags_h.array.ctypes.data_as(C.c_void_p), res["flags"].ptr, B)
-        return int(((flags_h.array >> 1) & 1).sum()), res["counters"]
+        _ffi.copy_h2d_async(ctx, nxb_d, nx_h.array)
+        _ffi.copy_h2d_async(ctx, nzb_d, nz_h.array)
+        res = model.run_bits(B, P_NOISE, noise_bits=(nxb_d, nzb_d), want_counters=True)
+        _ffi.call("fbgnn_memcpy_d2h", ctx.handle, planes_h.array.ctypes.data_as(C.c_void_p), res["frame_bits"].ptr,
+                  planes_h.array.nbytes)
+        return int(F.unpack_bits(planes_h.array[1], B).sum()), res["counters"]
 
     e2e_step()
     comm.barrier()
@@ -276,7 +279,7 @@ def main():
     e2e_ms = max(e2e_ms_dev, e2e_wall * 1e3)          # wall clock includes the Python host side
     e2e_ms = float(comm.allreduce_f64([e2e_ms], "max")[0])
     e2e_value = e2e_steps * B * world / (e2e_ms * 1e-3)
-    h2d_bytes, d2h_bytes = 2 * B * N_Q, B + 32
+    h2d_bytes, d2h_bytes = 2 * B * wq * 4, 3 * fw * 4 + 32
 
     if rank != 0:
         comm.close()
@@ -364,7 +367,8 @@ def main():
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes,
                     "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
-                    "path": "Sandwich_BP_GNN_Evaluation_Model.run(noise=host samples) -> flags/counters on host"},
+                    "path": "Sandwich_BP_GNN_Evaluation_Model.run_bits(noise_bits=host bit-planes) -> indicator planes + "
+                            "counters on host (fbgnn_pipeline_run_bits)"},
             "gpu_launches": int(launches),
             "skip_inactive": {"value": s_value, "unit": "frames/s", "steps": s_steps,
                               "block_errors": int(s_counters[2]), "frames": int(s_counters[0]),

@@ -17,8 +17,9 @@ static int pick_threads(int n_items_a, int n_items_b) {
 }
 
 static size_t bp4_smem(const SideDev &X, const SideDev &Z, bool const_prior, bool iter_logits) {
-    return sizeof(float) * ((size_t)X.E + Z.E + ((const_prior ? 2 : 3) + (iter_logits ? 2 : 0)) * (size_t)X.n) +
-           2 * (((size_t)X.n + 1) & ~(size_t)1) + X.m + Z.m + X.n + 16;
+    const size_t np = (size_t)pad4(X.n);
+    return sizeof(float) * ((size_t)X.E + Z.E + ((const_prior ? 2 : 3) + (iter_logits ? 2 : 0)) * np) +
+           (size_t)pad16(X.m + Z.m) + 2 * (((size_t)X.n + 1) & ~(size_t)1) + X.n + 16;
 }
 
 template <bool CP, int DV, int DC, typename MATH, bool FPX>
@@ -54,8 +55,8 @@ static int launch_bp4_m(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t s
 template <typename MATH>
 static int launch_bp4_gstate(fbgnn_ctx *ctx, Bp4Args a, int64_t grid, int threads, bool cp) {
     const SideDev &X = a.X, &Z = a.Z;
-    const size_t smem = 2 * (((size_t)X.n + 1) & ~(size_t)1) + X.m + Z.m + X.n + 16;
-    a.state_stride = (int64_t)X.E + Z.E + ((cp ? 2 : 3) + (a.iter_logits.ptr ? 2 : 0)) * (int64_t)X.n;
+    const size_t smem = (size_t)pad16(X.m + Z.m) + 2 * (((size_t)X.n + 1) & ~(size_t)1) + X.n + 16;
+    a.state_stride = (int64_t)X.E + Z.E + ((cp ? 2 : 3) + (a.iter_logits.ptr ? 2 : 0)) * (int64_t)pad4(X.n);
     CK(cudaMallocAsync(&a.state, sizeof(float) * (size_t)grid * a.state_stride, ctx->stream));
     int rc;
     if (cp) {

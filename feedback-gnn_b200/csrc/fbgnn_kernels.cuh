@@ -365,6 +365,35 @@ __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, f
         mz[v * DV + k] = FB_SUB(num_hz, logaddexp_sat<MATH>(-FB_SUB(lx, az[k]), -FB_SUB(ly, az[k])));
 }
 
+// ------------------------------------------------------------------ bulk-async staging --
+// TMA 1-D bulk copies (cp.async.bulk, SASS UBLKCP): one thread posts the transfers against an mbarrier, nobody spends
+// load / store instructions on them.  Source, destination and size must be multiples of 16 bytes.
+__device__ __forceinline__ uint32_t bulk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_mbar_init(uint64_t *bar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(bulk_smem_u32(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_expect(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bulk_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    constexpr uint32_t CHUNK = 32768;
+    for (uint32_t off = 0; off < bytes; off += CHUNK)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     :: "r"(bulk_smem_u32(dst) + off), "l"(reinterpret_cast<const char *>(src) + off),
+                        "r"(min(CHUNK, bytes - off)), "r"(bulk_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bulk_smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
+__host__ __device__ inline int pad16(int x) { return (x + 15) & ~15; }
+
 // ------------------------------------------------------------------ quaternary BP -----
 struct Bp4Args {
     SideDev X, Z;
@@ -374,6 +403,11 @@ struct Bp4Args {
     View3<const float> llr;             // (b, k, v); ptr == nullptr -> constant prior
     float prior;
     View2<const uint8_t> sx, sz;        // (c, b)
+    // pipeline workspace layout (optional, set together with llr / sx / sz): frame b's priors are the contiguous block
+    // llr_bulk + b * 3 * pad4(n) ([3][pad4(n)] floats) and its syndrome bytes synd_bulk + b * pad16(m_x + m_z) -- both 16-byte
+    // aligned, so the prologue stages them with bulk-async (TMA) copies instead of per-element loads
+    const float *llr_bulk;
+    const uint8_t *synd_bulk;
     View2<float> Lx, Ly, Lz;            // (b, v)   optional
     View2<uint8_t> xh, zh;              // (b, v)   optional (layer mode)
     View2<float> xl, zl;                // (row, b) optional: x_logit over hz rows, z_logit over hx rows
@@ -412,9 +446,10 @@ __device__ void bp4_iter_logits(const Bp4Args &a, const float *mx, const float *
         float Sx = 0.0f, Sz = 0.0f;
         for (int e = X.vn_ptr[v]; e < X.vn_ptr[v + 1]; e++) Sx = FB_ADD(Sx, mx[e]);
         for (int e = Z.vn_ptr[v]; e < Z.vn_ptr[v + 1]; e++) Sz = FB_ADD(Sz, mz[e]);
+        const int np = pad4(n);
         const float px = CONST_PRIOR ? a.prior : pri[v];
-        const float py = CONST_PRIOR ? a.prior : pri[n + v];
-        const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
+        const float py = CONST_PRIOR ? a.prior : pri[np + v];
+        const float pz = CONST_PRIOR ? a.prior : pri[2 * np + v];
         const float ly = FB_ADD(FB_ADD(Sz, Sx), py);
         const float lx = FB_ADD(Sz, px);
         const float lz = FB_ADD(Sx, pz);
@@ -465,27 +500,51 @@ __device__ void bp4_iter_logits(const Bp4Args &a, const float *mx, const float *
     __syncthreads();
 }
 
-// One CTA decodes one frame.  Dynamic shared memory:
-//   float msg_x[E_x], msg_z[E_z], pri[CONST_PRIOR ? 2n : 3n], (scr[2n] if iter_logits);  u16 rec[n];
-//   u8 sbx[m_x], sbz[m_z], dec[n]
+// One CTA decodes one frame.  Dynamic shared memory (np = pad4(n), mp = pad16(m_x + m_z); every float block starts on a
+// 16-byte boundary so the per-frame inputs can arrive by bulk-async copies):
+//   float pri[(CONST_PRIOR ? 2 : 3) * np];  u8 sb[mp] (sbx then sbz);  float msg_x[E_x], msg_z[E_z], (scr[2 np] if
+//   iter_logits);  u16 rec[n];  u8 dec[n]
 // GSTATE (codes whose state exceeds the 227 KB of an SM): the float arrays live in the CTA's slice of an HBM
 // scratch buffer (L2-resident while the CTA runs) instead; same code, same arithmetic, same results.
 template <bool CONST_PRIOR, int DV, int DC, typename MATH, bool FPX, bool GSTATE = false>
 static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(8) uint64_t load_bar;
     const SideDev &X = a.X, &Z = a.Z;
     const int n = X.n, T = blockDim.x, tid = threadIdx.x;
+    const int np = pad4(n), mp = pad16(X.m + Z.m), PRI = (CONST_PRIOR ? 2 : 3) * np;
     const int64_t b = a.frame_list ? a.frame_list[blockIdx.x] : blockIdx.x;
-    float *mx = GSTATE ? a.state + (int64_t)blockIdx.x * a.state_stride : smem;
-    float *mz = mx + X.E, *pri = mz + Z.E, *scr2 = pri + (CONST_PRIOR ? 2 : 3) * n;
-    uint16_t *rec = GSTATE ? (uint16_t *)smem : (uint16_t *)(scr2 + (a.iter_logits.ptr ? 2 * n : 0));
-    uint8_t *sbx = (uint8_t *)(rec + ((n + 1) & ~1)), *sbz = sbx + X.m, *dec = sbz + Z.m;
+    float *gs = GSTATE ? a.state + (int64_t)blockIdx.x * a.state_stride : nullptr;
+    float *pri = GSTATE ? gs : smem;
+    uint8_t *sbx = GSTATE ? (uint8_t *)smem : (uint8_t *)(smem + PRI), *sbz = sbx + X.m;
+    float *mx = GSTATE ? gs + PRI : (float *)(sbx + mp);
+    float *mz = mx + X.E, *scr2 = mz + Z.E;
+    uint16_t *rec = GSTATE ? (uint16_t *)(sbx + mp) : (uint16_t *)(scr2 + (a.iter_logits.ptr ? 2 * np : 0));
+    uint8_t *dec = (uint8_t *)(rec + ((n + 1) & ~1));
 
+    // per-frame inputs: the pipeline's workspace rows are 16-byte aligned blocks -> two bulk-async (TMA) copies posted by one
+    // thread, overlapped with the clearing of the messages; the layer API's strided views are read element by element
+    const bool bulk_pri = !GSTATE && !CONST_PRIOR && a.llr_bulk != nullptr;
+    const bool bulk_syn = !GSTATE && a.synd_bulk != nullptr;
+    if (bulk_pri || bulk_syn) {
+        if (tid == 0) bulk_mbar_init(&load_bar);
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bytes = (bulk_pri ? (uint32_t)PRI * 4u : 0u) + (bulk_syn ? (uint32_t)mp : 0u);
+            bulk_expect(&load_bar, bytes);
+            if (bulk_pri) bulk_g2s(pri, a.llr_bulk + b * PRI, (uint32_t)PRI * 4u, &load_bar);
+            if (bulk_syn) bulk_g2s(sbx, a.synd_bulk + b * mp, (uint32_t)mp, &load_bar);
+        }
+    }
     for (int e = tid; e < X.E + Z.E; e += T) mx[e] = 0.0f;
-    if (!CONST_PRIOR)
-        for (int i = tid; i < 3 * n; i += T) pri[i] = a.llr(b, i / n, i % n);
-    for (int c = tid; c < X.m; c += T) sbx[c] = a.sx(c, b);
-    for (int c = tid; c < Z.m; c += T) sbz[c] = a.sz(c, b);
+    if (!CONST_PRIOR && !bulk_pri)
+        for (int k = 0; k < 3; k++)
+            for (int v = tid; v < n; v += T) pri[k * np + v] = a.llr(b, k, v);
+    if (!bulk_syn) {
+        for (int c = tid; c < X.m; c += T) sbx[c] = a.sx(c, b);
+        for (int c = tid; c < Z.m; c += T) sbz[c] = a.sz(c, b);
+    }
+    if (bulk_pri || bulk_syn) bulk_wait(&load_bar, 0);
     __syncthreads();
 
     const bool fast = DV > 0 && a.cn_type == 0;     // regular graph + boxplus-phi: unrolled path
@@ -501,8 +560,8 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         // variable nodes (decoding_q.py:227-275)
         for (int v = tid; v < n; v += T) {
             const float px = CONST_PRIOR ? a.prior : pri[v];
-            const float py = CONST_PRIOR ? a.prior : pri[n + v];
-            const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
+            const float py = CONST_PRIOR ? a.prior : pri[np + v];
+            const float pz = CONST_PRIOR ? a.prior : pri[2 * np + v];
             if (DV > 0) {
                 vn_update_regular<(DV > 0 ? DV : 1), MATH, FPX>(v, mx, mz, px, py, pz, recp, sat_bits);
                 continue;
@@ -552,8 +611,8 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
                 for (int e = X.vn_ptr[v]; e < X.vn_ptr[v + 1]; e++) Sx = FB_ADD(Sx, mx[e]);
                 for (int e = Z.vn_ptr[v]; e < Z.vn_ptr[v + 1]; e++) Sz = FB_ADD(Sz, mz[e]);
                 const float px = CONST_PRIOR ? a.prior : pri[v];
-                const float py = CONST_PRIOR ? a.prior : pri[n + v];
-                const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
+                const float py = CONST_PRIOR ? a.prior : pri[np + v];
+                const float pz = CONST_PRIOR ? a.prior : pri[2 * np + v];
                 const float ly = FB_ADD(FB_ADD(Sz, Sx), py), lx = FB_ADD(Sz, px), lz = FB_ADD(Sx, pz);
                 int d = 0;
                 float best = 0.0f;
@@ -593,8 +652,8 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         for (int e = X.vn_ptr[v]; e < X.vn_ptr[v + 1]; e++) Sx = FB_ADD(Sx, mx[e]);
         for (int e = Z.vn_ptr[v]; e < Z.vn_ptr[v + 1]; e++) Sz = FB_ADD(Sz, mz[e]);
         const float px = CONST_PRIOR ? a.prior : pri[v];
-        const float py = CONST_PRIOR ? a.prior : pri[n + v];
-        const float pz = CONST_PRIOR ? a.prior : pri[2 * n + v];
+        const float py = CONST_PRIOR ? a.prior : pri[np + v];
+        const float pz = CONST_PRIOR ? a.prior : pri[2 * np + v];
         const float ly = FB_ADD(FB_ADD(Sz, Sx), py);
         const float lx = FB_ADD(Sz, px);
         const float lz = FB_ADD(Sx, pz);
@@ -612,7 +671,7 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
             d |= (llr_xp < 0.0f) << 2;
             d |= (llr_zp < 0.0f) << 3;
             pri[v] = MATH::phi4(fabsf(llr_xp));
-            pri[n + v] = MATH::phi4(fabsf(llr_zp));
+            pri[np + v] = MATH::phi4(fabsf(llr_zp));
         }
         dec[v] = (uint8_t)d;
     }
@@ -624,7 +683,7 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         const bool isx = c < X.m;                       // hx row: z_logit from llr_z', checks z_hat
         const SideDev &S = isx ? X : Z;
         const int cc = isx ? c : c - X.m;
-        const float *scr = isx ? pri + n : pri;
+        const float *scr = isx ? pri + np : pri;
         const int sbit = isx ? 3 : 2, dbit = isx ? 1 : 0;
         int par = 0, dpar = 0;
         float Tsum = 0.0f;
@@ -649,7 +708,7 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
             const int cc = isz ? c - a.rows_x_m : c;
             const int *ptr = isz ? a.rows_z_ptr : a.rows_x_ptr;
             const idx_t *col = isz ? a.rows_z_col : a.rows_x_col;
-            const float *scr = isz ? pri + n : pri;
+            const float *scr = isz ? pri + np : pri;
             int par = 0;
             float Tsum = 0.0f;
             for (int k = ptr[cc]; k < ptr[cc + 1]; k++) {
@@ -1756,8 +1815,11 @@ struct SampleArgs {
     float thr0, thr1, thr2;             // Pauli thresholds, or thr0 = p for BSC
     uint64_t seed, first_frame;
     View2<const uint8_t> nx_in, nz_in;  // optional given noise (b, v)
+    const uint32_t *nx_words, *nz_words;   // optional given noise as packed bit-planes [B][wq]: qubit v = bit (v & 31) of word v >> 5
+    int wq;                             // row stride of the packed planes in words
     uint8_t *vbits;                     // [B][n] out: bit0 noise_x (or BSC noise), bit1 noise_z
-    uint8_t *sbits;                     // [B][m_x+m_z] out (may be nullptr)
+    uint8_t *sbits;                     // [B][sb_stride] out (may be nullptr): syndrome_x then syndrome_z of the frame
+    int sb_stride;                      // row stride in bytes (pad16(m_x + m_z) in the pipelines' workspace)
     View2<uint8_t> nx_out, nz_out;      // optional separate outputs (Pauli / BSC layer API)
 };
 
@@ -1773,7 +1835,11 @@ static __global__ void k_sample(const SampleArgs a) {
     const int n = a.X.n, T = blockDim.x, tid = threadIdx.x;
     const int64_t b = blockIdx.x;
     const uint64_t frame = a.first_frame + (uint64_t)b;
-    if (a.nx_in.ptr) {
+    if (a.nx_words) {                   // packed planes: coalesced 32-bit loads, 32 qubits per word
+        const uint32_t *wx = a.nx_words + b * a.wq, *wz = a.nz_words ? a.nz_words + b * a.wq : nullptr;
+        for (int v = tid; v < n; v += T)
+            nb[v] = (uint8_t)(((wx[v >> 5] >> (v & 31)) & 1u) | (wz ? (((wz[v >> 5] >> (v & 31)) & 1u) << 1) : 0u));
+    } else if (a.nx_in.ptr) {
         for (int v = tid; v < n; v += T)
             nb[v] = (a.nx_in(b, v) ? 1 : 0) | ((a.nz_in.ptr && a.nz_in(b, v)) ? 2 : 0);
     } else if (a.mode == 2) {
@@ -1814,7 +1880,7 @@ static __global__ void k_sample(const SampleArgs a) {
     if (a.nx_out.ptr) for (int v = tid; v < n; v += T) a.nx_out(b, v) = nb[v] & 1;
     if (a.nz_out.ptr) for (int v = tid; v < n; v += T) a.nz_out(b, v) = (nb[v] >> 1) & 1;
     if (a.sbits) {
-        uint8_t *sb = a.sbits + b * (a.X.m + a.Z.m);
+        uint8_t *sb = a.sbits + b * a.sb_stride;
         for (int c = tid; c < a.X.m + a.Z.m; c += T) {
             const bool isx = c < a.X.m;                  // syndrome_x = hx . noise_z (bit1);
             const SideDev &S = isx ? a.X : a.Z;          // syndrome_z = hz . noise_x (bit0)
@@ -1974,7 +2040,8 @@ struct OsdLlrArgs {
     const int *frame_list;
     int64_t num_frames;
     const float *L;                     // [B][3][n]
-    float *out;                         // [B][3][n] (planes 0, 1 written)
+    float *out;                         // [B][3][np] (planes 0, 1 written)
+    int np;                             // plane stride of out (pad4(n) in the pipelines' workspace)
 };
 template <typename MATH>
 static __global__ void k_osd_llr(const OsdLlrArgs a) {
@@ -1985,8 +2052,8 @@ static __global__ void k_osd_llr(const OsdLlrArgs a) {
         const int64_t b = a.frame_list ? a.frame_list[fi] : fi;
         const float *L = a.L + b * 3 * a.n;
         const float lx = L[v], ly = L[a.n + v], lz = L[2 * a.n + v];
-        a.out[b * 3 * a.n + a.n + v] = FB_SUB(MATH::softplus(-lx), MATH::logaddexp(-lz, -ly));
-        a.out[b * 3 * a.n + v] = FB_SUB(MATH::softplus(-lz), MATH::logaddexp(-lx, -ly));
+        a.out[b * 3 * a.np + a.np + v] = FB_SUB(MATH::softplus(-lx), MATH::logaddexp(-lz, -ly));
+        a.out[b * 3 * a.np + v] = FB_SUB(MATH::softplus(-lz), MATH::logaddexp(-lx, -ly));
     }
 }
 
@@ -2001,6 +2068,12 @@ struct FinalArgs {
     uint8_t *flags;                     // [B] or nullptr
     View2<uint8_t> x_diff, z_diff;      // optional (b, v)
     unsigned long long *counters;       // [4] device: frames, flagged, block, stage-0 failures
+    // packed outputs (optional): per-frame indicator planes [3][fw] (flagged, block error, failed stage 0; frame b = bit b & 31
+    // of word b >> 5; cleared by the caller) and the residual errors as bit-planes [B][wq]
+    uint32_t *frame_bits;
+    int64_t fw;
+    uint32_t *xd_words, *zd_words;
+    int wq;
 };
 
 // smem: u8 d[n]; u32 xw[W], zw[W]
@@ -2025,6 +2098,8 @@ static __global__ void k_final(const FinalArgs a) {
         if ((tid & 31) == 0) { xw[v >> 5] = bx; zw[v >> 5] = bz; }
     }
     __syncthreads();
+    if (a.xd_words) for (int wi = tid; wi < W; wi += T) a.xd_words[b * a.wq + wi] = xw[wi];
+    if (a.zd_words) for (int wi = tid; wi < W; wi += T) a.zd_words[b * a.wq + wi] = zw[wi];
     int flagged = 0;
     for (int c = tid; c < a.X.m + a.Z.m; c += T) {
         const bool isx = c < a.X.m;                      // hx checks z_diff (quaternary) / the noise (binary)
@@ -2054,6 +2129,12 @@ static __global__ void k_final(const FinalArgs a) {
         const int blk = a.binary ? (a.kx > 0 ? logical : flagged) : (flagged | logical);
         const int rnd = a.rounds ? a.rounds[b] : 0;
         if (a.flags) a.flags[b] = (uint8_t)((flagged ? 1 : 0) | (blk ? 2 : 0) | (rnd << 2));
+        if (a.frame_bits) {
+            const uint32_t bit = 1u << (b & 31);
+            if (flagged) atomicOr(a.frame_bits + (b >> 5), bit);
+            if (blk) atomicOr(a.frame_bits + a.fw + (b >> 5), bit);
+            if (rnd > 0) atomicOr(a.frame_bits + 2 * a.fw + (b >> 5), bit);
+        }
         if (a.counters) {
             atomicAdd(a.counters + 0, 1ull);
             if (flagged) atomicAdd(a.counters + 1, 1ull);

@@ -39,13 +39,13 @@ static int ws_reserve(fbgnn_ctx *ctx, int64_t B, int n, int m) {
     ws_free(w);
     const size_t b = (size_t)B;
     CK(cudaMalloc(&w.vbits, b * n));
-    CK(cudaMalloc(&w.sbits, b * std::max(m, 1)));
+    CK(cudaMalloc(&w.sbits, b * (size_t)pad16(std::max(m, 1))));          // rows padded to 16 bytes (bulk-async staging)
     CK(cudaMalloc(&w.active[0], b));
     CK(cudaMalloc(&w.active[1], b));
     CK(cudaMalloc(&w.rounds, b));
     CK(cudaMalloc(&w.iters, b));
     CK(cudaMalloc(&w.L, b * 3 * n * sizeof(float)));
-    CK(cudaMalloc(&w.P, b * 3 * n * sizeof(float)));
+    CK(cudaMalloc(&w.P, b * 3 * (size_t)pad4(n) * sizeof(float)));        // [B][3][pad4(n)]: 16-byte aligned frame blocks
     CK(cudaMalloc(&w.logit, b * std::max(m, 1) * sizeof(float)));
     CK(cudaMalloc(&w.list[0], b * sizeof(int)));
     CK(cudaMalloc(&w.list[1], b * sizeof(int)));
@@ -55,9 +55,38 @@ static int ws_reserve(fbgnn_ctx *ctx, int64_t B, int n, int m) {
     return 0;
 }
 
+struct PackedIO {                   // packed bit-plane variants of the pipeline's inputs / outputs (fbgnn_pipeline_run_bits)
+    const uint32_t *nx_words = nullptr, *nz_words = nullptr;
+    uint32_t *frame_bits = nullptr, *xd_words = nullptr, *zd_words = nullptr;
+};
+
+static int pipeline_run_impl(fbgnn_code *code, const fbgnn_pipeline_cfg *cfg, uint64_t seed,
+                             uint64_t first_frame, int64_t B, fbgnn_tensor2 noise_x, fbgnn_tensor2 noise_z,
+                             uint8_t *flags, fbgnn_tensor2 x_diff, fbgnn_tensor2 z_diff, int64_t *counters,
+                             const PackedIO &pk);
+
 extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cfg, uint64_t seed,
                                   uint64_t first_frame, int64_t B, fbgnn_tensor2 noise_x, fbgnn_tensor2 noise_z,
                                   uint8_t *flags, fbgnn_tensor2 x_diff, fbgnn_tensor2 z_diff, int64_t *counters) {
+    return pipeline_run_impl(code, cfg, seed, first_frame, B, noise_x, noise_z, flags, x_diff, z_diff, counters, PackedIO());
+}
+
+extern "C" int fbgnn_pipeline_run_bits(fbgnn_code *code, const fbgnn_pipeline_cfg *cfg, uint64_t seed,
+                                       uint64_t first_frame, int64_t B, const uint32_t *noise_x_bits,
+                                       const uint32_t *noise_z_bits, uint32_t *frame_bits, uint32_t *x_diff_bits,
+                                       uint32_t *z_diff_bits, int64_t *counters) {
+    REQUIRE((noise_x_bits == nullptr) == (noise_z_bits == nullptr), "give both noise planes or neither");
+    PackedIO pk;
+    pk.nx_words = noise_x_bits; pk.nz_words = noise_z_bits;
+    pk.frame_bits = frame_bits; pk.xd_words = x_diff_bits; pk.zd_words = z_diff_bits;
+    const fbgnn_tensor2 none = {nullptr, 0, 0};
+    return pipeline_run_impl(code, cfg, seed, first_frame, B, none, none, nullptr, none, none, counters, pk);
+}
+
+static int pipeline_run_impl(fbgnn_code *code, const fbgnn_pipeline_cfg *cfg, uint64_t seed,
+                             uint64_t first_frame, int64_t B, fbgnn_tensor2 noise_x, fbgnn_tensor2 noise_z,
+                             uint8_t *flags, fbgnn_tensor2 x_diff, fbgnn_tensor2 z_diff, int64_t *counters,
+                             const PackedIO &pk) {
     REQUIRE(code && cfg, "NULL argument");
     REQUIRE(cfg->num_stages >= 1 && cfg->num_iter && cfg->factor && cfg->cn_type, "bad pipeline configuration");
     REQUIRE(cfg->num_stages == 1 || cfg->gnn, "feedback GNNs missing");
@@ -90,7 +119,10 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
     sa.thr0 = cfg->thr[0]; sa.thr1 = cfg->thr[1]; sa.thr2 = cfg->thr[2];
     sa.seed = seed; sa.first_frame = first_frame;
     sa.nx_in = v2<const uint8_t>(noise_x); sa.nz_in = v2<const uint8_t>(noise_z);
-    sa.vbits = w.vbits; sa.sbits = w.sbits;
+    const int wq = pad4((n + 31) / 32);                  // words per packed qubit plane (rows 16-byte aligned)
+    sa.nx_words = pk.nx_words; sa.nz_words = pk.nz_words; sa.wq = wq;
+    const int np = pad4(n), mp = pad16(m);
+    sa.vbits = w.vbits; sa.sbits = w.sbits; sa.sb_stride = mp;
     k_sample<<<(unsigned)B, 128, (size_t)3 * n + 8, st>>>(sa);
     CK(cudaGetLastError());
     ctx->launches++;
@@ -108,19 +140,20 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
             ga.h_vn = View3<const float>{w.L, 3 * (int64_t)n, 1, n};
             ga.logit_hx = View2<const float>{w.logit, 1, m};           // z_logit: rows of hx
             ga.logit_hz = View2<const float>{w.logit + X.m, 1, m};     // x_logit: rows of hz
-            ga.sx = View2<const uint8_t>{w.sbits, 1, m};
-            ga.sz = View2<const uint8_t>{w.sbits + X.m, 1, m};
-            ga.out = View3<float>{w.P, 3 * (int64_t)n, 1, n};
+            ga.sx = View2<const uint8_t>{w.sbits, 1, mp};
+            ga.sz = View2<const uint8_t>{w.sbits + X.m, 1, mp};
+            ga.out = View3<float>{w.P, 3 * (int64_t)np, 1, np};
             if (int rc = launch_gnn(ctx, cfg->gnn[s - 1], ga)) return rc;
         }
         Bp4Args a{};
         a.X = X; a.Z = Z;
         a.cn_type = cfg->cn_type[s]; a.num_iter = cfg->num_iter[s]; a.factor = cfg->factor[s];
         a.frame_list = cur_list;
-        if (s > 0) a.llr = View3<const float>{w.P, 3 * (int64_t)n, n, 1};
+        if (s > 0) { a.llr = View3<const float>{w.P, 3 * (int64_t)np, np, 1}; a.llr_bulk = w.P; }
         a.prior = cfg->prior;
-        a.sx = View2<const uint8_t>{w.sbits, 1, m};
-        a.sz = View2<const uint8_t>{w.sbits + X.m, 1, m};
+        a.sx = View2<const uint8_t>{w.sbits, 1, mp};
+        a.sz = View2<const uint8_t>{w.sbits + X.m, 1, mp};
+        a.synd_bulk = w.sbits;
         if (!last || cfg->osd0) {
             a.Lx = View2<float>{w.L, 3 * (int64_t)n, 1};
             a.Ly = View2<float>{w.L + n, 3 * (int64_t)n, 1};
@@ -154,7 +187,7 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
 
     if (cfg->osd0 && cur_count > 0 && cur_list) {
         // BP4_OSD_Model (bp_osd.py:80-197): frames still mismatching get both parts re-solved by OSD-0
-        OsdLlrArgs la{n, cur_list, cur_count, w.L, w.P};
+        OsdLlrArgs la{n, cur_list, cur_count, w.L, w.P, np};
         const int64_t blocks = std::min<int64_t>((cur_count * n + 255) / 256, (int64_t)ctx->num_sms * 8);
         if (ctx->math_mode == FBGNN_MATH_SFU) k_osd_llr<MathSfu><<<(unsigned)blocks, 256, 0, st>>>(la);
         else k_osd_llr<MathExact><<<(unsigned)blocks, 256, 0, st>>>(la);
@@ -164,12 +197,12 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
         oa.frame_list = cur_list; oa.sign = 1.0f;
         oa.vbits = w.vbits;
         oa.S = code->basis_x->dev;                                   // hx basis, osd_llrz, syndrome_x -> z_hat
-        oa.llr = View2<const float>{w.P + n, 3 * (int64_t)n, 1};
-        oa.synd = View2<const uint8_t>{w.sbits, 1, m}; oa.synd_row = code->pivot_x; oa.vbit = 3;
+        oa.llr = View2<const float>{w.P + np, 3 * (int64_t)np, 1};
+        oa.synd = View2<const uint8_t>{w.sbits, 1, mp}; oa.synd_row = code->pivot_x; oa.vbit = 3;
         if (int rc = launch_osd0(ctx, oa, cur_count)) return rc;
         oa.S = code->basis_z->dev;                                   // hz basis, osd_llrx, syndrome_z -> x_hat
-        oa.llr = View2<const float>{w.P, 3 * (int64_t)n, 1};
-        oa.synd = View2<const uint8_t>{w.sbits + X.m, 1, m}; oa.synd_row = code->pivot_z; oa.vbit = 2;
+        oa.llr = View2<const float>{w.P, 3 * (int64_t)np, 1};
+        oa.synd = View2<const uint8_t>{w.sbits + X.m, 1, mp}; oa.synd_row = code->pivot_z; oa.vbit = 2;
         if (int rc = launch_osd0(ctx, oa, cur_count)) return rc;
     }
 
@@ -180,6 +213,11 @@ extern "C" int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cf
     fa.vbits = w.vbits; fa.rounds = w.rounds; fa.flags = flags;
     fa.x_diff = v2<uint8_t>(x_diff); fa.z_diff = v2<uint8_t>(z_diff);
     fa.counters = w.counters;
+    if (pk.frame_bits) {
+        fa.frame_bits = pk.frame_bits; fa.fw = (B + 31) / 32;
+        CK(cudaMemsetAsync(pk.frame_bits, 0, sizeof(uint32_t) * 3 * (size_t)fa.fw, st));
+    }
+    fa.xd_words = pk.xd_words; fa.zd_words = pk.zd_words; fa.wq = wq;
     const int W = (n + 31) / 32;
     k_final<<<(unsigned)B, 128, (size_t)((n + 3) & ~3) + 8 * (size_t)W, st>>>(fa);
     CK(cudaGetLastError());
@@ -219,14 +257,15 @@ extern "C" int fbgnn_bsc_pipeline_run(fbgnn_graph *g, fbgnn_graph *logical, int3
     sa.X = S; sa.mode = 1; sa.thr0 = p;
     sa.seed = seed; sa.first_frame = first_frame;
     sa.nx_in = v2<const uint8_t>(noise);
-    sa.vbits = w.vbits; sa.sbits = w.sbits;
+    const int mp = pad16(m);
+    sa.vbits = w.vbits; sa.sbits = w.sbits; sa.sb_stride = mp;
     k_sample<<<(unsigned)B, 128, (size_t)n, st>>>(sa);
     CK(cudaGetLastError());
     ctx->launches++;
     Bp2Args a{};
     a.S = S; a.cn_type = cn_type; a.num_iter = num_iter; a.factor = factor;
     a.llr_const = llr_const;
-    a.synd = View2<const uint8_t>{w.sbits, 1, m};
+    a.synd = View2<const uint8_t>{w.sbits, 1, mp};
     a.vbits = w.vbits;                 // decision -> bit 2
     if (osd_basis) {
         CK(cudaMemsetAsync(w.list_count, 0, sizeof(int), st));
@@ -253,7 +292,7 @@ extern "C" int fbgnn_bsc_pipeline_run(fbgnn_graph *g, fbgnn_graph *logical, int3
             Osd0Args oa{};
             oa.S = osd_basis->dev; oa.frame_list = w.list[0];
             oa.llr = View2<const float>{w.L, n, 1}; oa.sign = -1.0f;      // llr_hat = -decoder output
-            oa.synd = View2<const uint8_t>{w.sbits, 1, m}; oa.synd_row = dp;
+            oa.synd = View2<const uint8_t>{w.sbits, 1, mp}; oa.synd_row = dp;
             oa.vbits = w.vbits; oa.vbit = 2;
             if (int rc = launch_osd0(ctx, oa, cnt)) return rc;
             CK(cudaStreamSynchronize(st));                                  // piv must outlive the copy

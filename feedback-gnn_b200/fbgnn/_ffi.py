@@ -111,6 +111,8 @@ _SIGNATURES = {
                          Tensor2],
     "fbgnn_pipeline_run": [C.c_void_p, C.POINTER(PipelineCfg), C.c_uint64, C.c_uint64, C.c_int64, Tensor2,
                            Tensor2, C.c_void_p, Tensor2, Tensor2, C.POINTER(C.c_int64)],
+    "fbgnn_pipeline_run_bits": [C.c_void_p, C.POINTER(PipelineCfg), C.c_uint64, C.c_uint64, C.c_int64, C.c_void_p,
+                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)],
     "fbgnn_bsc_pipeline_run": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_float, C.c_float,
                                C.c_uint64, C.c_uint64, C.c_int64, Tensor2, C.c_void_p, C.POINTER(C.c_int64),
                                C.c_void_p, _i32p],

@@ -186,6 +186,27 @@ class Feedback_GNN:
     call = __call__
 
 
+def packed_words(n):
+    """Words per packed bit-plane row of n bits: ceil(n / 32) rounded up to a multiple of 4 (16-byte rows)."""
+    return (((int(n) + 31) // 32) + 3) & ~3
+
+
+def pack_bits(a):
+    """[B, n] 0/1 array -> uint32 [B, packed_words(n)]: entry v = bit (v & 31) of word v >> 5."""
+    a = np.asarray(a).astype(bool)
+    B, n = a.shape
+    wq = packed_words(n)
+    padded = np.zeros((B, wq * 32), np.uint8)
+    padded[:, :n] = a
+    return np.ascontiguousarray(np.packbits(padded, axis=1, bitorder="little").view("<u4"))
+
+
+def unpack_bits(words, n):
+    """Inverse of ``pack_bits`` (also for the frame planes: unpack_bits(frame_bits, B))."""
+    w = np.ascontiguousarray(np.asarray(words), dtype="<u4")
+    return np.unpackbits(w.view(np.uint8), axis=-1, bitorder="little")[..., :n]
+
+
 class ErrorIndicator:
     """Lazy ``[B, rows]`` 0/1 matrix whose row-wise "any" is already known (see module doc)."""
 
@@ -271,13 +292,10 @@ class Sandwich_BP_GNN_Evaluation_Model:
         p0 = float(p) if self.p0 is None else float(self.p0)
         return np.float32(np.log(np.float64(np.float32(3. * (1. - p0) / p0))))
 
-    def run(self, batch_size, p, noise=None, want_flags=True, want_diff=True, want_counters=False):
-        """Device-level entry.  Returns dict(flags, x_diff, z_diff DeviceArrays, counters ndarray)."""
+    def _cfg(self, ctx, p):
+        """fbgnn_pipeline_cfg of this model at noise level ``p`` (+ the ctypes arrays it points into)."""
         import ctypes as C
-        dev = _ffi.device_code(self.code, self._ctx)
-        ctx = dev.ctx
         S = self.num_layers
-        B = int(batch_size)
         ni = (C.c_int32 * S)(*[d.num_iter for d in self.decoders[:S]])
         fa = (C.c_float * S)(*[d.normalization_factor for d in self.decoders[:S]])
         ct = (C.c_int32 * S)(*[CN_TYPES[d.cn_type] for d in self.decoders[:S]])
@@ -287,6 +305,15 @@ class Sandwich_BP_GNN_Evaluation_Model:
         cfg = _ffi.PipelineCfg(S, ni, fa, ct, gh, float(self.prior(p)), (C.c_float * 3)(*thr),
                                int(round(float(p))) if self.wt else 0, 1 if self.osd0 else 0,
                                1 if self.skip_inactive else 0, 1 if self.early_stop else 0)
+        return cfg, (ni, fa, ct, gh)
+
+    def run(self, batch_size, p, noise=None, want_flags=True, want_diff=True, want_counters=False):
+        """Device-level entry.  Returns dict(flags, x_diff, z_diff DeviceArrays, counters ndarray)."""
+        import ctypes as C
+        dev = _ffi.device_code(self.code, self._ctx)
+        ctx = dev.ctx
+        B = int(batch_size)
+        cfg, keepalive = self._cfg(ctx, p)
         nx = nz = _ffi.NULL2
         keep = None
         if noise is not None:
@@ -305,6 +332,36 @@ class Sandwich_BP_GNN_Evaluation_Model:
         if noise is None:
             self.next_frame += B
         res = dict(flags=flags, x_diff=xd, z_diff=zd,
+                   counters=np.array(list(counters), np.int64) if want_counters else None)
+        self.last_counters = res["counters"]
+        return res
+
+    def run_bits(self, batch_size, p, noise_bits=None, want_frame_bits=True, want_diff=False, want_counters=False):
+        """Packed-bitmask entry (fbgnn_pipeline_run_bits): what a Monte-Carlo host loop exchanges with the GPU is 32 qubits /
+        32 frames per word.  ``noise_bits``: optional pair of uint32 [B, wq] arrays (host or device; ``pack_bits``), qubit v of
+        frame b = bit (v & 31) of word [b, v >> 5].  Returns dict(frame_bits uint32 [3, ceil(B/32)] device: planes flagged /
+        block error / failed stage 0; x_diff_bits, z_diff_bits uint32 [B, wq]; counters)."""
+        import ctypes as C
+        dev = _ffi.device_code(self.code, self._ctx)
+        ctx = dev.ctx
+        B = int(batch_size)
+        cfg, keepalive = self._cfg(ctx, p)
+        wq = packed_words(dev.n)
+        nx = nz = None
+        if noise_bits is not None:
+            nx, nz = (ctx.asarray(a, np.uint32) for a in noise_bits)
+            if nx.shape != (B, wq) or nz.shape != (B, wq):
+                raise ValueError(f"packed noise planes must have shape [{B},{wq}], got {nx.shape} / {nz.shape}")
+        fb = ctx.empty((3, (B + 31) // 32), np.uint32) if want_frame_bits else None
+        xd = ctx.empty((B, wq), np.uint32) if want_diff else None
+        zd = ctx.empty((B, wq), np.uint32) if want_diff else None
+        counters = (C.c_int64 * 4)() if want_counters else None
+        ptr = lambda a: a.ptr if a is not None else None
+        _ffi.call("fbgnn_pipeline_run_bits", dev.handle, C.byref(cfg), self.seed, self.next_frame, B, ptr(nx), ptr(nz),
+                  ptr(fb), ptr(xd), ptr(zd), counters)
+        if noise_bits is None:
+            self.next_frame += B
+        res = dict(frame_bits=fb, x_diff_bits=xd, z_diff_bits=zd,
                    counters=np.array(list(counters), np.int64) if want_counters else None)
         self.last_counters = res["counters"]
         return res

@@ -320,6 +320,17 @@ int fbgnn_pipeline_run(fbgnn_code *code, const fbgnn_pipeline_cfg *cfg, uint64_t
                        fbgnn_tensor2 noise_z, uint8_t *flags, fbgnn_tensor2 x_diff,
                        fbgnn_tensor2 z_diff, int64_t *counters);
 
+/* The same pipeline with PACKED inputs and outputs (32 qubits / 32 frames per word; what a Monte-Carlo host loop needs
+ * is 8x smaller than byte arrays and the loads / stores are whole words):
+ *   noise_x_bits / noise_z_bits  optional uint32 [B][wq] device, wq = (ceil(n / 32) rounded up to 4): qubit v of frame b is
+ *                    bit (v & 31) of word [b][v >> 5]; NULL = sample in-kernel
+ *   frame_bits       optional uint32 [3][ceil(B / 32)] device: planes {flagged, block error, failed stage 0}, frame b is
+ *                    bit (b & 31) of word b >> 5
+ *   x_diff_bits / z_diff_bits  optional uint32 [B][wq] device: residual error after correction, packed like the noise */
+int fbgnn_pipeline_run_bits(fbgnn_code *code, const fbgnn_pipeline_cfg *cfg, uint64_t seed, uint64_t first_frame,
+                            int64_t B, const uint32_t *noise_x_bits, const uint32_t *noise_z_bits,
+                            uint32_t *frame_bits, uint32_t *x_diff_bits, uint32_t *z_diff_bits, int64_t *counters);
+
 /* BP_BSC_Model.call: Bernoulli(p) noise, syndrome with `graph`, binary BP from the constant
  * logit llr_const, residual syndrome + logical check against `logical` (block error = any row of
  * `logical` . residual; NULL: block error = flagged).  flags/counters as above.

@@ -240,6 +240,34 @@ def test_pipeline_bitexact(codes, oracle, weights, name, nG, p, B, skip):
     assert model.next_frame == 1000 + B
 
 
+@pytest.mark.parametrize("name,nG", [("c882", 2), ("rsurf3", 0)])
+def test_pipeline_packed_bit_io(codes, oracle, weights, name, nG):
+    """fbgnn_pipeline_run_bits: noise in / indicators and residual errors out as packed bit-planes (32 per word) give
+    exactly what the byte interface gives, for sampled and for given noise."""
+    import fbgnn as F
+    code = codes[name]
+    G = F.Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, use_bias=True)
+    G.set_weights(weights["c882"])
+    d1 = F.QLDPCBPDecoder(code, num_iter=16, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+    mk = lambda: F.Sandwich_BP_GNN_Evaluation_Model(code, [d1] * (nG + 1), [G] * nG, num_layers=nG + 1, seed=6, first_frame=77)
+    B, p = 203, 0.12                                   # a ragged last word of frames
+    a = mk().run(B, p, want_counters=True)
+    b = mk().run_bits(B, p, want_diff=True, want_counters=True)
+    flags = a["flags"].numpy()
+    planes = F.unpack_bits(b["frame_bits"].numpy(), B)
+    assert np.array_equal(planes[0], flags & 1) and np.array_equal(planes[1], (flags >> 1) & 1)
+    assert np.array_equal(planes[2], ((flags >> 2) > 0).astype(np.uint8))
+    assert np.array_equal(F.unpack_bits(b["x_diff_bits"].numpy(), code.N), a["x_diff"].numpy())
+    assert np.array_equal(F.unpack_bits(b["z_diff_bits"].numpy(), code.N), a["z_diff"].numpy())
+    assert a["counters"].tolist() == b["counters"].tolist()
+    nx, nz = oracle.pauli(6, 77, B, code.N, p)
+    assert np.array_equal(F.unpack_bits(F.pack_bits(nx), code.N), nx)
+    c = mk().run_bits(B, p, noise_bits=(F.pack_bits(nx), F.pack_bits(nz)), want_counters=True)
+    assert np.array_equal(c["frame_bits"].numpy(), b["frame_bits"].numpy()) and c["counters"].tolist() == a["counters"].tolist()
+    with pytest.raises(ValueError):
+        mk().run_bits(B, p, noise_bits=(F.pack_bits(nx)[:, :-1], F.pack_bits(nz)[:, :-1]))
+
+
 def test_pipeline_model_outputs_match_reference_matrices(codes, oracle, weights):
     """model(batch_size, p) -> (s_hat, ls_hat): dense matrices as the reference builds them
     (feedback_gnn.py:349-359) and the sim_ber counters."""
