@@ -11,8 +11,8 @@ filled entry by entry.  Two things ride along for the device side:
 * ``code.csr_x`` / ``code.csr_z``: int32 CSR of ``hx`` / ``hz`` (what ``fbgnn_code_create`` takes);
 * ``code.qc``: for quasi-cyclic constructions, the lifted description ``{"l", "x": [(block_row, block_col,
   shift)...], "z": [...]}`` -- every non-zero ``l x l`` block of ``hx`` / ``hz`` is the circulant
-  permutation ``P^shift`` (row ``r`` has its one in column ``(r - shift) mod l``).  ``fbgnn_code_set_qc``
-  checks it against the CSR and keeps it with the device code.
+  permutation ``P^shift`` (row ``r`` has its one in column ``(r - shift) mod l``).  It is host-side metadata (tests rebuild
+  the dense matrices from it); the kernels index through the CSR, see DESIGN.md on SURVEY.md H4.
 
 The GF(2) algebra (kernel, pivots, logical operators) is ``fbgnn.gf2``: bit-packed, same pivot order as
 the reference, hence identical ``hx_perp`` / ``lx`` / ``lz``.

@@ -16,8 +16,12 @@ ap.add_argument("-p", "--p", required=True, help="Physical error rate p to simul
 ap.add_argument("-id", "--gpu_id", default="0", help="GPU id")
 ap.add_argument("--batch_size", type=int, default=5000)
 ap.add_argument("--max_iter", type=int, default=100000)
+ap.add_argument("--math", choices=("exact", "sfu"), default=None,
+                help="arithmetic of the decoders (default: FBGNN_MATH, else exact); both are oracle-exact")
 args = ap.parse_args()
 os.environ["FBGNN_DEVICE"] = str(int(args.gpu_id))
+if args.math:
+    os.environ["FBGNN_MATH"] = args.math
 nG = 5
 
 import fbgnn                                                                                         # noqa: E402
