@@ -215,36 +215,43 @@ FB_HD float fb_atanhf(float x) {
 }
 
 /* ================================================================================================
- * SFU arithmetic (FBGNN_MATH_SFU): the same formulas with exp and log built on the GPU's special-
- * function unit -- MUFU.EX2 (ex2.approx) and MUFU.LG2 (lg2.approx) -- instead of polynomials.
+ * SFU arithmetic (FBGNN_MATH_SFU): exp, log and reciprocal on the GPU's special-function unit -- MUFU.EX2
+ * (ex2.approx), MUFU.LG2 (lg2.approx), MUFU.RCP (rcp.approx) -- with every formula arranged so that the
+ * MUFU inputs fall in finite sets.  The hardware functions are then TABLES: the repository carries them as
+ * measured on a B200 (tests/golden/sfu_b200_*.xz, written by tools/dump_sfu_tables.py), the CPU oracle
+ * looks the values up, and the CUDA kernels stay bit-identical to the oracle in this arithmetic too.
  *
- *   exp(x) : Cody-Waite reduction x = n ln2 + r in FMAs (as fb_expf_core); the argument of the MUFU,
- *            r log2(e), is rounded to a multiple of 2^-23 by adding 1.5 (one FMA), so the MUFU only ever
- *            sees the 2^23 + 8193 float32 values w = u - 1.5 with u in [1 - 2^-12, 2 + 2^-10]; 2^n goes into
- *            the exponent field.
- *   log(x) : exponent split as fb_logf; the MUFU only sees the mantissa m in [sqrt(1/2), sqrt(2)), where
- *            lg2.approx is absolutely accurate to 2^-22.  Arguments known to lie in [1, 2] (the 1 + exp(d), d <= 0,
- *            of logaddexp) skip the split: the table runs on to 2.0, 13 302 542 float32 values in all.
- *   1/q    : MUFU.RCP on q in [1, 2] (2^23 + 1 values), used by tanh = (1 - t) / (1 + t), t = exp(-2|x|).
+ *   2^(x c): n = round(x c) from one FMA against the 1.5 * 2^23 constant, then u = FMA(x, c, 1 - n) is the
+ *            fraction plus one, rounded once: u in [0.5, 1.5], 12 582 913 float32 values.  MUFU.EX2(u) =
+ *            2 * 2^frac, and n - 1 goes into the exponent field.  Five instructions; exp(x) is c = log2(e),
+ *            exp(-x) and exp(-2x) only change the constant.
+ *   log    : of 1 + t, t in [0, 1]: lg2 on [1, 2] directly.  Of 1 - t: every such float32 is a multiple of 2^-24
+ *            in [0, 1], so lg2 sees k 2^-24, k = 1 .. 2^24, directly as well -- no exponent split in either case.
+ *            (General positive arguments -- atanh only -- split off the exponent; mantissa in [sqrt(1/2), sqrt(2)).)
+ *   phi(x) = softplus(x) - log(expm1(x)) with softplus(x) = x + log(1 + t), log(expm1(x)) = x + log(1 - t),
+ *            t = exp(-x); the two terms are rounded separately, as the reference's are.  1 - t is kept >= 2^-23,
+ *            which bounds phi by 24 ln 2 = 16.635532, the reference's phi(8.5e-8).
+ *   softplus(x) = max(x, 0) + log(1 + exp(-|x|));  logaddexp(a, b) = max + log(1 + exp(min - max)).
+ *   tanh(x) = sign(x) (1 - t) / (1 + t), t = exp(-2|x|), MUFU.RCP on [1, 2] (2^23 + 1 values).
  *
- * Because the MUFU inputs are confined to three finite sets, the hardware functions are TABLES: the
- * repository carries them as measured on a B200 (tests/golden/sfu_b200_*.xz, written by
- * tools/dump_sfu_tables.py), the CPU oracle looks the values up, and the CUDA kernels stay bit-identical
- * to the oracle in this arithmetic too.  Accuracy: 2-3 ulp per exp / log instead of 1.  The saturation
- * constants of phi (phi(<= 8.5e-8) = 16.635532, phi(>= 16.635532) = 0: the reference's known answers) and
+ * Accuracy: 2-3 ulp per exp / log instead of 1.  The saturation constants of phi (phi(<= 8.5e-8) = 16.635532,
+ * phi(>= 16.635532) = 0: the reference's known answers), softplus(x < -thr) = exp(x), softplus(x > thr) = x and
  * the rule that a second term below e^-17.5 leaves logaddexp at its larger argument are part of this
  * specification, not consequences of rounding.
  * ================================================================================================ */
-#define FB_SFU_EX2_BASE   0x3F7FF000          /* bits of u for table entry 0:  1 - 2^-12           */
-#define FB_SFU_EX2_COUNT  ((1 << 23) + 8193)  /* entries up to u = 2 + 2^-10 (bits 0x40001000)      */
-#define FB_SFU_LG2_BASE   0x3f3504f3          /* bits of the smallest mantissa, sqrt(1/2)          */
-#define FB_SFU_LG2_COUNT  (0x40000000 - 0x3f3504f3 + 1)   /* up to and including 2.0               */
-#define FB_SFU_RCP_BASE   0x3F800000          /* q = 1.0                                           */
-#define FB_SFU_RCP_COUNT  ((1 << 23) + 1)     /* up to and including 2.0                           */
+#define FB_SFU_EX2_BASE   0x3F000000          /* bits of u for table entry 0: 0.5                          */
+#define FB_SFU_EX2_COUNT  (0x00C00000 + 1)    /* consecutive float32 values up to and including 1.5        */
+#define FB_SFU_LG2_BASE   0x3f3504f3          /* bits of the smallest mantissa, sqrt(1/2)                  */
+#define FB_SFU_LG2_COUNT  (0x40000000 - 0x3f3504f3 + 1)   /* up to and including 2.0                       */
+#define FB_SFU_LG2B_COUNT 11863284            /* k 2^-24 for k = 0 .. ceil(sqrt(1/2) 2^24) (entry 0 unused) */
+#define FB_SFU_RCP_BASE   0x3F800000          /* q = 1.0                                                   */
+#define FB_SFU_RCP_COUNT  ((1 << 23) + 1)     /* up to and including 2.0                                   */
+#define FB_LOG2E          1.44269504088896341f
+#define FB_LN2            0.693147180559945f
 
 #if defined(__CUDA_ARCH__)
-__device__ __forceinline__ float fb_mufu_ex2(float w, float u) {
-    (void)u; float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(w)); return y;
+__device__ __forceinline__ float fb_mufu_ex2(float u) {
+    float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(u)); return y;
 }
 __device__ __forceinline__ float fb_mufu_lg2(float m) {
     float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(m)); return y;
@@ -254,19 +261,25 @@ __device__ __forceinline__ float fb_mufu_rcp(float q) {
 }
 #elif !defined(__CUDACC__)
 /* host: the MUFU as measured on the hardware (tables installed through fb_sfu_set_tables) */
-static const float *fb_sfu_ex2_tab = 0, *fb_sfu_lg2_tab = 0, *fb_sfu_rcp_tab = 0;
-static inline void fb_sfu_set_tables(const float *ex2_tab, const float *lg2_tab, const float *rcp_tab) {
-    fb_sfu_ex2_tab = ex2_tab; fb_sfu_lg2_tab = lg2_tab; fb_sfu_rcp_tab = rcp_tab;
+static const float *fb_sfu_ex2_tab = 0, *fb_sfu_lg2_tab = 0, *fb_sfu_lg2b_tab = 0, *fb_sfu_rcp_tab = 0;
+static inline void fb_sfu_set_tables(const float *ex2_tab, const float *lg2_tab, const float *lg2b_tab,
+                                     const float *rcp_tab) {
+    fb_sfu_ex2_tab = ex2_tab; fb_sfu_lg2_tab = lg2_tab; fb_sfu_lg2b_tab = lg2b_tab; fb_sfu_rcp_tab = rcp_tab;
 }
-static inline float fb_mufu_ex2(float w, float u) {
-    int64_t i = (int64_t)FB_F2I(u) - FB_SFU_EX2_BASE; (void)w;
+static inline float fb_mufu_ex2(float u) {
+    int64_t i = (int64_t)FB_F2I(u) - FB_SFU_EX2_BASE;
     if (i < 0) i = 0;
     if (i >= FB_SFU_EX2_COUNT) i = FB_SFU_EX2_COUNT - 1;
     return fb_sfu_ex2_tab[i];
 }
 static inline float fb_mufu_lg2(float m) {
     int64_t i = (int64_t)FB_F2I(m) - FB_SFU_LG2_BASE;
-    if (i < 0) i = 0;
+    if (i < 0) {                                  /* below sqrt(1/2): the multiples of 2^-24 (1 - t) */
+        int64_t k = (int64_t)(m * 16777216.0f);
+        if (k < 1) k = 1;
+        if (k >= FB_SFU_LG2B_COUNT) k = FB_SFU_LG2B_COUNT - 1;
+        return fb_sfu_lg2b_tab[k];
+    }
     if (i >= FB_SFU_LG2_COUNT) i = FB_SFU_LG2_COUNT - 1;
     return fb_sfu_lg2_tab[i];
 }
@@ -278,49 +291,45 @@ static inline float fb_mufu_rcp(float q) {
 }
 #else
 /* host side of a .cu file: never evaluated (the library has no CPU compute path) */
-static inline float fb_mufu_ex2(float w, float u) { (void)w; (void)u; return 0.0f; }
+static inline float fb_mufu_ex2(float u) { (void)u; return 0.0f; }
 static inline float fb_mufu_lg2(float m) { (void)m; return 0.0f; }
 static inline float fb_mufu_rcp(float q) { (void)q; return 0.0f; }
 #endif
 
-/* exp(x) for -87 <= x <= 88 */
-FB_HD float fb_sfu_expf_core(float x) {
-    const float magic = 12582912.0f;
-    float t = FB_FMA(x, 1.44269504088896341f, magic);
-    float fn = FB_SUB(t, magic);
-    float r = FB_FMA(fn, -0.693359375f, x);
-    r = FB_FMA(fn, 2.12194440e-4f, r);
-    float u = FB_FMA(r, 1.44269504088896341f, 1.5f);          /* r log2(e) on the 2^-23 grid, offset by 1.5 */
-    float y = fb_mufu_ex2(FB_SUB(u, 1.5f), u);
+/* 2^(x c) for -125 <= x c <= 126 */
+FB_HD float fb_sfu_exp2s(float x, float c) {
+    const float magic = 12582912.0f;                          /* 1.5 * 2^23: ulp 1 */
+    float t = FB_FMA(x, c, 12582911.0f);                      /* magic + (n - 1), n = round(x c) */
+    float fn = FB_SUB(t, magic);                              /* n - 1 */
+    float u = FB_FMA(x, c, -fn);                              /* x c - n + 1, one rounding */
+    float y = fb_mufu_ex2(u);
     return FB_I2F(FB_F2I(y) + (int32_t)((uint32_t)FB_F2I(t) << 23));
 }
-FB_HD float fb_sfu_expf(float x) { return fb_sfu_expf_core(FB_FMAX(x, -87.0f)); }
+FB_HD float fb_sfu_expf_core(float x) { return fb_sfu_exp2s(x, FB_LOG2E); }
+FB_HD float fb_sfu_expf(float x) { return fb_sfu_expf_core(FB_FMAX(x, -86.0f)); }
 
-/* log(x) for positive normal x */
+/* log(x) for positive normal x (general argument: exponent split) */
 FB_HD float fb_sfu_logf(float x) {
     int32_t ix = FB_F2I(x);
     int32_t eb = (ix - 0x3f3504f3) & (int32_t)0xff800000;
     float m = FB_I2F(ix - eb);
     float fe = (float)eb;
     float l2 = fb_mufu_lg2(m);
-    return FB_FMA(fe, 0.693147180559945f * 1.1920928955078125e-7f, FB_MUL(l2, 0.693147180559945f));
+    return FB_FMA(fe, FB_LN2 * 1.1920928955078125e-7f, FB_MUL(l2, FB_LN2));
 }
 
-/* log(x) for 1 <= x <= 2: no exponent split */
-FB_HD float fb_sfu_logf_1to2(float x) { return FB_MUL(fb_mufu_lg2(x), 0.693147180559945f); }
-
 FB_HD float fb_sfu_softplusf(float x) {
-    float xc = FB_FMIN(x, FB_SOFTPLUS_THR);
-    float e = fb_sfu_expf(xc);
-    float l = fb_sfu_logf(FB_ADD(1.0f, e));
-    float r = (x < -FB_SOFTPLUS_THR) ? e : l;
+    float ax = FB_FMIN(FB_I2F(FB_F2I(x) & 0x7fffffff), 86.0f);
+    float e = fb_sfu_exp2s(ax, -FB_LOG2E);                    /* exp(-|x|), 0 < e <= 1 */
+    float r = FB_FMA(fb_mufu_lg2(FB_ADD(1.0f, e)), FB_LN2, FB_FMAX(x, 0.0f));
+    r = (x < -FB_SOFTPLUS_THR) ? e : r;
     return (x > FB_SOFTPLUS_THR) ? x : r;
 }
 
 /* log(exp(a) + exp(b)) for mn - mx >= -17.5 (the caller's side of the specification handles the rest) */
 FB_HD float fb_sfu_logaddexp_open(float mx, float d) {
-    float t = fb_sfu_expf_core(d);                       /* 0 < t <= 1 */
-    return FB_ADD(fb_sfu_logf_1to2(FB_ADD(1.0f, t)), mx);
+    float t = fb_sfu_expf_core(d);                            /* 0 < t <= 1 */
+    return FB_FMA(fb_mufu_lg2(FB_ADD(1.0f, t)), FB_LN2, mx);
 }
 FB_HD float fb_sfu_logaddexpf(float a, float b) {
     float mx = FB_FMAX(a, b);
@@ -330,34 +339,37 @@ FB_HD float fb_sfu_logaddexpf(float a, float b) {
     return (d < -17.5f) ? FB_ADD(0.0f, mx) : f;
 }
 
-/* phi on the open interval (8.5e-8, 16.635532).  Never negative: the two logs are one function of ordered
- * arguments, the outer max guards the seam between binades; the inner max keeps log away from zero. */
-FB_HD float fb_sfu_phi4_open(float x) {
-    float e = fb_sfu_expf_core(x);
-    float sp = (x > FB_SOFTPLUS_THR) ? x : fb_sfu_logf(FB_ADD(1.0f, e));
-    float lg = fb_sfu_logf(FB_FMAX(FB_SUB(e, 1.0f), 1.1920928955078125e-7f));
-    return FB_FMAX(FB_SUB(sp, lg), 0.0f);
+/* phi on the open interval (8.5e-8, 16.635532), t = exp(-x):  softplus(x) = x + log(1 + t) and log(expm1(x)) =
+ * x + log(1 - t), each rounded to float32 where the reference rounds them (at the magnitude of x), then subtracted --
+ * the reference's phi with its float32 cancellation for large x reproduced, which the decoder's error rates depend
+ * on (profiles/r02_ler_phi_forms.txt).  Never negative: lg2 >= 0 on [1, 2], <= 0 on (0, 1], and the two FMAs round
+ * monotonically.  FB_SFU_PHI_STABLE (lab) subtracts the logarithms first: the better conditioned log((1+t)/(1-t)). */
+#ifndef FB_SFU_PHI_STABLE
+#define FB_SFU_PHI_STABLE 0
+#endif
+FB_HD float fb_sfu_phi_open(float x) {
+    float t = fb_sfu_exp2s(x, -FB_LOG2E);
+    float la = fb_mufu_lg2(FB_ADD(1.0f, t));
+    float lb = fb_mufu_lg2(FB_FMAX(FB_SUB(1.0f, t), 1.1920928955078125e-7f));
+#if FB_SFU_PHI_STABLE
+    return FB_MUL(FB_SUB(la, lb), FB_LN2);
+#else
+    return FB_SUB(FB_FMA(la, FB_LN2, x), FB_FMA(lb, FB_LN2, x));
+#endif
 }
-FB_HD float fb_sfu_phi2_open(float x) {
-    float e = fb_sfu_expf_core(x);
-    float lg = fb_sfu_logf(FB_FMAX(FB_SUB(e, 1.0f), 1.1920928955078125e-7f));
-    return FB_FMAX(FB_SUB(fb_sfu_logf(FB_ADD(e, 1.0f)), lg), 0.0f);
-}
+FB_HD float fb_sfu_phi4_open(float x) { return fb_sfu_phi_open(x); }
+FB_HD float fb_sfu_phi2_open(float x) { return fb_sfu_phi_open(x); }
 FB_HD float fb_sfu_phi4f(float x) {
-    float f = fb_sfu_phi4_open(FB_FMIN(FB_FMAX(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI));
+    float f = fb_sfu_phi_open(FB_FMIN(FB_FMAX(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI));
     f = (x <= FB_PHI_CLIP_LO) ? FB_PHI_CLIP_HI : f;
     return (x >= FB_PHI_CLIP_HI) ? 0.0f : f;
 }
-FB_HD float fb_sfu_phi2f(float x) {
-    float f = fb_sfu_phi2_open(FB_FMIN(FB_FMAX(x, FB_PHI_CLIP_LO), FB_PHI_CLIP_HI));
-    f = (x <= FB_PHI_CLIP_LO) ? FB_PHI_CLIP_HI : f;
-    return (x >= FB_PHI_CLIP_HI) ? 0.0f : f;
-}
+FB_HD float fb_sfu_phi2f(float x) { return fb_sfu_phi4f(x); }
 
 /* tanh(x) = sign(x) (1 - t) / (1 + t), t = exp(-2 |x|); |x| >= 10 gives exactly 1 */
 FB_HD float fb_sfu_tanhf(float x) {
     float ax = FB_FMIN(FB_I2F(FB_F2I(x) & 0x7fffffff), 10.0f);
-    float t = fb_sfu_expf_core(FB_MUL(ax, -2.0f));
+    float t = fb_sfu_exp2s(ax, -2.0f * FB_LOG2E);
     float r = FB_MUL(FB_SUB(1.0f, t), fb_mufu_rcp(FB_ADD(1.0f, t)));
     return FB_I2F(FB_F2I(r) | (FB_F2I(x) & (int32_t)0x80000000));
 }

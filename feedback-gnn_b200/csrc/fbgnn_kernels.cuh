@@ -108,6 +108,9 @@ struct MathSfu {
 #define FBGNN_PHI_GROUP 3          // phi call sites of a check evaluated under one warp vote: the G polynomial chains
                                    // interleave (the single-site form leaves the warp latency-bound on one Horner chain)
 #endif
+#ifndef FBGNN_VOTE
+#define FBGNN_VOTE 1               // 0 (lab): evaluate always, select afterwards -- no warp vote / branch
+#endif
 #ifndef FBGNN_LEAN
 #define FBGNN_LEAN 1               // no clamps inside the voted evaluations (identity for the lanes that use them)
 #endif
@@ -133,7 +136,7 @@ __device__ __forceinline__ float phi_sat(float x) {
     if (!MATH::kSaturationShortcuts) return PHI4 ? MATH::phi4(x) : MATH::phi2(x);
     const bool hi = x >= FB_PHI_CLIP_HI, lo = x <= FB_PHI_CLIP_LO;
     float r = hi ? 0.0f : FB_PHI_CLIP_HI;
-    if (__any_sync(__activemask(), !(hi || lo))) {
+    if (!FBGNN_VOTE || __any_sync(__activemask(), !(hi || lo))) {
         const float f = phi_eval<MATH, PHI4>(x);
         r = (hi || lo) ? r : f;
     }
@@ -157,7 +160,7 @@ __device__ __forceinline__ void phi_sat_group(const float x[G], float r[G]) {
         r[k] = hi ? 0.0f : FB_PHI_CLIP_HI;
         need = need || !sat[k];
     }
-    if (__any_sync(__activemask(), need)) {
+    if (!FBGNN_VOTE || __any_sync(__activemask(), need)) {
 #pragma unroll
         for (int k = 0; k < G; k++) {
             const float f = phi_eval<MATH, PHI4>(x[k]);
@@ -172,7 +175,7 @@ __device__ __forceinline__ float logaddexp_sat(float a, float b) {
     const float mx = fmaxf(a, b), mn = fminf(a, b);
     const bool sat = FB_SUB(mn, mx) < -17.5f;
     float r = FB_ADD(0.0f, mx);
-    if (__any_sync(__activemask(), !sat)) {
+    if (!FBGNN_VOTE || __any_sync(__activemask(), !sat)) {
         float f;
         if (FBGNN_LEAN) {           // exp without its clamp: d >= -17.5 on the lanes that keep f
             f = MATH::logaddexp_open(mx, FB_SUB(mn, mx));
@@ -2159,7 +2162,7 @@ static __global__ void k_math_probe(int fn, const float *x, float *y, int64_t n)
         case 5: r = fb_phi2f(v); break;
         case 6: r = fb_tanhf(v); break;
         case 7: r = fb_atanhf(v); break;
-        case 8: r = fb_mufu_ex2(v, 0.0f); break;        // raw MUFU.EX2 (tools/dump_sfu_tables.py)
+        case 8: r = fb_mufu_ex2(v); break;              // raw MUFU.EX2 (tools/dump_sfu_tables.py)
         case 9: r = fb_mufu_lg2(v); break;              // raw MUFU.LG2
         case 15: r = fb_mufu_rcp(v); break;             // raw MUFU.RCP
         case 16: r = fb_sfu_tanhf(v); break;

@@ -87,7 +87,7 @@ def set_math(mode):
         if _sfu_keep is None:
             from . import sfu_tables
             _sfu_keep = sfu_tables.tables()
-            L.orc_set_sfu_tables(_p(_sfu_keep[0]), _p(_sfu_keep[1]), _p(_sfu_keep[2]))
+            L.orc_set_sfu_tables(_p(_sfu_keep[0]), _p(_sfu_keep[1]), _p(_sfu_keep[2]), _p(_sfu_keep[3]))
     elif mode != "exact":
         raise ValueError("math mode must be 'exact' or 'sfu'")
     rc = L.orc_set_math(1 if mode == "sfu" else 0)

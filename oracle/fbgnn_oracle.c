@@ -1317,12 +1317,14 @@ int orc_num_threads(void) {
  * needs orc_set_sfu_tables first).  See fb_math.h. */
 int orc_set_math(int mode) {
     if (mode != 0 && mode != 1) return -1;
-    if (mode == 1 && (!fb_sfu_ex2_tab || !fb_sfu_lg2_tab || !fb_sfu_rcp_tab)) return -2;
+    if (mode == 1 && (!fb_sfu_ex2_tab || !fb_sfu_lg2_tab || !fb_sfu_lg2b_tab || !fb_sfu_rcp_tab)) return -2;
     fb_math_mode = mode;
     return 0;
 }
 int orc_get_math(void) { return fb_math_mode; }
-void orc_set_sfu_tables(const float *ex2_tab, const float *lg2_tab, const float *rcp_tab) { fb_sfu_set_tables(ex2_tab, lg2_tab, rcp_tab); }
+void orc_set_sfu_tables(const float *ex2_tab, const float *lg2_tab, const float *lg2b_tab, const float *rcp_tab) {
+    fb_sfu_set_tables(ex2_tab, lg2_tab, lg2b_tab, rcp_tab);
+}
 
 void orc_set_num_threads(int t) {
 #ifdef _OPENMP

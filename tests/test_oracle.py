@@ -50,6 +50,9 @@ def test_first_stage_marginal_extrema_kat(oracle, c1270):
     assert mx[0] == float(np.float32(prior + np.float32(3) * np.float32(16.635532)))
 
 
+_CANCEL = 4e-6         # absolute noise of a check's phi sum in units of exp(|m|): ~2 float32 quanta at x >= 16 (1.9e-6 each)
+
+
 def _tol(ref, cn_type, got=None):
     """Float32 noise model of one check-node update.  A message of magnitude |m| leaves the phi
     formula as -log(T/2) with T ~ 2 exp(-|m|) a sum of phi values that are themselves differences of
@@ -58,7 +61,7 @@ def _tol(ref, cn_type, got=None):
     ar = np.abs(ref) if got is None else np.maximum(np.abs(ref), np.abs(got))
     tol = 2e-5 * ar + 1e-5
     if cn_type != "minsum":
-        tol = tol + np.minimum(4e-6 * np.exp(np.minimum(ar, 20.0)), 4.0)
+        tol = tol + np.minimum(_CANCEL * np.exp(np.minimum(ar, 20.0)), 4.0)
     return tol
 
 

@@ -1,8 +1,8 @@
 #!/usr/bin/env python
-"""Measure the special-function unit of the GPU on the two finite input sets the SFU arithmetic uses
+"""Measure the special-function unit of the GPU on the finite input sets the SFU arithmetic uses
 (csrc/fb_math.h) and store the result as the tables the CPU oracle evaluates MUFU.EX2 / MUFU.LG2 with.
 
-    python tools/dump_sfu_tables.py            (needs a GPU; writes tests/golden/sfu_b200_{ex2,lg2,rcp}.xz)
+    python tools/dump_sfu_tables.py            (needs a GPU; writes tests/golden/sfu_b200_{ex2,lg2,lg2b,rcp}.xz)
 
 Each file holds, lzma-compressed, one little-endian int32 per table entry: the difference between the bit
 pattern the hardware returned and the bit pattern of a reference value that any IEEE-754 machine reproduces
@@ -40,6 +40,7 @@ def main():
     outdir = os.path.join(ROOT, "tests", "golden")
     for name, inputs, ref, fn in (("ex2", T.ex2_inputs(), T.ex2_reference(), "mufu_ex2"),
                                   ("lg2", T.lg2_inputs(), T.lg2_reference(), "mufu_lg2"),
+                                  ("lg2b", T.lg2b_inputs(), T.lg2b_reference(), "mufu_lg2"),
                                   ("rcp", T.rcp_inputs(), T.rcp_reference(), "mufu_rcp")):
         hw = probe(ctx, fn, inputs)
         delta = hw.view(np.int32).astype(np.int64) - ref.view(np.int32).astype(np.int64)
