@@ -108,6 +108,12 @@ struct MathSfu {
 #define FBGNN_PHI_GROUP 3          // phi call sites of a check evaluated under one warp vote: the G polynomial chains
                                    // interleave (the single-site form leaves the warp latency-bound on one Horner chain)
 #endif
+#ifndef FBGNN_LAE_GROUP
+#define FBGNN_LAE_GROUP 3          // logaddexp sites of a variable node evaluated under one warp vote (3 = per side, 6 = all)
+#endif
+#ifndef FBGNN_UNIFORM
+#define FBGNN_UNIFORM 1            // regular fast path: warp-uniform node loops, full-mask votes
+#endif
 #ifndef FBGNN_VOTE
 #define FBGNN_VOTE 1               // 0 (lab): evaluate always, select afterwards -- no warp vote / branch
 #endif
@@ -145,7 +151,7 @@ __device__ __forceinline__ float phi_sat(float x) {
 
 // G call sites under one vote: the G independent polynomial chains interleave (ILP) at the price of evaluating
 // all G when any lane needs any of them.  Values are those of phi_sat.
-template <typename MATH, bool PHI4, int G>
+template <typename MATH, bool PHI4, int G, bool FULL = false>
 __device__ __forceinline__ void phi_sat_group(const float x[G], float r[G]) {
     if (!MATH::kSaturationShortcuts) {
 #pragma unroll
@@ -160,7 +166,7 @@ __device__ __forceinline__ void phi_sat_group(const float x[G], float r[G]) {
         r[k] = hi ? 0.0f : FB_PHI_CLIP_HI;
         need = need || !sat[k];
     }
-    if (!FBGNN_VOTE || __any_sync(__activemask(), need)) {
+    if (!FBGNN_VOTE || __any_sync(FULL ? 0xffffffffu : __activemask(), need)) {
 #pragma unroll
         for (int k = 0; k < G; k++) {
             const float f = phi_eval<MATH, PHI4>(x[k]);
@@ -185,6 +191,27 @@ __device__ __forceinline__ float logaddexp_sat(float a, float b) {
         r = sat ? r : f;
     }
     return r;
+}
+
+// G logaddexp sites under one vote (the warp is converged: full mask).  Values are those of logaddexp_sat.
+template <typename MATH, int G>
+__device__ __forceinline__ void logaddexp_sat_group(const float a[G], const float b[G], float r[G]) {
+    float mx[G], d[G];
+    bool need = false;
+#pragma unroll
+    for (int k = 0; k < G; k++) {
+        mx[k] = fmaxf(a[k], b[k]);
+        d[k] = FB_SUB(fminf(a[k], b[k]), mx[k]);
+        r[k] = FB_ADD(0.0f, mx[k]);
+        need = need || !(d[k] < -17.5f);
+    }
+    if (!FBGNN_VOTE || __any_sync(0xffffffffu, need)) {
+#pragma unroll
+        for (int k = 0; k < G; k++) {
+            const float f = MATH::logaddexp_open(mx[k], d[k]);
+            r[k] = (d[k] < -17.5f) ? r[k] : f;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ check nodes -------
@@ -284,9 +311,12 @@ __device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge,
 // is bit-identical to the one it replaces (saturated magnitude, same sign): when that holds for all
 // checks of a frame the decoder state is a fixed point of the (deterministic) iteration and the
 // remaining iterations cannot change it.
-template <int DC, int DV, bool PHI4, typename MATH, bool FPX>
+// FULL: the caller keeps all 32 lanes of the warp in the loop (lanes past the end redo the last check with `live` false
+// and store nothing), so the votes use the full mask -- no activemask / divergence check around each of them.
+template <int DC, int DV, bool PHI4, typename MATH, bool FPX, bool FULL = false>
 __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge, int c, float *msg,
-                                               int synd_bit, float factor, const uint16_t *rec, int slot0) {
+                                               int synd_bit, float factor, const uint16_t *rec, int slot0,
+                                               bool live = true) {
     int e[DC];
     float a[DC];
     uint32_t neg = 0;
@@ -304,7 +334,7 @@ __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge
         xin[k] = fabsf(m);
     }
 #pragma unroll
-    for (int k = 0; k < DC; k += GRP) phi_sat_group<MATH, PHI4, GRP>(xin + k, a + k);
+    for (int k = 0; k < DC; k += GRP) phi_sat_group<MATH, PHI4, GRP, FULL>(xin + k, a + k);
     float T = 0.0f;
 #pragma unroll
     for (int k = 0; k < DC; k++) T = FB_ADD(T, a[k]);
@@ -313,30 +343,37 @@ __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge
 #pragma unroll
     for (int k = 0; k < DC; k++) xo[k] = FB_SUB(T, a[k]);
 #pragma unroll
-    for (int k = 0; k < DC; k += GRP) phi_sat_group<MATH, PHI4, GRP>(xo + k, vo + k);
+    for (int k = 0; k < DC; k += GRP) phi_sat_group<MATH, PHI4, GRP, FULL>(xo + k, vo + k);
+    bool allsat = true;
 #pragma unroll
     for (int k = 0; k < DC; k++) {
-        const float x = xo[k];
         float v = vo[k];
         const uint32_t s = ((uint32_t)par ^ (neg >> k)) & 1u;
         v = __int_as_float(__float_as_int(v) ^ (int)(s << 31));
-        msg[e[k]] = FB_MUL(v, factor);
-        if (FPX && rec) {
-            if (__all_sync(__activemask(), x <= FB_PHI_CLIP_LO)) {
+        if (live) msg[e[k]] = FB_MUL(v, factor);
+        allsat = allsat && (xo[k] <= FB_PHI_CLIP_LO);
+    }
+    if (FPX && rec) {
+        // one vote per check: only the AND over the whole frame is used (k_bp4's __syncthreads_and), so a warp with
+        // any unsaturated output skips the record look-ups of all its lanes
+        if (__all_sync(FULL ? 0xffffffffu : __activemask(), allsat)) {
+#pragma unroll
+            for (int k = 0; k < DC; k++) {
+                const uint32_t s = ((uint32_t)par ^ (neg >> k)) & 1u;
                 const int vv = e[k] / DV;
                 const int r = rec[vv];
                 stable = stable && !(r & 0x8000) && ((uint32_t)((r >> (e[k] - vv * DV + slot0)) & 1) == s);
-            } else {
-                stable = false;
             }
+        } else {
+            stable = false;
         }
     }
     return stable;
 }
 
-template <int DV, typename MATH, bool FPX>
+template <int DV, typename MATH, bool FPX, bool FULL = false>
 __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, float px, float py, float pz,
-                                                  uint16_t *rec, int sat_bits) {
+                                                  uint16_t *rec, int sat_bits, bool live = true) {
     float ax[DV], az[DV];
 #pragma unroll
     for (int k = 0; k < DV; k++) { ax[k] = mx[v * DV + k]; az[k] = mz[v * DV + k]; }
@@ -349,7 +386,7 @@ __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, f
             r |= ((bz >> 31) & 1) << (DV + k);
             bad |= ((bx & 0x7fffffff) ^ sat_bits) | ((bz & 0x7fffffff) ^ sat_bits);
         }
-        rec[v] = (uint16_t)(bad ? 0x8000 : r);
+        if (live) rec[v] = (uint16_t)(bad ? 0x8000 : r);
     }
     float Sx = 0.0f, Sz = 0.0f;
 #pragma unroll
@@ -360,12 +397,36 @@ __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, f
     const float lx = FB_ADD(Sz, px);
     const float lz = FB_ADD(Sx, pz);
     const float num_hx = MATH::softplus(-lx), num_hz = MATH::softplus(-lz);
+    if (FULL && MATH::kSaturationShortcuts && FBGNN_LEAN) {
+        // the 2 DV logaddexp sites under FBGNN_LAE_GROUP-sized votes (same values as one vote per site)
+        constexpr int LG = (FBGNN_LAE_GROUP > 0 && (2 * DV) % FBGNN_LAE_GROUP == 0) ? FBGNN_LAE_GROUP : DV;
+        float p[2 * DV], q[2 * DV], r[2 * DV];
 #pragma unroll
-    for (int k = 0; k < DV; k++)
-        mx[v * DV + k] = FB_SUB(num_hx, logaddexp_sat<MATH>(-FB_SUB(lz, ax[k]), -FB_SUB(ly, ax[k])));
+        for (int k = 0; k < DV; k++) {
+            p[k] = -FB_SUB(lz, ax[k]); q[k] = -FB_SUB(ly, ax[k]);
+            p[DV + k] = -FB_SUB(lx, az[k]); q[DV + k] = -FB_SUB(ly, az[k]);
+        }
 #pragma unroll
-    for (int k = 0; k < DV; k++)
-        mz[v * DV + k] = FB_SUB(num_hz, logaddexp_sat<MATH>(-FB_SUB(lx, az[k]), -FB_SUB(ly, az[k])));
+        for (int k = 0; k < 2 * DV; k += LG) logaddexp_sat_group<MATH, LG>(p + k, q + k, r + k);
+        if (live) {
+#pragma unroll
+            for (int k = 0; k < DV; k++) {
+                mx[v * DV + k] = FB_SUB(num_hx, r[k]);
+                mz[v * DV + k] = FB_SUB(num_hz, r[DV + k]);
+            }
+        }
+        return;
+    }
+#pragma unroll
+    for (int k = 0; k < DV; k++) {
+        const float o = FB_SUB(num_hx, logaddexp_sat<MATH>(-FB_SUB(lz, ax[k]), -FB_SUB(ly, ax[k])));
+        if (live) mx[v * DV + k] = o;
+    }
+#pragma unroll
+    for (int k = 0; k < DV; k++) {
+        const float o = FB_SUB(num_hz, logaddexp_sat<MATH>(-FB_SUB(lx, az[k]), -FB_SUB(ly, az[k])));
+        if (live) mz[v * DV + k] = o;
+    }
 }
 
 // ------------------------------------------------------------------ bulk-async staging --
@@ -551,6 +612,7 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     __syncthreads();
 
     const bool fast = DV > 0 && a.cn_type == 0;     // regular graph + boxplus-phi: unrolled path
+    constexpr bool uniform = FBGNN_UNIFORM != 0;    // the launchers only use multiples of 32 threads
     // Fixed-point exit (exact arithmetic only): once an iteration reproduces every message bit for bit
     // the remaining iterations are no-ops, so they are skipped -- the outputs are unchanged by construction.
     // Only worth its bookkeeping for long runs (the 64-iteration first stage), and never before iteration 6.
@@ -561,6 +623,17 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         if (a.iter_logits.ptr) bp4_iter_logits<CONST_PRIOR, MATH>(a, mx, mz, pri, scr2, dec, b, it);
         uint16_t *recp = (fp_exit && it >= 6) ? rec : nullptr;
         // variable nodes (decoding_q.py:227-275)
+        if (DV > 0 && uniform) {
+            // all 32 lanes of a warp stay in the loop; lanes past the end redo variable n - 1 and store nothing
+            for (int vb = tid; (vb & ~31) < n; vb += T) {
+                const bool live = vb < n;
+                const int v = live ? vb : n - 1;
+                const float px = CONST_PRIOR ? a.prior : pri[v];
+                const float py = CONST_PRIOR ? a.prior : pri[np + v];
+                const float pz = CONST_PRIOR ? a.prior : pri[2 * np + v];
+                vn_update_regular<(DV > 0 ? DV : 1), MATH, FPX, true>(v, mx, mz, px, py, pz, recp, sat_bits, live);
+            }
+        } else
         for (int v = tid; v < n; v += T) {
             const float px = CONST_PRIOR ? a.prior : pri[v];
             const float py = CONST_PRIOR ? a.prior : pri[np + v];
@@ -589,6 +662,18 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         __syncthreads();
         // check nodes of both sides as one index space
         bool stable = true;
+        if (fast && uniform) {
+            const int mt = X.m + Z.m;
+            for (int cb = tid; (cb & ~31) < mt; cb += T) {
+                const bool live = cb < mt;
+                const int c = live ? cb : mt - 1;
+                const bool isx = c < X.m;
+                const int cc = isx ? c : c - X.m;
+                stable &= cn_phi_regular<(DC > 0 ? DC : 1), (DV > 0 ? DV : 1), true, MATH, FPX, true>(
+                    isx ? X.cn_edge : Z.cn_edge, cc, isx ? mx : mz, isx ? sbx[cc] : sbz[cc], a.factor, recp, isx ? 0 : DV,
+                    live);
+            }
+        } else
         for (int c = tid; c < X.m + Z.m; c += T) {
             const bool isx = c < X.m;
             const int cc = isx ? c : c - X.m;
