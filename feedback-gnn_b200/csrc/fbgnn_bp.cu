@@ -36,7 +36,8 @@ static int launch_bp4_m(fbgnn_ctx *ctx, const Bp4Args &a, int64_t grid, size_t s
     // fixed-point exit: regular graph, boxplus-phi, long runs (the bookkeeping costs ~5 % per unsaturated iteration
     // and a 16-iteration stage does not converge-and-saturate in time).  Valid in both arithmetics: the saturation
     // constants are exact in each.
-    const bool fpx = DV > 0 && a.cn_type == 0 && a.num_iter >= 32 && !a.iter_logits.ptr;
+    static const int fpx_min_iter = getenv("FBGNN_FPX_MIN_ITER") ? atoi(getenv("FBGNN_FPX_MIN_ITER")) : 32;   // lab knob
+    const bool fpx = DV > 0 && a.cn_type == 0 && a.num_iter >= fpx_min_iter && !a.iter_logits.ptr;
     if (ctx->math_mode == FBGNN_MATH_SFU) {
         if (fpx)
             return cp ? launch_bp4_t<true, DV, DC, MathSfu, true>(ctx, a, grid, smem, threads)

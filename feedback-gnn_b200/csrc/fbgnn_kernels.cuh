@@ -311,12 +311,12 @@ __device__ __forceinline__ void cn_update_one(const idx_t *__restrict__ cn_edge,
 // is bit-identical to the one it replaces (saturated magnitude, same sign): when that holds for all
 // checks of a frame the decoder state is a fixed point of the (deterministic) iteration and the
 // remaining iterations cannot change it.
-// FULL: the caller keeps all 32 lanes of the warp in the loop (lanes past the end redo the last check with `live` false
-// and store nothing), so the votes use the full mask -- no activemask / divergence check around each of them.
+// FULL: the caller guarantees that all 32 lanes of the warp are here (k_bp4 runs the whole warps of a node loop through
+// this instantiation and the ragged last warp through the other one), so the votes use the full mask -- no activemask /
+// divergence check around each of them.
 template <int DC, int DV, bool PHI4, typename MATH, bool FPX, bool FULL = false>
 __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge, int c, float *msg,
-                                               int synd_bit, float factor, const uint16_t *rec, int slot0,
-                                               bool live = true) {
+                                               int synd_bit, float factor, const uint16_t *rec, int slot0) {
     int e[DC];
     float a[DC];
     uint32_t neg = 0;
@@ -350,7 +350,7 @@ __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge
         float v = vo[k];
         const uint32_t s = ((uint32_t)par ^ (neg >> k)) & 1u;
         v = __int_as_float(__float_as_int(v) ^ (int)(s << 31));
-        if (live) msg[e[k]] = FB_MUL(v, factor);
+        msg[e[k]] = FB_MUL(v, factor);
         allsat = allsat && (xo[k] <= FB_PHI_CLIP_LO);
     }
     if (FPX && rec) {
@@ -373,10 +373,13 @@ __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge
 
 template <int DV, typename MATH, bool FPX, bool FULL = false>
 __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, float px, float py, float pz,
-                                                  uint16_t *rec, int sat_bits, bool live = true) {
+                                                  uint16_t *rec, int sat_bits) {
     float ax[DV], az[DV];
 #pragma unroll
-    for (int k = 0; k < DV; k++) { ax[k] = mx[v * DV + k]; az[k] = mz[v * DV + k]; }
+    for (int k = 0; k < DV; k++) {
+        ax[k] = mx[v * DV + k];
+        az[k] = mz[v * DV + k];
+    }
     if (FPX && rec) {      // signs of the incoming messages and whether all of them are saturated (see cn_phi_regular)
         int r = 0, bad = 0;
 #pragma unroll
@@ -386,7 +389,7 @@ __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, f
             r |= ((bz >> 31) & 1) << (DV + k);
             bad |= ((bx & 0x7fffffff) ^ sat_bits) | ((bz & 0x7fffffff) ^ sat_bits);
         }
-        if (live) rec[v] = (uint16_t)(bad ? 0x8000 : r);
+        rec[v] = (uint16_t)(bad ? 0x8000 : r);
     }
     float Sx = 0.0f, Sz = 0.0f;
 #pragma unroll
@@ -408,25 +411,19 @@ __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, f
         }
 #pragma unroll
         for (int k = 0; k < 2 * DV; k += LG) logaddexp_sat_group<MATH, LG>(p + k, q + k, r + k);
-        if (live) {
 #pragma unroll
-            for (int k = 0; k < DV; k++) {
-                mx[v * DV + k] = FB_SUB(num_hx, r[k]);
-                mz[v * DV + k] = FB_SUB(num_hz, r[DV + k]);
-            }
+        for (int k = 0; k < DV; k++) {
+            mx[v * DV + k] = FB_SUB(num_hx, r[k]);
+            mz[v * DV + k] = FB_SUB(num_hz, r[DV + k]);
         }
         return;
     }
 #pragma unroll
-    for (int k = 0; k < DV; k++) {
-        const float o = FB_SUB(num_hx, logaddexp_sat<MATH>(-FB_SUB(lz, ax[k]), -FB_SUB(ly, ax[k])));
-        if (live) mx[v * DV + k] = o;
-    }
+    for (int k = 0; k < DV; k++)
+        mx[v * DV + k] = FB_SUB(num_hx, logaddexp_sat<MATH>(-FB_SUB(lz, ax[k]), -FB_SUB(ly, ax[k])));
 #pragma unroll
-    for (int k = 0; k < DV; k++) {
-        const float o = FB_SUB(num_hz, logaddexp_sat<MATH>(-FB_SUB(lx, az[k]), -FB_SUB(ly, az[k])));
-        if (live) mz[v * DV + k] = o;
-    }
+    for (int k = 0; k < DV; k++)
+        mz[v * DV + k] = FB_SUB(num_hz, logaddexp_sat<MATH>(-FB_SUB(lx, az[k]), -FB_SUB(ly, az[k])));
 }
 
 // ------------------------------------------------------------------ bulk-async staging --
@@ -624,14 +621,13 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         uint16_t *recp = (fp_exit && it >= 6) ? rec : nullptr;
         // variable nodes (decoding_q.py:227-275)
         if (DV > 0 && uniform) {
-            // all 32 lanes of a warp stay in the loop; lanes past the end redo variable n - 1 and store nothing
-            for (int vb = tid; (vb & ~31) < n; vb += T) {
-                const bool live = vb < n;
-                const int v = live ? vb : n - 1;
+            // whole warps take the full-mask instantiation, the ragged last warp the activemask one
+            for (int v = tid; v < n; v += T) {
                 const float px = CONST_PRIOR ? a.prior : pri[v];
                 const float py = CONST_PRIOR ? a.prior : pri[np + v];
                 const float pz = CONST_PRIOR ? a.prior : pri[2 * np + v];
-                vn_update_regular<(DV > 0 ? DV : 1), MATH, FPX, true>(v, mx, mz, px, py, pz, recp, sat_bits, live);
+                if ((v | 31) < n) vn_update_regular<(DV > 0 ? DV : 1), MATH, FPX, true>(v, mx, mz, px, py, pz, recp, sat_bits);
+                else vn_update_regular<(DV > 0 ? DV : 1), MATH, FPX, false>(v, mx, mz, px, py, pz, recp, sat_bits);
             }
         } else
         for (int v = tid; v < n; v += T) {
@@ -664,14 +660,15 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
         bool stable = true;
         if (fast && uniform) {
             const int mt = X.m + Z.m;
-            for (int cb = tid; (cb & ~31) < mt; cb += T) {
-                const bool live = cb < mt;
-                const int c = live ? cb : mt - 1;
+            for (int c = tid; c < mt; c += T) {
                 const bool isx = c < X.m;
                 const int cc = isx ? c : c - X.m;
-                stable &= cn_phi_regular<(DC > 0 ? DC : 1), (DV > 0 ? DV : 1), true, MATH, FPX, true>(
-                    isx ? X.cn_edge : Z.cn_edge, cc, isx ? mx : mz, isx ? sbx[cc] : sbz[cc], a.factor, recp, isx ? 0 : DV,
-                    live);
+                if ((c | 31) < mt)
+                    stable &= cn_phi_regular<(DC > 0 ? DC : 1), (DV > 0 ? DV : 1), true, MATH, FPX, true>(
+                        isx ? X.cn_edge : Z.cn_edge, cc, isx ? mx : mz, isx ? sbx[cc] : sbz[cc], a.factor, recp, isx ? 0 : DV);
+                else
+                    stable &= cn_phi_regular<(DC > 0 ? DC : 1), (DV > 0 ? DV : 1), true, MATH, FPX, false>(
+                        isx ? X.cn_edge : Z.cn_edge, cc, isx ? mx : mz, isx ? sbx[cc] : sbz[cc], a.factor, recp, isx ? 0 : DV);
             }
         } else
         for (int c = tid; c < X.m + Z.m; c += T) {
@@ -924,6 +921,10 @@ static __global__ void __launch_bounds__(512) k_bp2(const Bp2Args a) {
 }
 
 // ------------------------------------------------------------------ feedback GNN ------
+#ifndef FBGNN_GNN_UNROLL
+#define FBGNN_GNN_UNROLL 1            // hidden units of the regular path per loop trip (lab knob)
+#endif
+constexpr int kGnnUnroll = FBGNN_GNN_UNROLL;
 struct GnnArgs {
     SideDev X, Z;
     const float *weights;               // packed, see GnnLayout
@@ -1016,7 +1017,7 @@ __device__ __forceinline__ void gnn_body(const GnnArgs &a, const WSRC w) {
             }
 #pragma unroll
             for (int i = 0; i < M; i++) { rx[i] = 0.0f; rz[i] = 0.0f; }
-#pragma unroll 1
+#pragma unroll kGnnUnroll
             for (int j = 0; j < H; j++) {
                 const float4 wx = w.ld4(Lay::W1tx + 4 * j), wz = w.ld4(Lay::W1tz + 4 * j);
                 const float bx = w.ld(Lay::b1x + j), bz = w.ld(Lay::b1z + j);

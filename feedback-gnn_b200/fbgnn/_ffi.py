@@ -246,6 +246,10 @@ class Context:
             self.sync()                                    # h may be a temporary
         return a
 
+    def edge_vn(self):
+        """Variable node of every edge, edges sorted by (variable, check) -- the order of the message vectors."""
+        return self._vn_of_edge
+
     def __del__(self):
         try:
             if self.handle:
@@ -510,8 +514,13 @@ class Graph:
         self.ctx = ctx or default_context()
         self.m, self.n, indptr, indices = _csr(pcm)
         self.E = int(indptr[-1])
+        self._vn_of_edge = np.sort(np.asarray(indices[:self.E], np.int64))
         self.handle = C.c_void_p()
         call("fbgnn_graph_create", self.ctx.handle, self.n, self.m, _ip(indptr), _ip(indices), C.byref(self.handle))
+
+    def edge_vn(self):
+        """Variable node of every edge, edges sorted by (variable, check) -- the order of the message vectors."""
+        return self._vn_of_edge
 
     def __del__(self):
         try:

@@ -10,13 +10,22 @@ The decoding runs in the CUDA kernel ``k_bp2`` behind ``fbgnn_bp2_decode``.
 Edge order: variable-node sorted, as the reference intends (its ``sp.sparse.find`` relied on
 column-major output, which scipy >= 1.11 no longer gives -- SURVEY.md F8).
 
-Not provided (outside the quantum hot path): ``trainable`` edge weights, ``stateful``
-message passing between calls and ``track_exit`` EXIT-chart tracking.
+``trainable`` (per-edge weights), ``stateful`` (message state in / out) and ``track_exit`` (EXIT trajectory
+``ie_v`` / ``ie_c``, ``decoding.py:955-1000``) are provided; the latter steps the kernel one iteration at a time and
+evaluates the mutual-information estimate ``llr2mi`` (``fec/utils.py:151-218``) on the host.
 """
 import numpy as np
 
 from . import _ffi
 from .decoding_q import CN_TYPES, _is_device, _to_u8
+
+
+def _llr2mi(llr):
+    """``sionna.fec.utils.llr2mi`` (``fec/utils.py:203-218``) for an all-zero codeword: 1 - mean(log2(1 + exp(llr)))
+    with the LLRs clipped to +-20, float32."""
+    z = np.clip(np.asarray(llr, np.float32), np.float32(-20.0), np.float32(20.0))
+    x = np.log(np.float32(1.0) + np.exp(z)) / np.float32(np.log(2.0))
+    return np.float32(1.0) - np.mean(x, dtype=np.float32)
 
 
 class LDPCBPDecoder:
@@ -42,8 +51,9 @@ class LDPCBPDecoder:
         assert isinstance(stateful, bool), 'stateful must be bool.'
         if cn_type not in CN_TYPES:
             raise ValueError('Unknown node type.')
-        if track_exit:
-            raise NotImplementedError("track_exit (EXIT-chart bookkeeping, decoding.py:958-961) is not provided")
+        self._track_exit = track_exit
+        self._ie_c = 0
+        self._ie_v = 0
         if stateful and is_syndrome:
             raise ValueError("the reference takes either (llr, msg_vn) or (llr, syndrome), decoding.py:901-909")
         self._stateful = stateful
@@ -78,6 +88,16 @@ class LDPCBPDecoder:
     @property
     def pcm(self):
         return self._pcm
+
+    @property
+    def ie_c(self):
+        "Extrinsic mutual information at check node."
+        return self._ie_c
+
+    @property
+    def ie_v(self):
+        "Extrinsic mutual information at variable node."
+        return self._ie_v
 
     def graph(self):
         if self._graph is None:
@@ -156,10 +176,40 @@ class LDPCBPDecoder:
                 m_in = ctx.asarray(msg_vn, np.float32)
                 if m_in.shape != (g.E, B):
                     raise ValueError(f"msg_vn must have shape [{g.E},{B}]")
-        _ffi.call("fbgnn_bp2_decode_ex", g.handle, CN_TYPES[self._cn_type], self._num_iter,
-                  self._normalization_factor, B, llr.t2(), synd.t2() if synd is not None else _ffi.NULL2,
-                  soft.t2(), hard.t2(), ew,
-                  m_in.T.t2() if m_in is not None else _ffi.NULL2, m_out.T.t2() if m_out is not None else _ffi.NULL2)
+        def run(num_iter, state_in, state_out):
+            _ffi.call("fbgnn_bp2_decode_ex", g.handle, CN_TYPES[self._cn_type], num_iter,
+                      self._normalization_factor, B, llr.t2(), synd.t2() if synd is not None else _ffi.NULL2,
+                      soft.t2(), hard.t2(), ew,
+                      state_in.T.t2() if state_in is not None else _ffi.NULL2,
+                      state_out.T.t2() if state_out is not None else _ffi.NULL2)
+
+        if self._track_exit:
+            # EXIT trajectory (decoding.py:955-1000): one kernel call per iteration through the message-state interface;
+            # slot it = 1 .. num_iter of ie_v / ie_c holds the mutual-information estimate of the variable-node / check-node
+            # output messages of that iteration (slot 0 stays 0, as in the reference)
+            ie_v = np.zeros(self._num_iter + 1, np.float32)
+            ie_c = np.zeros(self._num_iter + 1, np.float32)
+            vn_of_edge = g.edge_vn()
+            llr_true = -llr.numpy().T                                     # [n, B], the reference's internal sign
+            state = m_in if m_in is not None else ctx.asarray(np.zeros((g.E, B), np.float32))
+            bufs = [ctx.empty((B, g.E), np.float32).T, ctx.empty((B, g.E), np.float32).T]
+            if self._num_iter == 0:
+                run(0, state, bufs[0])
+                state = bufs[0]
+            for it in range(1, self._num_iter + 1):
+                c2v = state.numpy()                                       # [E, B], edges sorted by variable
+                tot = llr_true.copy()
+                np.add.at(tot, vn_of_edge, c2v)
+                ie_v[it] = _llr2mi(-(tot[vn_of_edge] - c2v))
+                nxt = bufs[it % 2]
+                run(1, state, nxt)
+                ie_c[it] = _llr2mi(-nxt.numpy())
+                state = nxt
+            if self._stateful:
+                m_out = state
+            self._ie_v, self._ie_c = ie_v, ie_c
+        else:
+            run(self._num_iter, m_in, m_out)
         if on_device:
             res = hard if self._hard_out else soft
             return (res, m_out) if self._stateful else res

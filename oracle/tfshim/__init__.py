@@ -630,7 +630,8 @@ def build_modules():
     rnd = _Random()
     dtypes = {n: DType(d, n) for n, d in dict(float32="float32", float64="float64", float16="float16", int32="int32",
                                                int64="int64", int8="int8", uint8="uint8", bool="bool",
-                                               complex64="complex64", complex128="complex128").items()}
+                                               complex64="complex64", complex128="complex128",
+                                               bfloat16="V2").items()}      # numpy has no bfloat16: a name that equals nothing
     tf.__dict__.update(dtypes)
     tf.DType = DType
     tf.Tensor = T

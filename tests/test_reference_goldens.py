@@ -219,8 +219,42 @@ def test_cuda_bp2_trainable_and_stateful(ref, allcodes, oracle):
     x2, m2 = st((llr, m1))
     for got, key in ((x1, "x1"), (x2, "x2"), (m1, "m1"), (m2, "m2")):
         assert np.array_equal(got, Z[f"c882.stateful.{key}"]), key
-    with pytest.raises(NotImplementedError):
-        F.LDPCBPDecoder(hx, track_exit=True)
+
+
+def test_llr2mi_known_answers():
+    """fec/utils.py:151-218: I = 1 - mean(log2(1 + exp(llr))), LLRs clipped to +-20."""
+    from fbgnn.decoding import _llr2mi
+    assert _llr2mi(np.zeros(7, np.float32)) == 0.0                              # no knowledge
+    assert abs(float(_llr2mi(np.full(5, -30.0, np.float32))) - 1.0) < 1e-6      # certain and right (clipped at -20)
+    assert abs(float(_llr2mi(np.full(5, 30.0, np.float32))) - (1.0 - 20.0 / np.log(2.0))) < 1e-4
+
+
+@pytest.mark.gpu
+def test_cuda_bp2_track_exit_matches_the_reference_code(allcodes):
+    """track_exit=True (decoding.py:955-1000): the EXIT trajectory ie_v / ie_c of the reference's own decoder, executed
+    under oracle/tfshim (tests/golden/make_reference_golden_exit.py)."""
+    import fbgnn as F
+    Z = np.load(os.path.join(GOLDEN, "ref_exit.npz"))
+    hx = allcodes["c882"].hx
+    for cn_type in ("boxplus-phi", "minsum"):
+        dec = F.LDPCBPDecoder(hx, track_exit=True, num_iter=6, normalization_factor=0.9, cn_type=cn_type, hard_out=False)
+        assert dec.ie_c == 0 and dec.ie_v == 0                                  # before the first call, as in the reference
+        soft = dec(Z["llr"])
+        plain = F.LDPCBPDecoder(hx, num_iter=6, normalization_factor=0.9, cn_type=cn_type, hard_out=False)(Z["llr"])
+        assert np.array_equal(soft, plain)                                      # tracking does not change the decoding
+        assert dec.ie_v.shape == dec.ie_c.shape == (7,) and dec.ie_v[0] == 0 and dec.ie_c[0] == 0
+        assert np.abs(dec.ie_v - Z[f"{cn_type}.ie_v"]).max() < 2e-5, cn_type
+        assert np.abs(dec.ie_c - Z[f"{cn_type}.ie_c"]).max() < 2e-5, cn_type
+        assert np.abs(soft - Z[f"{cn_type}.soft"]).max() < (1e-5 if cn_type == "minsum" else 5e-3)
+    # with a syndrome as well, and zero iterations
+    Zb = np.load(os.path.join(GOLDEN, "ref_bp2.npz"))
+    dec = F.LDPCBPDecoder(hx, track_exit=True, is_syndrome=True, num_iter=3, normalization_factor=0.9, hard_out=False)
+    ref3 = F.LDPCBPDecoder(hx, is_syndrome=True, num_iter=3, normalization_factor=0.9, hard_out=False)
+    assert np.array_equal(dec((Zb["c882.llr"], Zb["c882.synd"])), ref3((Zb["c882.llr"], Zb["c882.synd"])))
+    assert np.all(np.diff(dec.ie_c[1:]) != 0)
+    z = F.LDPCBPDecoder(hx, track_exit=True, num_iter=0, hard_out=False)
+    z(Z["llr"])
+    assert z.ie_c.tolist() == [0.0] and z.ie_v.tolist() == [0.0]
 
 
 @pytest.mark.parametrize("arith", ["exact", "sfu"])
