@@ -111,6 +111,9 @@ struct MathSfu {
 #ifndef FBGNN_LAE_GROUP
 #define FBGNN_LAE_GROUP 3          // logaddexp sites of a variable node evaluated under one warp vote (3 = per side, 6 = all)
 #endif
+#ifndef FBGNN_SIGNBITS
+#define FBGNN_SIGNBITS 1           // quaternary check nodes: sign parity as an XOR of the message words (lab: 0 = comparisons)
+#endif
 #ifndef FBGNN_UNIFORM
 #define FBGNN_UNIFORM 1            // regular fast path: warp-uniform node loops, full-mask votes
 #endif
@@ -319,7 +322,12 @@ __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge
                                                int synd_bit, float factor, const uint16_t *rec, int slot0) {
     int e[DC];
     float a[DC];
-    uint32_t neg = 0;
+    // Signs.  The quaternary decoder's variable-to-check messages are differences num - logaddexp(..) of this kernel's own
+    // making: never -0.0 (x - y rounds to +0 when it is zero) and never NaN, so "m < 0" IS the sign bit and the parity
+    // of the signs is an XOR of the message words (SIGNBITS).  The binary decoder keeps the comparisons: its messages
+    // can be scaled by negative edge weights, which makes -0.0 reachable, and sign(-0.0) counts as +1 in the reference.
+    constexpr bool SIGNBITS = PHI4 && FBGNN_SIGNBITS;
+    uint32_t neg = 0, word[DC], pw = (uint32_t)synd_bit << 31;
     int par = synd_bit;
 #pragma unroll
     for (int k = 0; k < DC; k++) e[k] = cn_edge[c * DC + k];
@@ -328,11 +336,17 @@ __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge
 #pragma unroll
     for (int k = 0; k < DC; k++) {
         const float m = msg[e[k]];
-        const uint32_t sgn = (m < 0.0f) ? 1u : 0u;
-        neg |= sgn << k;
-        par ^= (int)sgn;
+        if (SIGNBITS) {
+            word[k] = (uint32_t)__float_as_int(m);
+            pw ^= word[k];
+        } else {
+            const uint32_t sgn = (m < 0.0f) ? 1u : 0u;
+            neg |= sgn << k;
+            par ^= (int)sgn;
+        }
         xin[k] = fabsf(m);
     }
+    pw &= 0x80000000u;                              // parity of the signs and the syndrome bit, in the sign position
 #pragma unroll
     for (int k = 0; k < DC; k += GRP) phi_sat_group<MATH, PHI4, GRP, FULL>(xin + k, a + k);
     float T = 0.0f;
@@ -345,11 +359,11 @@ __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge
 #pragma unroll
     for (int k = 0; k < DC; k += GRP) phi_sat_group<MATH, PHI4, GRP, FULL>(xo + k, vo + k);
     bool allsat = true;
+    uint32_t sw[DC];                                // sign of the outgoing message, in the sign position
 #pragma unroll
     for (int k = 0; k < DC; k++) {
-        float v = vo[k];
-        const uint32_t s = ((uint32_t)par ^ (neg >> k)) & 1u;
-        v = __int_as_float(__float_as_int(v) ^ (int)(s << 31));
+        sw[k] = SIGNBITS ? ((word[k] & 0x80000000u) ^ pw) : ((((uint32_t)par ^ (neg >> k)) & 1u) << 31);
+        const float v = __int_as_float(__float_as_int(vo[k]) ^ (int)sw[k]);
         msg[e[k]] = FB_MUL(v, factor);
         allsat = allsat && (xo[k] <= FB_PHI_CLIP_LO);
     }
@@ -359,10 +373,9 @@ __device__ __forceinline__ bool cn_phi_regular(const idx_t *__restrict__ cn_edge
         if (__all_sync(FULL ? 0xffffffffu : __activemask(), allsat)) {
 #pragma unroll
             for (int k = 0; k < DC; k++) {
-                const uint32_t s = ((uint32_t)par ^ (neg >> k)) & 1u;
                 const int vv = e[k] / DV;
                 const int r = rec[vv];
-                stable = stable && !(r & 0x8000) && ((uint32_t)((r >> (e[k] - vv * DV + slot0)) & 1) == s);
+                stable = stable && !(r & 0x8000) && ((uint32_t)((r >> (e[k] - vv * DV + slot0)) & 1) == (sw[k] >> 31));
             }
         } else {
             stable = false;
