@@ -10,16 +10,21 @@ published table, examples/n1270.ipynb cell 2), depolarising noise p = 0.10, BP p
 every frame runs every round (reference-equivalent work; no round skipping), B frames per step per
 GPU.  A "step" = one pass of the whole pipeline over one batch of B synthetic frames.
 
-  value         frames/s, device-timed (CUDA events on the launching stream), noise sampled in-kernel
-  e2e           frames/s through the public Python API with HOST buffers: per step the noise samples
-                [B,n]x2 are copied from pinned host memory, the pipeline runs on them, and the
-                per-frame flags + counters are read back to the host
-  roofline      the dominant kernel (k_bp4, stage 0) against the MEASURED MUFU peak (SURVEY.md 8(d):
-                the path is transcendental-bound, not HBM- or tensor-bound), plus the measured FP32
-                issue peak that bounds the bit-exact software-libm path actually executed
-  cpu_baseline  the CPU oracle (oracle/fbgnn_oracle.c, the restatement of the reference; TensorFlow
-                is not installable in this image) on the box's host cores, bounded sample
+  value         frames/s, device-timed (CUDA events on the launching stream), noise sampled in-kernel; --math sfu
+                (default: exp / log on the special-function unit) or exact (FP32 polynomials) -- both bit-exact
+                against the CPU oracle in the same arithmetic; the other arithmetic is timed beside it
+  e2e           frames/s through the public Python API with HOST buffers: per step the noise bit-planes
+                (packed, 32 qubits per word) are copied from pinned host memory, the pipeline runs on them
+                (fbgnn_pipeline_run_bits) and the indicator planes + counters are read back to the host
+  roofline      the dominant kernel (k_bp4, stage 0) against the MEASURED MUFU peak (the path
+                is transcendental-bound, not HBM- or tensor-bound): frac on the algorithmic work, executed_frac
+                on the iterations the kernel reports as executed, issue_frac / traffic / pipe utilisation from the
+                committed ncu capture of the same launch (profiles/r02_ncu_k_bp4_stage0_<math>.json)
+  cpu_baseline  the CPU oracle (oracle/fbgnn_oracle.c, the restatement of the reference; TensorFlow is not
+                installable in this image) on the box's host cores, bounded sample; the numpy oracle beside it
   --impl reference   times that same CPU restatement alone (all host threads) and prints its line
+  N > 1         one process per GPU (RANK / WORLD_SIZE from the launcher), frames sharded by global frame id, one
+                NCCL all-reduce of the four counters per step inside the timed region (libfbgnn.so; no PyTorch)
 """
 import argparse
 import json
@@ -317,6 +322,12 @@ def main():
     roofline = {"bound": "sfu", "kernel": "k_bp4<const prior, fixed-point exit>, 64 iterations, arithmetic " + args.math,
                 "achieved": achieved / 1e9, "peak": sfu_peak / 1e9, "unit": "G transcendental evals/s",
                 "frac": achieved / sfu_peak,
+                "frac_note": "ALGORITHMIC transcendental evaluations of the reference formulas (SURVEY.md 8(d): 52n per "
+                             "iteration, all 64 iterations of every frame) / launch time / MUFU peak.  It can exceed 1: the "
+                             "fixed-point exit proves part of the iterations redundant and the SFU arithmetic shares one "
+                             "exp between the two terms of phi, so the kernel needs fewer MUFU instructions than the "
+                             "reference formulas have transcendentals.  What bounds the executed work is instruction "
+                             "issue: see executed_frac, issue_frac and profile.*_pipe_pct",
                 "peak_source": "measured live: ex2.approx micro-benchmark (fbgnn_sfu_peak); SURVEY.md 8(d) names the SFU "
                                "as the bound of this path, MEASURED_PEAKS.json holds only HBM / bf16 figures",
                 "units_per_launch": B, "te_per_unit": 64 * TE_ITER + TE_EPI, "launch_ms": k_ms,
