@@ -62,10 +62,10 @@ def build_code():
                                  name="GHP_n1270_k28")
 
 
-def build_model(code, seed=2, first_frame=0):
+def build_model(code, seed=2, first_frame=0, gemm="fma"):
     import fbgnn as F
     G = F.Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, reduce_op="mean",
-                       activation="tanh", use_bias=True)
+                       activation="tanh", use_bias=True, gemm=gemm)
     F.load_weights(G, os.path.join(F.WEIGHTS_DIR, WEIGHTS))
     d1 = F.QLDPCBPDecoder(code=code, num_iter=64, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
     d2 = F.QLDPCBPDecoder(code=code, num_iter=16, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
@@ -250,6 +250,13 @@ def main():
     model.skip_inactive = False
     s_value = s_steps * B * world / (s_ms * 1e-3)
 
+    # ---- the same workload with the feedback GNN's dense products on the tcgen05 tensor cores (opt-in, 3xTF32 split:
+    # float32 re-association accuracy, NOT bit-identical to the oracle) -- reported beside the headline, never as it
+    tc_model = build_model(code, seed=2, first_frame=rank * per_rank_frames, gemm="tf32x3")
+    t_steps = max(3, min(args.steps, 5))
+    t_ms, t_counters = time_pipeline(ctx, comm, tc_model, B, t_steps, 2)
+    t_value = t_steps * B * world / (t_ms * 1e-3)
+
     # ---- end to end through the public API with HOST buffers: packed noise bit-planes in, packed indicator planes out
     # (32 qubits / 32 frames per word: 10.5 MB in, 12 KB out per step instead of 83 MB / 33 KB as byte arrays)
     host_src = F.Pauli(seed=2, first_frame=10 ** 10 + rank * B).sample_device(B, N_Q, F.pauli_thresholds(P_NOISE))
@@ -387,6 +394,13 @@ def main():
                                       "GNN/BP rounds: bit-identical results (the reference masks those updates, "
                                       "feedback_gnn.py:339-340) but less work than the reference executes, so it "
                                       "is reported beside the headline, not as the headline"},
+            "tensor_core_gnn": {"value": t_value, "unit": "frames/s", "steps": t_steps,
+                                "block_errors": int(t_counters[2]), "frames": int(t_counters[0]),
+                                "note": "Feedback_GNN(gemm='tf32x3'): the three dense products of the node update on the "
+                                        "tcgen05 tensor cores (csrc/fbgnn_gnn_tc.cuh, operands in TMEM, 3-product TF32 "
+                                        "split).  Outputs agree with the bit-exact kernel to 1e-5 of the largest value "
+                                        "(tests/test_gpu_gnn_tc.py), decisions to the float32 noise floor of the "
+                                        "decoder; not a bit-exact mode, so it is reported beside the headline"},
             "roofline": roofline,
             "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)

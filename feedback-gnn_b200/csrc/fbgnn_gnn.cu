@@ -1,5 +1,6 @@
 // fbgnn_gnn.cu -- feedback GNN: weight packing, launch selection, C ABI.
 #include "fbgnn_internal.h"
+#include "fbgnn_gnn_tc.cuh"
 
 // ------------------------------------------------------------------ feedback GNN --------
 template <int H, int M>
@@ -42,7 +43,35 @@ extern "C" int fbgnn_gnn_create(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t ac
     g->total = (int)w.size();
     CK(cudaMalloc(&g->weights, w.size() * sizeof(float)));
     CK(cudaMemcpy(g->weights, w.data(), w.size() * sizeof(float), cudaMemcpyHostToDevice));
+    if (H == 40 && M == 20) {   // tensor-core operand tiles (TF32 hi / lo, canonical K-major UMMA layout) + the scalar block
+        using tc::GnnW;
+        std::vector<float> tv(GnnW::total, 0.0f);
+        auto tile = [&](int off, int kpad, int npad, auto wf) {
+            for (int nn = 0; nn < npad; nn++)
+                for (int k = 0; k < kpad; k++) {
+                    const float x = wf(k, nn), hi = tc::tf32_hi(x);
+                    tv[off + tc::b_tile_offset(nn, k, kpad)] = hi;
+                    tv[off + kpad * npad + tc::b_tile_offset(nn, k, kpad)] = x - hi;
+                }
+        };
+        tile(GnnW::W2X, 40, 32, [&](int k, int nn) { return nn < 20 ? W2x[k * 20 + nn] : 0.0f; });
+        tile(GnnW::W2Z, 40, 32, [&](int k, int nn) { return nn < 20 ? W2z[k * 20 + nn] : 0.0f; });
+        tile(GnnW::W3AB, 40, 48, [&](int k, int nn) { return nn < 40 ? W3[k * 40 + nn] : 0.0f; });
+        std::memcpy(&tv[GnnW::SCALAR], w.data(), sizeof(float) * w.size());
+        CK(cudaMalloc(&g->w_tc, tv.size() * sizeof(float)));
+        CK(cudaMemcpy(g->w_tc, tv.data(), tv.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     *out = g;
+    return 0;
+}
+
+extern "C" int fbgnn_gnn_set_gemm(fbgnn_gnn *g, int32_t mode) {
+    REQUIRE(g, "NULL handle");
+    REQUIRE(mode == FBGNN_GEMM_FMA || mode == FBGNN_GEMM_TF32X3, "unknown gemm mode %d", mode);
+    if (mode == FBGNN_GEMM_TF32X3 && !(g->w_tc && g->layers == 2 && g->reduce <= 1 && g->act == FBGNN_ACT_TANH))
+        return fail(FBGNN_E_UNSUPPORTED, "the tensor-core form of the feedback GNN is built for num_hidden_units = 40, "
+                    "num_msg_dims = 20, 2-layer MLPs, tanh, reduce_op mean / sum");
+    g->gemm = mode;
     return 0;
 }
 
@@ -79,6 +108,7 @@ extern "C" int fbgnn_gnn_destroy(fbgnn_gnn *g) {
     cudaSetDevice(g->ctx->device);
     cudaStreamSynchronize(g->ctx->stream);
     cudaFree(g->weights);
+    cudaFree(g->w_tc);
     delete g;
     return 0;
 }
@@ -116,6 +146,22 @@ int launch_gnn(fbgnn_ctx *ctx, const fbgnn_gnn *g, GnnArgs &a) {
         return 0;
     }
     const bool reg3 = a.X.reg_dv == 3 && a.Z.reg_dv == 3;      // the (3,6)-regular GHP / bivariate codes
+    if (g->gemm == FBGNN_GEMM_TF32X3) {                         // opt-in: dense products on tcgen05 (fbgnn_gnn_tc.cuh)
+        if (!reg3) return fail(FBGNN_E_UNSUPPORTED, "the tensor-core form of the feedback GNN needs (3, .)-regular sides");
+        const size_t smem = sizeof(float) * tc::GnnW::total;
+        const int64_t tiles = (a.num_frames * a.X.n + 127) / 128;
+        const unsigned blocks = (unsigned)std::min<int64_t>((tiles + 1) / 2, (int64_t)ctx->num_sms * 2);
+        if (ctx->math_mode == FBGNN_MATH_SFU) {
+            if (int rc = set_smem(tc::k_gnn_tc<3, MathSfu>, smem, ctx, "feedback GNN (tensor cores)")) return rc;
+            tc::k_gnn_tc<3, MathSfu><<<blocks, 256, smem, ctx->stream>>>(a, g->w_tc);
+        } else {
+            if (int rc = set_smem(tc::k_gnn_tc<3, MathExact>, smem, ctx, "feedback GNN (tensor cores)")) return rc;
+            tc::k_gnn_tc<3, MathExact><<<blocks, 256, smem, ctx->stream>>>(a, g->w_tc);
+        }
+        CK(cudaGetLastError());
+        ctx->launches++;
+        return 0;
+    }
     const bool tb = g->act == FBGNN_ACT_TANH && g->use_bias;   // the shipped configuration
     const bool fact = g->reduce <= 1;                          // mean / sum: output layer after the reduction
     if (g->H == 40 && g->M == 20) {

@@ -1,0 +1,143 @@
+// fbgnn_gnn_tc.cuh -- tensor-core (tcgen05 / TMEM) form of the feedback GNN's dense products, sm_100a.
+//
+// Feedback_GNN.call (feedback_gnn.py:161-188) per variable node: six edge MLPs whose first layer is rank one in the
+// check feature (thread-local FMAs + tanh), and then three dense products with the weights as the stationary operand:
+//     [hidden sums of the x edges, 40] x W2x [40 x 20],  [.. of the z edges, 40] x W2z [40 x 20],
+//     [m_x, m_z, 40] x W3[0:40] [40 x 40]                       (the three prior features of W3 stay thread-local).
+// Rows = frames x variable nodes: the one place on the headline path where "frames x nodes x hidden" is a real dense
+// GEMM (north star).  Same machinery as GNN_BP4's tensor-core path (fbgnn_gbp_tc.cuh): a group of 128
+// threads owns 128 rows, thread r <-> row r <-> TMEM lane r; the A operand goes registers -> TMEM (tcgen05.st), the
+// weights sit in shared memory as TF32 hi / lo tiles in the canonical K-major UMMA layout (staged by one bulk-async
+// copy), D accumulates in TMEM; float32 accuracy from TF32 hardware by the three-product split.
+//
+// Opt-in (Feedback_GNN(..., gemm="tf32x3") / fbgnn_gnn_set_gemm): the results agree with k_gnn / the oracle to float32
+// re-association accuracy (1e-6 of the largest output), NOT bit for bit, so it is never part of a bit-exact parity
+// claim; tests/test_gpu_gnn_tc.py states the tolerance and checks the error rates.
+#ifndef FBGNN_GNN_TC_CUH
+#define FBGNN_GNN_TC_CUH
+
+#include "fbgnn_gbp_tc.cuh"
+
+namespace fbgnn {
+namespace tc {
+
+struct GnnW {                                  // offsets in floats; each operand: [hi tile][lo tile]
+    static constexpr int H = 40, M = 20;
+    static constexpr int W2X = 0, W2Z = W2X + t(40, 32);              // K = H, N = M (32)
+    static constexpr int W3AB = W2Z + t(40, 32);                      // K = 2M, N = H (48)
+    static constexpr int SCALAR = W3AB + t(40, 48);                   // GnnLayout<40, 20> block (first layers, biases, W3 rows 40..42, W0)
+    static constexpr int total = SCALAR + GnnLayout<40, 20>::total;
+};
+
+// One side's edge phase of a tile row: hidden sums over the DV edges, 8 hidden units at a time, straight into TMEM as
+// the A operand of the W2 product (hi at [0, 40), lo at [40, 80)).
+template <int DV, typename MATH>
+__device__ __forceinline__ void gnn_edges_tc(const Grp &g, const float *__restrict__ w1t, const float *__restrict__ b1,
+                                             const float hc[DV], float f1, float f2, float f3) {
+    constexpr int H = 40, JB = 8;
+#pragma unroll 1
+    for (int j0 = 0; j0 < H; j0 += JB) {
+        uint32_t hi[JB], lo[JB];
+#pragma unroll
+        for (int q = 0; q < JB; q++) {
+            const float4 w = *reinterpret_cast<const float4 *>(w1t + 4 * (j0 + q));      // {w_cn, w_Lx, w_Ly, w_Lz}
+            const float base = FB_ADD(FB_FMA(f3, w.w, FB_FMA(f2, w.z, FB_FMA(f1, w.y, 0.0f))), b1[j0 + q]);
+            float hs = 0.0f;
+#pragma unroll
+            for (int k = 0; k < DV; k++) hs = FB_ADD(hs, MATH::tanh(FB_FMA(hc[k], w.x, base)));
+            const float h = tf32_hi(hs);
+            hi[q] = __float_as_uint(h);
+            lo[q] = __float_as_uint(hs - h);
+        }
+        __syncwarp();
+        tmem_st8(g.lane_base + j0, hi);
+        tmem_st8(g.lane_base + H + j0, lo);
+    }
+}
+
+// TMEM columns of a group: A operands at [0, 80) (hi, lo), D at [80, 128).
+template <int DV, typename MATH>
+__global__ void __launch_bounds__(256, 2) k_gnn_tc(const GnnArgs a, const float *__restrict__ wtc) {
+    constexpr int H = 40, M = 20;
+    typedef GnnLayout<H, M> Lay;
+    extern __shared__ __align__(128) float sm[];
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tslot;
+    Grp g = cta_setup(sm, wtc, GnnW::total, bars, &tslot);
+    const uint32_t sbase = smem_u32(sm);
+    const float *ws = sm + GnnW::SCALAR;                        // scalar-path weights, GnnLayout offsets
+    const int n = a.X.n, t = threadIdx.x & 127;
+    const int64_t total = a.num_frames * n, ntiles = (total + 127) / 128;
+    const float dg = (float)DV;
+    for (int64_t tile = (int64_t)blockIdx.x * 2 + g.gid; tile < ntiles; tile += (int64_t)gridDim.x * 2) {
+        const int64_t it = tile * 128 + t;
+        const bool valid = it < total;
+        const int64_t fi = valid ? it / n : 0;
+        const int v = valid ? (int)(it - fi * n) : 0;
+        const int64_t b = a.frame_list ? a.frame_list[fi] : fi;
+        float f1 = 0.0f, f2 = 0.0f, f3 = 0.0f, hcx[DV], hcz[DV];
+#pragma unroll
+        for (int k = 0; k < DV; k++) { hcx[k] = 0.0f; hcz[k] = 0.0f; }
+        if (valid) {
+            f1 = a.h_vn(b, v, 0); f2 = a.h_vn(b, v, 1); f3 = a.h_vn(b, v, 2);
+#pragma unroll
+            for (int k = 0; k < DV; k++) {
+                const int cx = a.X.vn_cn[v * DV + k], cz = a.Z.vn_cn[v * DV + k];
+                const float lx = a.logit_hx(cx, b), lz = a.logit_hz(cz, b);
+                hcx[k] = a.sx(cx, b) ? -lx : lx;
+                hcz[k] = a.sz(cz, b) ? -lz : lz;
+            }
+        }
+        float mm[2 * M];
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            gnn_edges_tc<DV, MATH>(g, ws + (side ? Lay::W1tz : Lay::W1tx), ws + (side ? Lay::b1z : Lay::b1x),
+                                   side ? hcz : hcx, f1, f2, f3);
+            gemm(g, 0, H, H, 80, sbase + 4 * (side ? GnnW::W2Z : GnnW::W2X), 32, false);
+            const float *b2 = ws + (side ? Lay::b2z : Lay::b2x);
+#pragma unroll
+            for (int c0 = 0; c0 < 24; c0 += 8) {
+                float d[8];
+                tmem_ld8(g.lane_base + 80 + c0, d);
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (c0 + q < M) {
+                        const float r = (a.reduce == 0) ? FB_ADD(FB_DIV(d[q], dg), b2[c0 + q]) : FB_FMA(dg, b2[c0 + q], d[q]);
+                        if (side == 0) mm[c0 + q] = r;
+                        else mm[M + c0 + q] = r;
+                    }
+                }
+            }
+        }
+        store_a<2 * M>(g, 0, 2 * M, mm);
+        gemm(g, 0, 2 * M, 2 * M, 80, sbase + 4 * GnnW::W3AB, 48, false);
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < H; c0 += 8) {
+            float d[8];
+            tmem_ld8(g.lane_base + 80 + c0, d);
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int j = c0 + q;
+                float h = FB_FMA(f1, ws[Lay::W3 + (2 * M) * H + j], d[q]);
+                h = FB_FMA(f2, ws[Lay::W3 + (2 * M + 1) * H + j], h);
+                h = FB_FMA(f3, ws[Lay::W3 + (2 * M + 2) * H + j], h);
+                h = MATH::tanh(FB_ADD(h, ws[Lay::b3 + j]));
+                o0 = FB_FMA(h, ws[Lay::W0 + j * 3 + 0], o0);
+                o1 = FB_FMA(h, ws[Lay::W0 + j * 3 + 1], o1);
+                o2 = FB_FMA(h, ws[Lay::W0 + j * 3 + 2], o2);
+            }
+        }
+        if (valid) {
+            a.out(b, v, 0) = FB_ADD(o0, ws[Lay::b0 + 0]);
+            a.out(b, v, 1) = FB_ADD(o1, ws[Lay::b0 + 1]);
+            a.out(b, v, 2) = FB_ADD(o2, ws[Lay::b0 + 2]);
+        }
+    }
+    cta_teardown(&tslot);
+}
+
+}  // namespace tc
+}  // namespace fbgnn
+
+#endif  // FBGNN_GNN_TC_CUH

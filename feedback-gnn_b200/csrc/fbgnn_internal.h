@@ -98,6 +98,8 @@ struct fbgnn_gnn {
     float *weights = nullptr;      // packed GnnLayout<H,M> (layers == 2) or the layer sequence of k_gnn_deep
     int total = 0;
     int layers = 2;                // num_mlp_layers
+    float *w_tc = nullptr;         // tensor-core operand tiles + scalar block (tc::GnnW), H = 40 / M = 20 only
+    int gemm = FBGNN_GEMM_FMA;     // FBGNN_GEMM_*: how the dense products of the node update are evaluated
 };
 
 

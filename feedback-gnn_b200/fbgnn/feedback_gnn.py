@@ -41,7 +41,14 @@ class Feedback_GNN:
                  reduce_op="mean",
                  activation="tanh",
                  use_bias=False,
-                 ctx=None):
+                 ctx=None,
+                 gemm="fma"):
+        """``gemm`` (extension): "fma" (default; bit-exact against the oracle) or "tf32x3" -- the dense products of the
+        node update on the tcgen05 tensor cores (csrc/fbgnn_gnn_tc.cuh): float32 re-association accuracy, not
+        bit-identical; built for the shipped configuration (20 / 40, two layers, tanh, mean or sum, (3,.)-regular codes)."""
+        if gemm not in ("fma", "tf32x3"):
+            raise ValueError("gemm must be 'fma' or 'tf32x3'")
+        self._gemm = gemm
         self._code = code
         self._num_cn_x, self._num_vn = code.hx.shape
         self._num_cn_z = code.hz.shape[0]
@@ -132,6 +139,8 @@ class Feedback_GNN:
         ent = self._handles.get(id(ctx))          # one device copy of the weights per context (GPU)
         if (ent is None or ent[0] is not ctx) and self._num_mlp_layers != 2:
             import ctypes as C
+            if self._gemm != "fma":
+                raise _ffi.FbgnnError("the tensor-core form of the feedback GNN is built for 2-layer MLPs")
             packed = []
             step = 2 if self._use_bias else 1
             for i in range(0, len(self._weights), step):
@@ -156,6 +165,8 @@ class Feedback_GNN:
             _ffi.call("fbgnn_gnn_create", ctx.handle, self._num_hidden_units, self._num_msg_dims,
                       ACTS[self._activation], REDUCE[self._reduce_op],
                       *[fp(a) for a in (W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3)], C.byref(h))
+            if self._gemm == "tf32x3":
+                _ffi.call("fbgnn_gnn_set_gemm", h, 1)
             self._handles[id(ctx)] = (ctx, h)
         return self._handles[id(ctx)][1]
 

@@ -244,6 +244,11 @@ int fbgnn_gnn_create(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t activation, i
 int fbgnn_gnn_create_deep(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t num_mlp_layers, int32_t activation,
                           int32_t reduce_op, int32_t use_bias, const float *packed, int64_t count, fbgnn_gnn **gnn);
 int fbgnn_gnn_destroy(fbgnn_gnn *gnn);
+/* Select how the dense products of the node update (hidden sums x W2x / W2z, messages x W3) are evaluated (FBGNN_GEMM_*).
+ * FBGNN_GEMM_TF32X3 runs them on the tcgen05 tensor cores with the three-product TF32 split (csrc/fbgnn_gnn_tc.cuh):
+ * float32 re-association accuracy, NOT bit-identical to the default FMA form / the oracle.  Built for H = 40, M = 20,
+ * 2-layer MLPs, tanh, reduce_op mean / sum and (3, .)-regular codes; otherwise FBGNN_E_UNSUPPORTED. */
+int fbgnn_gnn_set_gemm(fbgnn_gnn *gnn, int32_t mode);
 /* Feedback_GNN.call.  h_vn float32 (b, v, k); logit_hx (row of hx, b), logit_hz (row of hz, b);
  * synd_x/z uint8 (c, b); out float32 (b, v, k). */
 int fbgnn_gnn_forward(fbgnn_code *code, fbgnn_gnn *gnn, int64_t B, fbgnn_tensor3 h_vn,

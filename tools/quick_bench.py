@@ -12,7 +12,8 @@ def make(code_name, nG, skip=False):
     else:
         code = F.create_QC_GHP_codes(63, F.create_cyclic_permuting_matrix(7, [27,54,0]), [0,1,6])
         wf = "feedback_GNN_n882_k24_wt_4_60_iter_64_16_mixed.npy"
-    G = F.Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, reduce_op="mean", activation="tanh", use_bias=True)
+    G = F.Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, reduce_op="mean", activation="tanh", use_bias=True,
+                       gemm=os.environ.get("FBGNN_LAB_GNN_GEMM", "fma"))
     F.load_weights(G, os.path.join(F.WEIGHTS_DIR, wf))
     d1 = F.QLDPCBPDecoder(code, num_iter=64, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
     d2 = F.QLDPCBPDecoder(code, num_iter=16, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
