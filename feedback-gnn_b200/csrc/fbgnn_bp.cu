@@ -137,7 +137,8 @@ int launch_bp4(fbgnn_ctx *ctx, const Bp4Args &a_in, int64_t grid) {
     Bp4Args a = a_in;
     a.stats = ctx->stats;
     const bool cp = a.llr.ptr == nullptr;
-    const size_t smem = bp4_smem(a.X, a.Z, cp, a.iter_logits.ptr != nullptr);
+    static const size_t smem_pad = getenv("FBGNN_BP4_SMEM_PAD") ? (size_t)atoi(getenv("FBGNN_BP4_SMEM_PAD")) : 0;   // lab knob
+    const size_t smem = bp4_smem(a.X, a.Z, cp, a.iter_logits.ptr != nullptr) + smem_pad;
     int threads = pick_threads(a.X.n, a.X.m + a.Z.m);
     if (const char *t = getenv("FBGNN_BP4_THREADS")) threads = std::max(32, std::min(512, atoi(t) / 32 * 32));   // lab knob
     if (smem > ctx->smem_optin) {
