@@ -19,7 +19,8 @@ static int pick_threads(int n_items_a, int n_items_b) {
 static size_t bp4_smem(const SideDev &X, const SideDev &Z, bool const_prior, bool iter_logits) {
     const size_t np = (size_t)pad4(X.n);
     return sizeof(float) * ((size_t)X.E + Z.E + ((const_prior ? 2 : 3) + (iter_logits ? 2 : 0)) * np) +
-           (size_t)pad16(X.m + Z.m) + 2 * (((size_t)X.n + 1) & ~(size_t)1) + X.n + 16;
+           (size_t)pad16(X.m + Z.m) + 2 * (((size_t)X.n + 1) & ~(size_t)1) + X.n + 16 +
+           (FBGNN_SMEM_TABLES ? 2 * ((size_t)X.E + Z.E) + 32 : 0);
 }
 
 template <bool CP, int DV, int DC, typename MATH, bool FPX>

@@ -114,6 +114,9 @@ struct MathSfu {
 #ifndef FBGNN_SIGNBITS
 #define FBGNN_SIGNBITS 1           // quaternary check nodes: sign parity as an XOR of the message words (lab: 0 = comparisons)
 #endif
+#ifndef FBGNN_SMEM_TABLES
+#define FBGNN_SMEM_TABLES 0        // lab: check-side edge tables in shared memory instead of global memory behind L1
+#endif
 #ifndef FBGNN_UNIFORM
 #define FBGNN_UNIFORM 1            // regular fast path: warp-uniform node loops, full-mask votes
 #endif
@@ -595,6 +598,14 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     float *mz = mx + X.E, *scr2 = mz + Z.E;
     uint16_t *rec = GSTATE ? (uint16_t *)(sbx + mp) : (uint16_t *)(scr2 + (a.iter_logits.ptr ? 2 * np : 0));
     uint8_t *dec = (uint8_t *)(rec + ((n + 1) & ~1));
+#if FBGNN_SMEM_TABLES       // lab: the check-side edge tables copied into shared memory (north star "edge lists in shared memory")
+    idx_t *tabx = (idx_t *)(dec + ((n + 15) & ~15)), *tabz = tabx + X.E;
+    for (int e = tid; e < X.E; e += T) tabx[e] = X.cn_edge[e];
+    for (int e = tid; e < Z.E; e += T) tabz[e] = Z.cn_edge[e];
+    const idx_t *cn_edge_x = tabx, *cn_edge_z = tabz;
+#else
+    const idx_t *cn_edge_x = X.cn_edge, *cn_edge_z = Z.cn_edge;
+#endif
 
     // per-frame inputs: the pipeline's workspace rows are 16-byte aligned blocks -> two bulk-async (TMA) copies posted by one
     // thread, overlapped with the clearing of the messages; the layer API's strided views are read element by element
@@ -678,10 +689,10 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
                 const int cc = isx ? c : c - X.m;
                 if ((c | 31) < mt)
                     stable &= cn_phi_regular<(DC > 0 ? DC : 1), (DV > 0 ? DV : 1), true, MATH, FPX, true>(
-                        isx ? X.cn_edge : Z.cn_edge, cc, isx ? mx : mz, isx ? sbx[cc] : sbz[cc], a.factor, recp, isx ? 0 : DV);
+                        isx ? cn_edge_x : cn_edge_z, cc, isx ? mx : mz, isx ? sbx[cc] : sbz[cc], a.factor, recp, isx ? 0 : DV);
                 else
                     stable &= cn_phi_regular<(DC > 0 ? DC : 1), (DV > 0 ? DV : 1), true, MATH, FPX, false>(
-                        isx ? X.cn_edge : Z.cn_edge, cc, isx ? mx : mz, isx ? sbx[cc] : sbz[cc], a.factor, recp, isx ? 0 : DV);
+                        isx ? cn_edge_x : cn_edge_z, cc, isx ? mx : mz, isx ? sbx[cc] : sbz[cc], a.factor, recp, isx ? 0 : DV);
             }
         } else
         for (int c = tid; c < X.m + Z.m; c += T) {
@@ -691,7 +702,7 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
             const int sb = isx ? sbx[cc] : sbz[cc];
             if (fast) {
                 stable &= cn_phi_regular<(DC > 0 ? DC : 1), (DV > 0 ? DV : 1), true, MATH, FPX>(
-                    isx ? X.cn_edge : Z.cn_edge, cc, msg, sb, a.factor, recp, isx ? 0 : DV);
+                    isx ? cn_edge_x : cn_edge_z, cc, msg, sb, a.factor, recp, isx ? 0 : DV);
             } else {
                 const SideDev &S = isx ? X : Z;
                 cn_update_one<true, MATH>(S.cn_edge, S.cn_ptr[cc], S.cn_ptr[cc + 1], msg, sb, a.cn_type, a.factor);
