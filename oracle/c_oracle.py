@@ -50,7 +50,7 @@ class _Rows(C.Structure):
 class _Gnn(C.Structure):
     _fields_ = [("H", C.c_int32), ("M", C.c_int32), ("act", C.c_int32), ("reduce", C.c_int32)] + \
                [(k, C.c_void_p) for k in ("W0", "b0", "W1x", "b1x", "W2x", "b2x",
-                                          "W1z", "b1z", "W2z", "b2z", "W3", "b3")]
+                                          "W1z", "b1z", "W2z", "b2z", "W3", "b3")] + [("gemm", C.c_int32)]
 
 
 class _PipeCfg(C.Structure):
@@ -159,7 +159,9 @@ class Rows:
 class Gnn:
     """Weights in Keras ``get_weights()`` order."""
 
-    def __init__(self, weights, activation="tanh", reduce_op="mean", use_bias=True):
+    def __init__(self, weights, activation="tanh", reduce_op="mean", use_bias=True, gemm="fma"):
+        """gemm="tf32x3": the tensor-core form of the layer (csrc/fbgnn_gnn_tc.cuh), its tcgen05.mma steps emulated
+        exactly by csrc/fb_umma.h."""
         w = [_f32(a) for a in weights]
         if use_bias:
             (W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3) = w
@@ -169,7 +171,10 @@ class Gnn:
         self.keep = [W0, b0, W1x, b1x, W2x, b2x, W1z, b1z, W2z, b2z, W3, b3]
         H, M = W2x.shape
         assert W1x.shape == (4, H) and W3.shape == (2 * M + 3, H) and W0.shape == (H, 3)
-        self.c = _Gnn(H, M, ACTS[activation], REDUCE[reduce_op], *[_p(a) for a in self.keep])
+        assert gemm in ("fma", "tf32x3")
+        if gemm == "tf32x3":
+            assert activation == "tanh" and reduce_op in ("mean", "sum") and H % 8 == 0 and (2 * M) % 8 == 0
+        self.c = _Gnn(H, M, ACTS[activation], REDUCE[reduce_op], *[_p(a) for a in self.keep], 1 if gemm == "tf32x3" else 0)
 
 
 class _GnnD(C.Structure):

@@ -41,6 +41,7 @@
 #include <omp.h>
 #endif
 #include "fb_math.h"
+#include "fb_umma.h"
 
 #define ORC_CN_PHI    0
 #define ORC_CN_TANH   1
@@ -70,6 +71,7 @@ typedef struct {             /* Feedback_GNN weights, Keras get_weights() order 
     const float *W2x, *b2x;  /* [H,M], [M]     vn_msg_mlp_x layer 1                         */
     const float *W1z, *b1z, *W2z, *b2z;
     const float *W3, *b3;    /* [2M+3,H], [H]  vn_embed_mlp                                 */
+    int32_t gemm;            /* 0: FP32 FMAs; 1: the tensor-core form (fbgnn_gnn_tc.cuh), see gnn_frame_tc */
 } orc_gnn_t;
 
 /* ---------------------------------------------------------------- Philox4x32-10 ---- */
@@ -602,6 +604,11 @@ static void gnn_side(const orc_side_t *S, const orc_gnn_t *G, const float *W1, c
     }
 }
 
+static void gnn_frame_tc(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t *G,
+                         const float *Lx, const float *Ly, const float *Lz, const float *logit_hx,
+                         const float *logit_hz, const uint8_t *sx, const uint8_t *sz,
+                         float *ox, float *oy, float *oz);
+
 /* One frame of Feedback_GNN.call.  logit_hx [m_x] pairs with hx rows, logit_hz [m_z] with hz
  * rows (the caller passes the decoder's z_logit and x_logit, feedback_gnn.py:335). */
 static void gnn_frame(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t *G,
@@ -609,6 +616,7 @@ static void gnn_frame(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t 
                       const float *logit_hz, const uint8_t *sx, const uint8_t *sz,
                       float *ox, float *oy, float *oz, float *work) {
     const int n = X->n, H = G->H, M = G->M;
+    if (G->gemm == 1) { gnn_frame_tc(X, Z, G, Lx, Ly, Lz, logit_hx, logit_hz, sx, sz, ox, oy, oz); return; }
     float *hcx = work, *hcz = hcx + X->m, *in = hcz + Z->m, *hid = in + 2 * M + 3, *msg = hid + H;
     for (int c = 0; c < X->m; c++) hcx[c] = FB_MUL(logit_hx[c], sx[c] ? -1.0f : 1.0f);
     for (int c = 0; c < Z->m; c++) hcz[c] = FB_MUL(logit_hz[c], sz[c] ? -1.0f : 1.0f);
@@ -632,6 +640,70 @@ static void gnn_frame(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t 
         }
         ox[v] = o[0]; oy[v] = o[1]; oz[v] = o[2];
     }
+}
+
+/* The tensor-core form of Feedback_GNN.call, operation by operation as csrc/fbgnn_gnn_tc.cuh evaluates it: the first
+ * layers of the edge MLPs, tanh and the 3-wide output layer in float32 FMAs in the kernel's order; the three dense
+ * products (hidden sums x W2x / W2z, messages x W3[0:2M]) as tcgen05.mma kind::tf32 steps on TF32 hi / lo splits,
+ * emulated exactly by fb_umma.h.  tanh, reduce_op mean / sum, H and 2M multiples of 8. */
+static void gnn_frame_tc(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t *G,
+                         const float *Lx, const float *Ly, const float *Lz, const float *logit_hx,
+                         const float *logit_hz, const uint8_t *sx, const uint8_t *sz,
+                         float *ox, float *oy, float *oz) {
+    const int n = X->n, H = G->H, M = G->M;
+    float *w2h[2], *w2l[2];
+    float *w3h = (float *)malloc(sizeof(float) * 2 * (size_t)(2 * M) * H), *w3l = w3h + (size_t)(2 * M) * H;
+    for (int sd = 0; sd < 2; sd++) {
+        const float *W2 = sd ? G->W2z : G->W2x;
+        w2h[sd] = (float *)malloc(sizeof(float) * 2 * (size_t)H * M); w2l[sd] = w2h[sd] + (size_t)H * M;
+        for (int i = 0; i < H * M; i++) { w2h[sd][i] = fb_tf32_hi(W2[i]); w2l[sd][i] = FB_SUB(W2[i], w2h[sd][i]); }
+    }
+    for (int i = 0; i < 2 * M * H; i++) { w3h[i] = fb_tf32_hi(G->W3[i]); w3l[i] = FB_SUB(G->W3[i], w3h[i]); }
+    float *hi = (float *)malloc(sizeof(float) * 2 * (size_t)(H > 2 * M ? H : 2 * M)), *lo = hi + (H > 2 * M ? H : 2 * M);
+    float *mm = (float *)malloc(sizeof(float) * 2 * (size_t)M);
+    for (int v = 0; v < n; v++) {
+        const float f1 = Lx[v], f2 = Ly[v], f3 = Lz[v];
+        for (int sd = 0; sd < 2; sd++) {
+            const orc_side_t *S = sd ? Z : X;
+            const float *W1 = sd ? G->W1z : G->W1x, *b1 = sd ? G->b1z : G->b1x, *b2 = sd ? G->b2z : G->b2x;
+            const float *logit = sd ? logit_hz : logit_hx;
+            const uint8_t *sy = sd ? sz : sx;
+            const int e0 = S->vn_ptr[v], e1 = S->vn_ptr[v + 1];
+            const float dg = (float)(e1 - e0);
+            for (int j = 0; j < H; j++) {
+                const float base = FB_ADD(FB_FMA(f3, W1[3 * H + j], FB_FMA(f2, W1[2 * H + j], FB_FMA(f1, W1[H + j], 0.0f))),
+                                          b1 ? b1[j] : 0.0f);
+                float hs = 0.0f;
+                for (int e = e0; e < e1; e++) {
+                    const int c = S->vn_cn[e];
+                    const float hc = sy[c] ? -logit[c] : logit[c];
+                    hs = FB_ADD(hs, gnn_act(G->act, FB_FMA(hc, W1[j], base)));
+                }
+                hi[j] = fb_tf32_hi(hs); lo[j] = FB_SUB(hs, hi[j]);
+            }
+            for (int i = 0; i < M; i++) {
+                const float d = fb_umma_dot3(hi, lo, w2h[sd] + i, w2l[sd] + i, M, H);
+                const float bb = b2 ? b2[i] : 0.0f;
+                mm[sd * M + i] = (G->reduce == 0) ? FB_ADD(FB_DIV(d, dg), bb) : FB_FMA(dg, bb, d);
+            }
+        }
+        for (int k = 0; k < 2 * M; k++) { hi[k] = fb_tf32_hi(mm[k]); lo[k] = FB_SUB(mm[k], hi[k]); }
+        float o0 = 0.0f, o1 = 0.0f, o2 = 0.0f;
+        for (int j = 0; j < H; j++) {
+            const float d = fb_umma_dot3(hi, lo, w3h + j, w3l + j, H, 2 * M);
+            float h = FB_FMA(f1, G->W3[(2 * M) * H + j], d);
+            h = FB_FMA(f2, G->W3[(2 * M + 1) * H + j], h);
+            h = FB_FMA(f3, G->W3[(2 * M + 2) * H + j], h);
+            h = gnn_act(G->act, FB_ADD(h, G->b3 ? G->b3[j] : 0.0f));
+            o0 = FB_FMA(h, G->W0[j * 3 + 0], o0);
+            o1 = FB_FMA(h, G->W0[j * 3 + 1], o1);
+            o2 = FB_FMA(h, G->W0[j * 3 + 2], o2);
+        }
+        ox[v] = FB_ADD(o0, G->b0 ? G->b0[0] : 0.0f);
+        oy[v] = FB_ADD(o1, G->b0 ? G->b0[1] : 0.0f);
+        oz[v] = FB_ADD(o2, G->b0 ? G->b0[2] : 0.0f);
+    }
+    free(w2h[0]); free(w2h[1]); free(w3h); free(hi); free(mm);
 }
 
 static size_t gnn_work_floats(const orc_side_t *X, const orc_side_t *Z, const orc_gnn_t *G) {
@@ -1332,4 +1404,22 @@ void orc_set_num_threads(int t) {
 #else
     (void)t;
 #endif
+}
+
+
+/* ---------------------------------------------------------------- tensor-core step model ---------------- */
+/* Replays a dump of tools/micro/umma_probe.cu (A [T,128,8], B [T,8,16], Din / Dout [T,128,16]) through fb_umma8 and
+ * returns the number of outputs whose bits differ from the hardware's. */
+int64_t orc_umma8_check(const float *A, const float *B, const float *Din, const float *Dout, int32_t trials) {
+    int64_t bad = 0;
+    for (int tr = 0; tr < trials; tr++)
+        for (int m = 0; m < 128; m++)
+            for (int n = 0; n < 16; n++) {
+                const float got = fb_umma8(Din[((int64_t)tr * 128 + m) * 16 + n], 1, A + ((int64_t)tr * 128 + m) * 8,
+                                           B + (int64_t)tr * 128 + n, 16);
+                uint32_t g, w;
+                memcpy(&g, &got, 4); memcpy(&w, &Dout[((int64_t)tr * 128 + m) * 16 + n], 4);
+                bad += g != w;
+            }
+    return bad;
 }

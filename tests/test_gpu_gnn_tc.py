@@ -1,6 +1,7 @@
-"""Feedback GNN with its dense products on the tcgen05 tensor cores (``gemm="tf32x3"``, csrc/fbgnn_gnn_tc.cuh): an opt-in
-form that agrees with the default FMA kernel / the oracle to float32 re-association accuracy, not bit for bit.  The
-tolerance is stated here: 1e-5 of the largest output per call (north star: FP32 quantities within 1e-5 relative)."""
+"""Feedback GNN with its dense products on the tcgen05 tensor cores (``gemm="tf32x3"``, csrc/fbgnn_gnn_tc.cuh).  The
+arithmetic of a tcgen05.mma kind::tf32 step is an integer model characterised on a B200 (csrc/fb_umma.h,
+tests/test_umma_model.py), so the CPU oracle reproduces this form BIT FOR BIT too (oracle.Gnn(gemm="tf32x3")); against
+the FMA form it agrees to float32 re-association accuracy (1e-5 of the largest output is the stated tolerance)."""
 import os
 
 import numpy as np
@@ -33,10 +34,17 @@ def test_gnn_tensor_core_form_within_tolerance(codes, c1270, oracle, weights, na
             G.set_weights(weights[name])
             outs[gemm] = np.asarray(G((h_vn, lhx, lhz, sx, sz)))
         with oracle.math(arith):
-            ref = oracle.gnn(oracle.CodeGraph(code), oracle.Gnn(weights[name], "tanh", reduce_op), h_vn, lhx, lhz, sx, sz)
+            g = oracle.CodeGraph(code)
+            ref = oracle.gnn(g, oracle.Gnn(weights[name], "tanh", reduce_op), h_vn, lhx, lhz, sx, sz)
+            nt = min(B, 40)                                                         # the emulation is slow: a slice
+            ref_tc = oracle.gnn(g, oracle.Gnn(weights[name], "tanh", reduce_op, gemm="tf32x3"), h_vn[:nt],
+                                np.ascontiguousarray(lhx[:, :nt]), np.ascontiguousarray(lhz[:, :nt]),
+                                np.ascontiguousarray(sx[:, :nt]), np.ascontiguousarray(sz[:, :nt]))
     finally:
         ctx.set_math("exact")
     assert np.array_equal(outs["fma"].view(np.uint32), ref.view(np.uint32))          # the default stays bit-exact
+    assert np.array_equal(outs["tf32x3"][:nt].view(np.uint32), ref_tc.view(np.uint32)), \
+        f"tensor-core form differs from its oracle on {int(np.sum(outs['tf32x3'][:nt] != ref_tc))} values"
     scale = float(np.abs(ref).max())
     err = float(np.abs(outs["tf32x3"] - ref).max())
     assert err <= 1e-5 * scale, (err, scale)
@@ -80,3 +88,56 @@ def test_pipeline_with_tensor_core_gnn_tracks_the_bit_exact_pipeline(codes, orac
     assert agree > 0.985, agree
     ka, kb = res["fma"][1][2], res["tf32x3"][1][2]
     assert abs(ka - kb) <= 4.0 * np.sqrt(max(ka, kb, 1)) + 5, (ka, kb)
+
+
+@pytest.mark.parametrize("arith", ["exact", "sfu"])
+def test_pipeline_with_tensor_core_gnn_bitexact(codes, oracle, weights, arith):
+    """BP -> (GNN -> BP) x 2 with the tensor-core GNN against the oracle pipeline with the emulated tensor-core GNN:
+    per-frame flags, residual errors and counters bit for bit."""
+    import fbgnn as F
+    code = codes["c882"]
+    w = weights["c882"]
+    ctx = F.default_context()
+    ctx.set_math(arith)
+    try:
+        G = F.Feedback_GNN(code, 20, 40, 2, "mean", "tanh", True, gemm="tf32x3")
+        G.set_weights(w)
+        d1 = F.QLDPCBPDecoder(code, num_iter=24, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+        d2 = F.QLDPCBPDecoder(code, num_iter=8, normalization_factor=0.9, cn_type="boxplus-phi", stage_one=True)
+        model = F.Sandwich_BP_GNN_Evaluation_Model(code, [d1, d2, d2], [G, G], num_layers=3, seed=7, first_frame=1000)
+        B, p = 128, 0.12
+        res = model.run(B, p, want_counters=True)
+        with oracle.math(arith):
+            ref = oracle.pipeline(oracle.CodeGraph(code), [24, 8, 8], [oracle.Gnn(w, gemm="tf32x3")] * 2, p, p0=0.05,
+                                  factors=[1.0, 0.9, 0.9], seed=7, first_frame=1000, B=B, skip_inactive=False, want_diff=True)
+    finally:
+        ctx.set_math("exact")
+    assert np.array_equal(res["flags"].numpy(), ref["flags"])
+    assert np.array_equal(res["x_diff"].numpy(), ref["x_diff"]) and np.array_equal(res["z_diff"].numpy(), ref["z_diff"])
+    assert np.array_equal(res["counters"], ref["counters"])
+
+
+def test_headline_pipeline_with_tensor_core_gnn_bitexact(c1270, oracle, weights):
+    """The bench configuration -- [[1270,28]], BP64 -> (GNN -> BP16) x 3, p = 0.10, SFU arithmetic, tensor-core GNN --
+    frame by frame against the oracle (MUFU tables + emulated tensor-core steps)."""
+    import fbgnn as F
+    w = weights["c1270"]
+    ctx = F.default_context()
+    ctx.set_math("sfu")
+    try:
+        G = F.Feedback_GNN(c1270, 20, 40, 2, "mean", "tanh", True, gemm="tf32x3")
+        G.set_weights(w)
+        d1 = F.QLDPCBPDecoder(c1270, num_iter=64, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+        d2 = F.QLDPCBPDecoder(c1270, num_iter=16, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
+        model = F.Sandwich_BP_GNN_Evaluation_Model(c1270, [d1, d2, d2, d2], [G] * 3, num_layers=4, seed=2, first_frame=5000)
+        B, p = 96, 0.10
+        res = model.run(B, p, want_counters=True)
+        with oracle.math("sfu"):
+            ref = oracle.pipeline(oracle.CodeGraph(c1270), [64, 16, 16, 16], [oracle.Gnn(w, gemm="tf32x3")] * 3, p, p0=0.05,
+                                  seed=2, first_frame=5000, B=B, skip_inactive=False, want_diff=True)
+    finally:
+        ctx.set_math("exact")
+    assert np.array_equal(res["flags"].numpy(), ref["flags"])
+    assert np.array_equal(res["x_diff"].numpy(), ref["x_diff"]) and np.array_equal(res["z_diff"].numpy(), ref["z_diff"])
+    assert np.array_equal(res["counters"], ref["counters"])
+    assert int(ref["counters"][3]) > 10                      # frames did reach the GNN rounds

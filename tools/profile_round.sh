@@ -3,7 +3,7 @@
 #   profile_round.sh sfu|exact : ncu --set full capture of the hot kernels at the bench's B = 32768 in that arithmetic
 #   profile_round.sh bench     : launch list of the bench command (durations only) + the bench line itself
 case "$1" in
-sfu)   timeout 900 ncu --set full --clock-control none -k regex:'k_bp4|k_gnn' -s 3 -c 3 -o gpurun_out/r02_headline_sfu -f \
+sfu)   FBGNN_LAB_GNN_GEMM=tf32x3 timeout 900 ncu --set full --clock-control none -k regex:'k_bp4|k_gnn' -s 3 -c 3 -o gpurun_out/r02_headline_sfu -f \
            python tools/prof_run_sfu.py 32768 1 > /dev/null 2>&1 ;;
 exact) timeout 900 ncu --set full --clock-control none -k regex:'k_bp4|k_gnn' -s 3 -c 3 -o gpurun_out/r02_headline_exact -f \
            python tools/prof_run.py 32768 1 > /dev/null 2>&1 ;;
