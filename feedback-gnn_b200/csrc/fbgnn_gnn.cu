@@ -75,6 +75,16 @@ extern "C" int fbgnn_gnn_set_gemm(fbgnn_gnn *g, int32_t mode) {
     return 0;
 }
 
+extern "C" int fbgnn_umma_probe(fbgnn_ctx *ctx, const float *A, const float *B, const float *Din, float *Dout, int32_t trials) {
+    REQUIRE(ctx && A && B && Din && Dout && trials >= 0, "bad argument");
+    if (set_device(ctx)) return FBGNN_E_CUDA;
+    if (trials == 0) return 0;
+    tc::k_umma_probe<<<1, 128, 0, ctx->stream>>>(A, B, Din, Dout, trials);
+    CK(cudaGetLastError());
+    ctx->launches++;
+    return 0;
+}
+
 extern "C" int fbgnn_gnn_create_deep(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t num_mlp_layers, int32_t activation,
                                      int32_t reduce_op, int32_t use_bias, const float *packed, int64_t count,
                                      fbgnn_gnn **out) {

@@ -105,6 +105,7 @@ _SIGNATURES = {
     "fbgnn_gbp_destroy": [C.c_void_p],
     "fbgnn_gbp_set_gemm": [C.c_void_p, C.c_int32],
     "fbgnn_gnn_set_gemm": [C.c_void_p, C.c_int32],
+    "fbgnn_umma_probe": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32],
     "fbgnn_gbp_set_chunk": [C.c_void_p, C.c_int64],
     "fbgnn_second_stage_grad": [C.c_void_p, C.c_void_p, C.c_int32, C.c_float, C.c_int32, C.c_int64, Tensor3, Tensor2,
                                 Tensor2, Tensor2, Tensor2, C.c_int32, C.POINTER(C.c_double), C.POINTER(C.c_float)],

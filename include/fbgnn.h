@@ -382,6 +382,9 @@ int fbgnn_fma_peak(fbgnn_ctx *ctx, double *instr_per_s);
  * "softplus","phi4","phi2","tanh","atanh"} (exact arithmetic), {"sfu_exp","sfu_log","sfu_softplus","sfu_phi4","sfu_phi2"}
  * "sfu_tanh","sfu_atanh" (SFU arithmetic) and the raw hardware functions {"mufu_ex2","mufu_lg2","mufu_rcp"} (tools/dump_sfu_tables.py); x,y device float32 [n]. */
 int fbgnn_math_probe(fbgnn_ctx *ctx, const char *fn, const float *x, float *y, int64_t n);
+/* Probe of one tcgen05.mma kind::tf32 step (M = 128, N = 16, K = 8) on `trials` operand sets: Dout = A B + Din with device
+ * float32 A [T,128,8], B [T,8,16], Din / Dout [T,128,16] -- tests compare it with the integer model of csrc/fb_umma.h. */
+int fbgnn_umma_probe(fbgnn_ctx *ctx, const float *A, const float *B, const float *Din, float *Dout, int32_t trials);
 
 #ifdef __cplusplus
 }

@@ -141,3 +141,39 @@ def test_headline_pipeline_with_tensor_core_gnn_bitexact(c1270, oracle, weights)
     assert np.array_equal(res["x_diff"].numpy(), ref["x_diff"]) and np.array_equal(res["z_diff"].numpy(), ref["z_diff"])
     assert np.array_equal(res["counters"], ref["counters"])
     assert int(ref["counters"][3]) > 10                      # frames did reach the GNN rounds
+
+
+def test_this_gpus_tensor_core_is_the_model(oracle):
+    """One tcgen05.mma kind::tf32 step on fresh random operands (TF32-exact and full 24-bit significands, exponents over
+    2^-14 .. 2^14, with and without accumulator, sparse rows): the GPU the tests run on returns, on every one of the
+    262 144 outputs, the bits of the integer model the repository carries (csrc/fb_umma.h)."""
+    import ctypes as C
+    import fbgnn as F
+    from fbgnn import _ffi
+    ctx = F.default_context()
+    rng = np.random.default_rng(2026)
+    T = 128
+
+    def rnd(shape, bits, span):
+        e = rng.integers(-span, span + 1, shape)
+        m = (1 << (bits - 1)) + rng.integers(0, 1 << (bits - 1), shape)
+        v = np.ldexp(m.astype(np.float64), e - (bits - 1)) * rng.choice([-1.0, 1.0], shape)
+        return v.astype(np.float32)
+
+    A = np.empty((T, 128, 8), np.float32); B = np.empty((T, 8, 16), np.float32); Din = np.zeros((T, 128, 16), np.float32)
+    for tr in range(T):
+        span = 14 if tr & 1 else 2
+        bits = 24 if (tr >> 2) & 1 else 11
+        A[tr], B[tr] = rnd((128, 8), bits, span), rnd((8, 16), bits, span)
+        if tr & 2:
+            Din[tr] = rnd((128, 16), 24, 2 * span)
+        if tr % 16 == 9:
+            A[tr][rng.random((128, 8)) < 0.3] = 0.0
+    dA, dB, dD = ctx.asarray(A), ctx.asarray(B), ctx.asarray(Din)
+    dO = ctx.empty((T, 128, 16), np.float32)
+    _ffi.call("fbgnn_umma_probe", ctx.handle, dA.ptr, dB.ptr, dD.ptr, dO.ptr, T)
+    out = np.ascontiguousarray(dO.numpy())
+    L = oracle.lib()
+    L.orc_umma8_check.restype = C.c_int64
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    assert L.orc_umma8_check(p(A), p(B), p(Din), p(out), C.c_int32(T)) == 0
