@@ -54,8 +54,11 @@ extern "C" int fbgnn_gnn_create(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t ac
                     tv[off + kpad * npad + tc::b_tile_offset(nn, k, kpad)] = x - hi;
                 }
         };
-        tile(GnnW::W2X, 40, 32, [&](int k, int nn) { return nn < 20 ? W2x[k * 20 + nn] : 0.0f; });
-        tile(GnnW::W2Z, 40, 32, [&](int k, int nn) { return nn < 20 ? W2z[k * 20 + nn] : 0.0f; });
+        // reduce_op mean: the division by the node degree (3: this form is built for (3,.)-regular codes) is folded into
+        // the tiles as a multiplication by float32(1/3); the oracle's tensor-core form scales W2 the same way
+        const float inv = reduce_op == 0 ? 1.0f / 3.0f : 1.0f;
+        tile(GnnW::W2X, 40, 32, [&](int k, int nn) { return nn < 20 ? W2x[k * 20 + nn] * inv : 0.0f; });
+        tile(GnnW::W2Z, 40, 32, [&](int k, int nn) { return nn < 20 ? W2z[k * 20 + nn] * inv : 0.0f; });
         tile(GnnW::W3AB, 40, 48, [&](int k, int nn) { return nn < 40 ? W3[k * 40 + nn] : 0.0f; });
         std::memcpy(&tv[GnnW::SCALAR], w.data(), sizeof(float) * w.size());
         CK(cudaMalloc(&g->w_tc, tv.size() * sizeof(float)));

@@ -42,10 +42,10 @@ __device__ __forceinline__ void gnn_edges_tc(const Grp &g, const float *__restri
 #pragma unroll
         for (int q = 0; q < JB; q++) {
             const float4 w = *reinterpret_cast<const float4 *>(w1t + 4 * (j0 + q));      // {w_cn, w_Lx, w_Ly, w_Lz}
-            const float base = FB_ADD(FB_FMA(f3, w.w, FB_FMA(f2, w.z, FB_FMA(f1, w.y, 0.0f))), b1[j0 + q]);
-            float hs = 0.0f;
+            const float base = FB_FMA(f3, w.w, FB_FMA(f2, w.z, FB_FMA(f1, w.y, b1[j0 + q])));     // bias first
+            float hs = MATH::tanh(FB_FMA(hc[0], w.x, base));
 #pragma unroll
-            for (int k = 0; k < DV; k++) hs = FB_ADD(hs, MATH::tanh(FB_FMA(hc[k], w.x, base)));
+            for (int k = 1; k < DV; k++) hs = FB_ADD(hs, MATH::tanh(FB_FMA(hc[k], w.x, base)));
             const float h = tf32_hi(hs);
             hi[q] = __float_as_uint(h);
             lo[q] = __float_as_uint(hs - h);
@@ -70,25 +70,43 @@ __global__ void __launch_bounds__(256, 2) k_gnn_tc(const GnnArgs a, const float 
     const int n = a.X.n, t = threadIdx.x & 127;
     const int64_t total = a.num_frames * n, ntiles = (total + 127) / 128;
     const float dg = (float)DV;
-    for (int64_t tile = (int64_t)blockIdx.x * 2 + g.gid; tile < ntiles; tile += (int64_t)gridDim.x * 2) {
+    // inputs of a row: the three prior features and the signed logits of its 2 DV checks; the next tile's are fetched
+    // while the current tile is processed (the gathers are L2 latency)
+    auto fetch = [&](int64_t tile, float &q1, float &q2, float &q3, float (&qx)[DV], float (&qz)[DV], int64_t &qb, int &qv) -> bool {
         const int64_t it = tile * 128 + t;
-        const bool valid = it < total;
-        const int64_t fi = valid ? it / n : 0;
-        const int v = valid ? (int)(it - fi * n) : 0;
-        const int64_t b = a.frame_list ? a.frame_list[fi] : fi;
-        float f1 = 0.0f, f2 = 0.0f, f3 = 0.0f, hcx[DV], hcz[DV];
+        const bool ok = tile < ntiles && it < total;
+        q1 = q2 = q3 = 0.0f;
 #pragma unroll
-        for (int k = 0; k < DV; k++) { hcx[k] = 0.0f; hcz[k] = 0.0f; }
-        if (valid) {
-            f1 = a.h_vn(b, v, 0); f2 = a.h_vn(b, v, 1); f3 = a.h_vn(b, v, 2);
+        for (int k = 0; k < DV; k++) { qx[k] = 0.0f; qz[k] = 0.0f; }
+        qb = 0; qv = 0;
+        if (ok) {
+            const int64_t fi = it / n;
+            qv = (int)(it - fi * n);
+            qb = a.frame_list ? a.frame_list[fi] : fi;
+            q1 = a.h_vn(qb, qv, 0); q2 = a.h_vn(qb, qv, 1); q3 = a.h_vn(qb, qv, 2);
 #pragma unroll
             for (int k = 0; k < DV; k++) {
-                const int cx = a.X.vn_cn[v * DV + k], cz = a.Z.vn_cn[v * DV + k];
-                const float lx = a.logit_hx(cx, b), lz = a.logit_hz(cz, b);
-                hcx[k] = a.sx(cx, b) ? -lx : lx;
-                hcz[k] = a.sz(cz, b) ? -lz : lz;
+                const int cx = a.X.vn_cn[qv * DV + k], cz = a.Z.vn_cn[qv * DV + k];
+                const float lx = a.logit_hx(cx, qb), lz = a.logit_hz(cz, qb);
+                qx[k] = a.sx(cx, qb) ? -lx : lx;
+                qz[k] = a.sz(cz, qb) ? -lz : lz;
             }
         }
+        return ok;
+    };
+    float n1, n2, n3, nhx[DV], nhz[DV];
+    int64_t nb;
+    int nv;
+    bool nvalid = fetch((int64_t)blockIdx.x * 2 + g.gid, n1, n2, n3, nhx, nhz, nb, nv);
+    for (int64_t tile = (int64_t)blockIdx.x * 2 + g.gid; tile < ntiles; tile += (int64_t)gridDim.x * 2) {
+        const bool valid = nvalid;
+        const int64_t b = nb;
+        const int v = nv;
+        const float f1 = n1, f2 = n2, f3 = n3;
+        float hcx[DV], hcz[DV];
+#pragma unroll
+        for (int k = 0; k < DV; k++) { hcx[k] = nhx[k]; hcz[k] = nhz[k]; }
+        nvalid = fetch(tile + (int64_t)gridDim.x * 2, n1, n2, n3, nhx, nhz, nb, nv);
         float mm[2 * M];
 #pragma unroll 1
         for (int side = 0; side < 2; side++) {
@@ -103,7 +121,8 @@ __global__ void __launch_bounds__(256, 2) k_gnn_tc(const GnnArgs a, const float 
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
                     if (c0 + q < M) {
-                        const float r = (a.reduce == 0) ? FB_ADD(FB_DIV(d[q], dg), b2[c0 + q]) : FB_FMA(dg, b2[c0 + q], d[q]);
+                        // mean: the 1 / DV is folded into the W2 tiles (fbgnn_gnn.cu), so D already is the mean
+                        const float r = (a.reduce == 0) ? FB_ADD(d[q], b2[c0 + q]) : FB_FMA(dg, b2[c0 + q], d[q]);
                         if (side == 0) mm[c0 + q] = r;
                         else mm[M + c0 + q] = r;
                     }

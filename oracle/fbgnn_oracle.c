@@ -656,7 +656,13 @@ static void gnn_frame_tc(const orc_side_t *X, const orc_side_t *Z, const orc_gnn
     for (int sd = 0; sd < 2; sd++) {
         const float *W2 = sd ? G->W2z : G->W2x;
         w2h[sd] = (float *)malloc(sizeof(float) * 2 * (size_t)H * M); w2l[sd] = w2h[sd] + (size_t)H * M;
-        for (int i = 0; i < H * M; i++) { w2h[sd][i] = fb_tf32_hi(W2[i]); w2l[sd][i] = FB_SUB(W2[i], w2h[sd][i]); }
+        /* mean: the kernel folds 1 / degree into the W2 tiles as a float32 factor (regular degree, taken from variable 0) */
+        const orc_side_t *S0 = sd ? Z : X;
+        const float inv = (G->reduce == 0) ? FB_DIV(1.0f, (float)(S0->vn_ptr[1] - S0->vn_ptr[0])) : 1.0f;
+        for (int i = 0; i < H * M; i++) {
+            const float w = FB_MUL(W2[i], inv);
+            w2h[sd][i] = fb_tf32_hi(w); w2l[sd][i] = FB_SUB(w, w2h[sd][i]);
+        }
     }
     for (int i = 0; i < 2 * M * H; i++) { w3h[i] = fb_tf32_hi(G->W3[i]); w3l[i] = FB_SUB(G->W3[i], w3h[i]); }
     float *hi = (float *)malloc(sizeof(float) * 2 * (size_t)(H > 2 * M ? H : 2 * M)), *lo = hi + (H > 2 * M ? H : 2 * M);
@@ -671,20 +677,20 @@ static void gnn_frame_tc(const orc_side_t *X, const orc_side_t *Z, const orc_gnn
             const int e0 = S->vn_ptr[v], e1 = S->vn_ptr[v + 1];
             const float dg = (float)(e1 - e0);
             for (int j = 0; j < H; j++) {
-                const float base = FB_ADD(FB_FMA(f3, W1[3 * H + j], FB_FMA(f2, W1[2 * H + j], FB_FMA(f1, W1[H + j], 0.0f))),
-                                          b1 ? b1[j] : 0.0f);
+                const float base = FB_FMA(f3, W1[3 * H + j], FB_FMA(f2, W1[2 * H + j], FB_FMA(f1, W1[H + j], b1 ? b1[j] : 0.0f)));
                 float hs = 0.0f;
                 for (int e = e0; e < e1; e++) {
                     const int c = S->vn_cn[e];
                     const float hc = sy[c] ? -logit[c] : logit[c];
-                    hs = FB_ADD(hs, gnn_act(G->act, FB_FMA(hc, W1[j], base)));
+                    const float t = gnn_act(G->act, FB_FMA(hc, W1[j], base));
+                    hs = (e == e0) ? t : FB_ADD(hs, t);
                 }
                 hi[j] = fb_tf32_hi(hs); lo[j] = FB_SUB(hs, hi[j]);
             }
             for (int i = 0; i < M; i++) {
                 const float d = fb_umma_dot3(hi, lo, w2h[sd] + i, w2l[sd] + i, M, H);
                 const float bb = b2 ? b2[i] : 0.0f;
-                mm[sd * M + i] = (G->reduce == 0) ? FB_ADD(FB_DIV(d, dg), bb) : FB_FMA(dg, bb, d);
+                mm[sd * M + i] = (G->reduce == 0) ? FB_ADD(d, bb) : FB_FMA(dg, bb, d);
             }
         }
         for (int k = 0; k < 2 * M; k++) { hi[k] = fb_tf32_hi(mm[k]); lo[k] = FB_SUB(mm[k], hi[k]); }
