@@ -339,6 +339,21 @@ FB_HD float fb_sfu_logaddexpf(float a, float b) {
     return (d < -17.5f) ? FB_ADD(0.0f, mx) : f;
 }
 
+/* Variable-node update of the quaternary decoder in SFU arithmetic.  The outgoing messages of one side are
+ *     num - logaddexp(-(l1 - a_k), -(ly - a_k))  =  num - ((a_k - min(l1, ly)) + log(1 + exp(-|ly - l1|)))
+ * (l1 = lz for the x edges, lx for the z edges; a_k the incoming message of edge k): the correction term does not depend
+ * on the edge, so it is evaluated ONCE per side and variable instead of once per edge -- two exp / log pairs per variable
+ * node instead of 2 DV.  A correction below e^-17.5 is zero (as in logaddexp). */
+FB_HD float fb_sfu_vn_corr(float l1, float ly) {
+    float d = FB_SUB(ly, l1);
+    d = FB_I2F(FB_F2I(d) | (int32_t)0x80000000);              /* -|ly - l1| */
+    float f = fb_sfu_logaddexp_open(0.0f, FB_FMAX(d, -17.5f));
+    return (d < -17.5f) ? 0.0f : f;
+}
+FB_HD float fb_sfu_vn_msg(float num, float a, float u, float corr) {      /* u = min(l1, ly) */
+    return FB_SUB(num, FB_ADD(FB_SUB(a, u), corr));
+}
+
 /* phi on the open interval (8.5e-8, 16.635532), t = exp(-x):  softplus(x) = x + log(1 + t) and log(expm1(x)) =
  * x + log(1 - t), each rounded to float32 where the reference rounds them (at the magnitude of x), then subtracted --
  * the reference's phi with its float32 cancellation for large x reproduced, which the decoder's error rates depend

@@ -91,6 +91,13 @@ static __global__ void __launch_bounds__(512) k_bp4_cluster(const Bp4Args a, con
             const float lx = FB_ADD(Sz, px);
             const float lz = FB_ADD(Sx, pz);
             const float num_hx = MATH::softplus(-lx), num_hz = MATH::softplus(-lz);
+            if (MATH::kSharedVnCorr) {
+                float ux, cx, uz, cz;
+                vn_corr_pair<MATH, false>(lx, ly, lz, ux, cx, uz, cz);
+                for (int e = x0; e < x1; e++) mx[e] = vn_msg(num_hx, mx[e], ux, cx);
+                for (int e = z0; e < z1; e++) mz[e] = vn_msg(num_hz, mz[e], uz, cz);
+                continue;
+            }
             for (int e = x0; e < x1; e++) {
                 const float m = mx[e];
                 mx[e] = FB_SUB(num_hx, logaddexp_sat<MATH>(-FB_SUB(lz, m), -FB_SUB(ly, m)));

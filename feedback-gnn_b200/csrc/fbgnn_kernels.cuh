@@ -66,6 +66,7 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.96
 // error rates are reproduced in both (tests/test_gpu_sfu.py).
 struct MathExact {
     static constexpr bool kSaturationShortcuts = true;
+    static constexpr bool kSharedVnCorr = false;       // the reference's per-edge logaddexp
     static __device__ __forceinline__ float softplus(float x) { return fb_softplusf(x); }
     static __device__ __forceinline__ float logaddexp(float a, float b) { return fb_logaddexpf(a, b); }
     static __device__ __forceinline__ float phi4(float x) { return fb_phi4f(x); }
@@ -90,6 +91,7 @@ struct MathExact {
 
 struct MathSfu {
     static constexpr bool kSaturationShortcuts = true;
+    static constexpr bool kSharedVnCorr = true;        // fb_math.h fb_sfu_vn_corr: one correction term per side and variable
     static __device__ __forceinline__ float softplus(float x) { return fb_sfu_softplusf(x); }
     static __device__ __forceinline__ float logaddexp(float a, float b) { return fb_sfu_logaddexpf(a, b); }
     static __device__ __forceinline__ float phi4(float x) { return fb_sfu_phi4f(x); }
@@ -219,6 +221,21 @@ __device__ __forceinline__ void logaddexp_sat_group(const float a[G], const floa
         }
     }
 }
+
+// SFU arithmetic: the two edge-independent terms of a variable node's outgoing messages (fb_math.h fb_sfu_vn_corr), the x
+// edges' (from lz, ly) and the z edges' (from lx, ly), evaluated under one warp vote.
+template <typename MATH, bool FULL>
+__device__ __forceinline__ void vn_corr_pair(float lx, float ly, float lz, float &ux, float &cx, float &uz, float &cz) {
+    ux = fminf(lz, ly); uz = fminf(lx, ly);
+    const float dx = -fabsf(FB_SUB(ly, lz)), dz = -fabsf(FB_SUB(ly, lx));
+    const bool satx = dx < -17.5f, satz = dz < -17.5f;
+    cx = 0.0f; cz = 0.0f;
+    if (!FBGNN_VOTE || __any_sync(FULL ? 0xffffffffu : __activemask(), !(satx && satz))) {
+        const float fx = MATH::logaddexp_open(0.0f, dx), fz = MATH::logaddexp_open(0.0f, dz);
+        cx = satx ? 0.0f : fx; cz = satz ? 0.0f : fz;
+    }
+}
+__device__ __forceinline__ float vn_msg(float num, float a, float u, float corr) { return FB_SUB(num, FB_ADD(FB_SUB(a, u), corr)); }
 
 // ------------------------------------------------------------------ check nodes -------
 // Update one check node in place: msg[] holds v2c on entry, c2v on exit.  Two passes over
@@ -416,6 +433,16 @@ __device__ __forceinline__ void vn_update_regular(int v, float *mx, float *mz, f
     const float lx = FB_ADD(Sz, px);
     const float lz = FB_ADD(Sx, pz);
     const float num_hx = MATH::softplus(-lx), num_hz = MATH::softplus(-lz);
+    if (MATH::kSharedVnCorr) {
+        float ux, cx, uz, cz;
+        vn_corr_pair<MATH, FULL>(lx, ly, lz, ux, cx, uz, cz);
+#pragma unroll
+        for (int k = 0; k < DV; k++) {
+            mx[v * DV + k] = vn_msg(num_hx, ax[k], ux, cx);
+            mz[v * DV + k] = vn_msg(num_hz, az[k], uz, cz);
+        }
+        return;
+    }
     if (FULL && MATH::kSaturationShortcuts && FBGNN_LEAN) {
         // the 2 DV logaddexp sites under FBGNN_LAE_GROUP-sized votes (same values as one vote per site)
         constexpr int LG = (FBGNN_LAE_GROUP > 0 && (2 * DV) % FBGNN_LAE_GROUP == 0) ? FBGNN_LAE_GROUP : DV;
@@ -670,6 +697,13 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
             const float lx = FB_ADD(Sz, px);
             const float lz = FB_ADD(Sx, pz);
             const float num_hx = MATH::softplus(-lx), num_hz = MATH::softplus(-lz);
+            if (MATH::kSharedVnCorr) {
+                float ux, cx, uz, cz;
+                vn_corr_pair<MATH, false>(lx, ly, lz, ux, cx, uz, cz);
+                for (int e = x0; e < x1; e++) mx[e] = vn_msg(num_hx, mx[e], ux, cx);
+                for (int e = z0; e < z1; e++) mz[e] = vn_msg(num_hz, mz[e], uz, cz);
+                continue;
+            }
             for (int e = x0; e < x1; e++) {
                 const float m = mx[e];
                 mx[e] = FB_SUB(num_hx, logaddexp_sat<MATH>(-FB_SUB(lz, m), -FB_SUB(ly, m)));

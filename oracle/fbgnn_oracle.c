@@ -356,6 +356,12 @@ static void bp4_frame_il(const orc_side_t *X, const orc_side_t *Z, int cn_type, 
             float lz = FB_ADD(Sx, llrz[v]);
             float num_hx = fb_m_softplusf(-lx);
             float num_hz = fb_m_softplusf(-lz);
+            if (fb_math_mode) {         /* SFU arithmetic: one correction term per side (fb_math.h fb_sfu_vn_corr) */
+                const float ux = FB_FMIN(lz, ly), cx = fb_sfu_vn_corr(lz, ly), uz = FB_FMIN(lx, ly), cz = fb_sfu_vn_corr(lx, ly);
+                for (int e = X->vn_ptr[v]; e < X->vn_ptr[v + 1]; e++) mx[e] = fb_sfu_vn_msg(num_hx, mx[e], ux, cx);
+                for (int e = Z->vn_ptr[v]; e < Z->vn_ptr[v + 1]; e++) mz[e] = fb_sfu_vn_msg(num_hz, mz[e], uz, cz);
+                continue;
+            }
             for (int e = X->vn_ptr[v]; e < X->vn_ptr[v + 1]; e++) {
                 float a = FB_SUB(lz, mx[e]), b = FB_SUB(ly, mx[e]);
                 mx[e] = FB_SUB(num_hx, fb_m_logaddexpf(-a, -b));
