@@ -12,14 +12,15 @@ from ._ffi import device_count
 
 
 def evaluate_feedback_gnn(code, weights_file, nG, p, gpu_num=0, batch_size=5000, max_mc_iter=100000, num_iter1=64,
-                          num_iter2=16, factor1=1.0, factor2=1.0, num_target_block_errors=100):
+                          num_iter2=16, factor1=1.0, factor2=1.0, num_target_block_errors=100, gnn_gemm="fma"):
     """Run the Monte-Carlo evaluation and print the reference's progress table; returns the ``PlotBER`` object
-    (``ber_plot._snrs[1]`` / ``ber_plot._bers[1]`` hold the point and its block-error rate)."""
+    (``ber_plot._snrs[1]`` / ``ber_plot._bers[1]`` hold the point and its block-error rate).  ``gnn_gemm="tf32x3"`` (extension):
+    the feedback GNN's dense products on the tensor cores."""
     print('Number of GPUs available :', device_count())
     print('Only GPU number', gpu_num, 'used.')
     print(f"Running for {nG} rounds of GNN feedback at p={p} on GPU {gpu_num}.")
     G = Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, reduce_op="mean",
-                     activation="tanh", use_bias=True)
+                     activation="tanh", use_bias=True, gemm=gnn_gemm)
     load_weights(G, os.path.join(WEIGHTS_DIR, weights_file))
     decoder1 = QLDPCBPDecoder(code=code, num_iter=num_iter1, normalization_factor=factor1, cn_type="boxplus-phi",
                               trainable=False, stage_one=True)

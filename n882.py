@@ -16,6 +16,8 @@ ap.add_argument("-p", "--p", required=True, help="Physical error rate p to simul
 ap.add_argument("-id", "--gpu_id", default="0", help="GPU id")
 ap.add_argument("--batch_size", type=int, default=5000)
 ap.add_argument("--max_iter", type=int, default=100000)
+ap.add_argument("--gnn_gemm", choices=("fma", "tf32x3"), default="fma",
+                help="dense products of the feedback GNN: FP32 FMAs (default) or tcgen05 tensor cores; both oracle-exact")
 ap.add_argument("--math", choices=("exact", "sfu"), default=None,
                 help="arithmetic of the decoders (default: FBGNN_MATH, else exact); both are oracle-exact")
 args = ap.parse_args()
@@ -29,4 +31,4 @@ from fbgnn.evaluate import evaluate_feedback_gnn                                
 
 code = fbgnn.create_QC_GHP_codes(63, fbgnn.create_cyclic_permuting_matrix(7, [27, 54, 0]), [0, 1, 6])   # 18 <= d <= 24
 evaluate_feedback_gnn(code, "feedback_GNN_n882_k24_wt_4_60_iter_64_16_mixed.npy", nG=nG, p=float(args.p),
-                      gpu_num=int(args.gpu_id), batch_size=args.batch_size, max_mc_iter=args.max_iter)
+                      gpu_num=int(args.gpu_id), batch_size=args.batch_size, max_mc_iter=args.max_iter, gnn_gemm=args.gnn_gemm)

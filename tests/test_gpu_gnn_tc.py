@@ -90,8 +90,8 @@ def test_pipeline_with_tensor_core_gnn_tracks_the_bit_exact_pipeline(codes, orac
     assert abs(ka - kb) <= 4.0 * np.sqrt(max(ka, kb, 1)) + 5, (ka, kb)
 
 
-@pytest.mark.parametrize("arith", ["exact", "sfu"])
-def test_pipeline_with_tensor_core_gnn_bitexact(codes, oracle, weights, arith):
+@pytest.mark.parametrize("arith,skip", [("exact", False), ("sfu", False), ("sfu", True)])
+def test_pipeline_with_tensor_core_gnn_bitexact(codes, oracle, weights, arith, skip):
     """BP -> (GNN -> BP) x 2 with the tensor-core GNN against the oracle pipeline with the emulated tensor-core GNN:
     per-frame flags, residual errors and counters bit for bit."""
     import fbgnn as F
@@ -104,7 +104,8 @@ def test_pipeline_with_tensor_core_gnn_bitexact(codes, oracle, weights, arith):
         G.set_weights(w)
         d1 = F.QLDPCBPDecoder(code, num_iter=24, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
         d2 = F.QLDPCBPDecoder(code, num_iter=8, normalization_factor=0.9, cn_type="boxplus-phi", stage_one=True)
-        model = F.Sandwich_BP_GNN_Evaluation_Model(code, [d1, d2, d2], [G, G], num_layers=3, seed=7, first_frame=1000)
+        model = F.Sandwich_BP_GNN_Evaluation_Model(code, [d1, d2, d2], [G, G], num_layers=3, seed=7, first_frame=1000,
+                                                   skip_inactive=skip)
         B, p = 128, 0.12
         res = model.run(B, p, want_counters=True)
         with oracle.math(arith):
