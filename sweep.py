@@ -37,6 +37,8 @@ def main():
     ap.add_argument("--batch", type=int, default=200000)
     ap.add_argument("--seed", type=int, default=3)
     ap.add_argument("--target_block_errors", type=int, default=None)
+    ap.add_argument("--math", choices=("exact", "sfu"), default=None, help="arithmetic (default: FBGNN_MATH, else exact)")
+    ap.add_argument("--gnn_gemm", choices=("fma", "tf32x3"), default="fma", help="dense products of the feedback GNN")
     ap.add_argument("--full_work", action="store_true", help="run every round on every frame (as the reference does)")
     ap.add_argument("--checkpoint", default=None, help="counters.json: per-rank progress, resumed when present")
     ap.add_argument("--checkpoint_every", type=int, default=8, help="batches between checkpoint writes")
@@ -45,6 +47,8 @@ def main():
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     os.environ.setdefault("FBGNN_DEVICE", str(local_rank))
+    if args.math:
+        os.environ["FBGNN_MATH"] = args.math
     import fbgnn as F
     from fbgnn.distributed import init_from_env, run_sharded
     comm = init_from_env()
@@ -58,7 +62,7 @@ def main():
         wfile = "feedback_GNN_n1270_k28_wt_10_80_iter_64_16_mixed.npy"
     nG = args.num_G
     G = F.Feedback_GNN(code=code, num_msg_dims=20, num_hidden_units=40, num_mlp_layers=2, reduce_op="mean",
-                       activation="tanh", use_bias=True)
+                       activation="tanh", use_bias=True, gemm=args.gnn_gemm)
     F.load_weights(G, os.path.join(F.WEIGHTS_DIR, wfile))
     d1 = F.QLDPCBPDecoder(code=code, num_iter=64, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
     d2 = F.QLDPCBPDecoder(code=code, num_iter=16, normalization_factor=1.0, cn_type="boxplus-phi", stage_one=True)
@@ -114,7 +118,8 @@ def main():
         print(json.dumps({"code": code.name, "nG": nG, "p": args.p, "seed": args.seed, "gpus": world,
                           "frames": frames, "flagged": flagged, "block_errors": block, "stage0_failures": s0,
                           "bler": block / max(frames, 1), "seconds": dt, "frames_per_s": frames / dt,
-                          "skip_inactive": not args.full_work}), flush=True)
+                          "skip_inactive": not args.full_work, "math": os.environ.get("FBGNN_MATH", "exact"),
+                          "gnn_gemm": args.gnn_gemm}), flush=True)
     comm.close()
 
 
