@@ -17,4 +17,6 @@ run racecheck exact tests/test_gpu_parity.py -k "(bp4_layer or pipeline_bitexact
 run racecheck exact tests/test_gpu_sfu.py -k "bp4_layer_bitexact_sfu and (gb48 or c882)"
 run synccheck exact tests/test_gpu_parity.py -k "(bp4_layer or pipeline_bitexact or pipeline_packed) and (gb48 or c882)"
 run memcheck exact tests/test_gpu_parity.py -k "larger_than_shared_memory"
+run memcheck exact tests/test_gpu_gnn_tc.py -k "tolerance or bitexact and not headline"
+run racecheck exact tests/test_gpu_gnn_tc.py -k "tolerance and c882 and sum"
 cat $out
