@@ -59,7 +59,7 @@ __device__ __forceinline__ float u01(uint32_t r) { return (float)(r >> 8) * 5.96
 // ------------------------------------------------------------------ math policies -----
 // MathExact: exp / log as polynomials on the FP32 pipe (fb_math.h, the restatement of Eigen's CPU kernels TF runs).
 // MathSfu  : exp / log on the special-function unit (MUFU.EX2 / MUFU.LG2 with range reductions that confine the MUFU
-//            inputs to two finite sets; fb_math.h "SFU arithmetic").  2-3 ulp instead of 1, ~2.3x fewer instructions
+//            inputs to finite sets; fb_math.h "SFU arithmetic").  2-3 ulp instead of 1, ~2.3x fewer instructions
 //            per transcendental.
 // Both are bit-identical to the CPU oracle in the same arithmetic (the oracle evaluates the MUFU through tables
 // measured on the hardware), both carry the reference's saturation constants exactly, and the published logical

@@ -44,8 +44,8 @@ class Feedback_GNN:
                  ctx=None,
                  gemm="fma"):
         """``gemm`` (extension): "fma" (default; bit-exact against the oracle) or "tf32x3" -- the dense products of the
-        node update on the tcgen05 tensor cores (csrc/fbgnn_gnn_tc.cuh): float32 re-association accuracy, not
-        bit-identical; built for the shipped configuration (20 / 40, two layers, tanh, mean or sum, (3,.)-regular codes)."""
+        node update on the tcgen05 tensor cores (csrc/fbgnn_gnn_tc.cuh): within 5e-7 of the FMA form, bit-exact against
+        the oracle's emulation of the tensor-core arithmetic (csrc/fb_umma.h); built for the shipped configuration (20 / 40, two layers, tanh, mean or sum, (3,.)-regular codes)."""
         if gemm not in ("fma", "tf32x3"):
             raise ValueError("gemm must be 'fma' or 'tf32x3'")
         self._gemm = gemm

@@ -69,7 +69,7 @@ extern "C" {
 #define FBGNN_ACT_RELU   1
 #define FBGNN_ACT_LINEAR 2
 #define FBGNN_GEMM_FMA    0           /* GNN_BP4 matrix products in FP32 FMAs, bit-exact with the oracle (default) */
-#define FBGNN_GEMM_TF32X3 1           /* on tcgen05 tensor cores, 3-product TF32 split: float32 accuracy, not bit-exact */
+#define FBGNN_GEMM_TF32X3 1           /* on tcgen05 tensor cores, 3-product TF32 split: float32 accuracy; other bits than the FMA form */
 #define FBGNN_REDUCE_MEAN 0
 #define FBGNN_REDUCE_SUM  1
 #define FBGNN_REDUCE_MAX  2
@@ -246,7 +246,8 @@ int fbgnn_gnn_create_deep(fbgnn_ctx *ctx, int32_t H, int32_t M, int32_t num_mlp_
 int fbgnn_gnn_destroy(fbgnn_gnn *gnn);
 /* Select how the dense products of the node update (hidden sums x W2x / W2z, messages x W3) are evaluated (FBGNN_GEMM_*).
  * FBGNN_GEMM_TF32X3 runs them on the tcgen05 tensor cores with the three-product TF32 split (csrc/fbgnn_gnn_tc.cuh):
- * float32 re-association accuracy, NOT bit-identical to the default FMA form / the oracle.  Built for H = 40, M = 20,
+ * float32 re-association accuracy (5e-7 from the default FMA form); the oracle reproduces it bit for bit through the integer
+ * model of a tcgen05.mma step (csrc/fb_umma.h).  Built for H = 40, M = 20,
  * 2-layer MLPs, tanh, reduce_op mean / sum and (3, .)-regular codes; otherwise FBGNN_E_UNSUPPORTED. */
 int fbgnn_gnn_set_gemm(fbgnn_gnn *gnn, int32_t mode);
 /* Feedback_GNN.call.  h_vn float32 (b, v, k); logit_hx (row of hx, b), logit_hz (row of hz, b);

@@ -1,5 +1,5 @@
 """The SFU arithmetic (Context.set_math("sfu"); csrc/fb_math.h): exp / log on MUFU.EX2 / MUFU.LG2 with range
-reductions that confine the MUFU inputs to two finite sets, which the CPU oracle evaluates through tables measured on
+reductions that confine the MUFU inputs to finite sets, which the CPU oracle evaluates through tables measured on
 a B200 (tests/golden/sfu_b200_*.xz).  Same bar as the exact arithmetic: every float32 output BIT-EXACT against the
 oracle in the same arithmetic, and the reference's published logical error rates reproduced.  The parity cases are
 the ones of test_gpu_parity.py / test_gpu_baseline_configs.py, re-run with both sides switched to SFU arithmetic."""
