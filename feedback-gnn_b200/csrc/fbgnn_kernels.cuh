@@ -116,6 +116,12 @@ struct MathSfu {
 #ifndef FBGNN_SIGNBITS
 #define FBGNN_SIGNBITS 1           // quaternary check nodes: sign parity as an XOR of the message words (lab: 0 = comparisons)
 #endif
+#ifndef FBGNN_FPX_START
+#define FBGNN_FPX_START 6          // first iteration with a fixed-point test
+#endif
+#ifndef FBGNN_FPX_STRIDE
+#define FBGNN_FPX_STRIDE 3         // iterations between two fixed-point tests of the first stage (1 / 2 / 3 / 4: 414 / 434 / 441 / 436 k frames/s)
+#endif
 #ifndef FBGNN_SMEM_TABLES
 #define FBGNN_SMEM_TABLES 0        // lab: check-side edge tables in shared memory instead of global memory behind L1
 #endif
@@ -669,7 +675,8 @@ static __global__ void __launch_bounds__(512) k_bp4(const Bp4Args a) {
     int it_done = a.num_iter;
     for (int it = 0; it < a.num_iter; it++) {
         if (a.iter_logits.ptr) bp4_iter_logits<CONST_PRIOR, MATH>(a, mx, mz, pri, scr2, dec, b, it);
-        uint16_t *recp = (fp_exit && it >= 6) ? rec : nullptr;
+        // the fixed-point test runs every FBGNN_FPX_STRIDE-th iteration: a later test only delays the exit by no-op iterations
+        uint16_t *recp = (fp_exit && it >= FBGNN_FPX_START && (it % FBGNN_FPX_STRIDE) == 0) ? rec : nullptr;
         // variable nodes (decoding_q.py:227-275)
         if (DV > 0 && uniform) {
             // whole warps take the full-mask instantiation, the ragged last warp the activemask one
